@@ -1,0 +1,238 @@
+// Prime-field arithmetic for the B200 prover: Fp<P> over 32-bit limbs in Montgomery form.
+//
+// Replaces, on the hot path, ark-ff 0.3.0's Fp256/Fp384 ([u64;4]/[u64;6] Montgomery; reference
+// Cargo.lock:159-186).  The in-memory layout is identical to arkworks' (little-endian limbs of the
+// Montgomery representative, R = 2^256 / 2^384), so buffers cross the C-ABI without conversion.
+//
+// Two multipliers:
+//   * mont_mul_portable : CIOS on uint64_t, compiles for host and device (host side is unit-tested on CPU)
+//   * mont_mul_raw_{8,12}: generated inline PTX (tools/gen_mont_asm.py), even/odd split carry chains so
+//     every 32x32->64 product is one IMAD.WIDE feeding a carry chain; device only.
+// ZK_FF_PORTABLE forces the portable multiplier on device (used by the on-GPU self test to cross-check).
+#pragma once
+#include <cstdint>
+#include "params_gen.h"
+
+#if defined(__CUDACC__)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_DEV __device__ __forceinline__
+#else
+#define ZK_HD inline
+#define ZK_DEV inline
+#endif
+
+namespace zk {
+
+#if defined(__CUDACC__)
+#include "ff_mont_asm.inc"
+#endif
+
+template <int N>
+ZK_HD uint32_t add_n(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+}
+
+// r = a - b, returns borrow (0/1)
+template <int N>
+ZK_HD uint32_t sub_n(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    int64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        c += (int64_t)a[i] - (int64_t)b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;  // arithmetic shift: 0 or -1
+    }
+    return (uint32_t)(c & 1);
+}
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    static ZK_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = 0;
+        return r;
+    }
+    static ZK_HD Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = P::ONE(i);
+        return r;
+    }
+    static ZK_HD Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = P::R2(i);
+        return r;
+    }
+    ZK_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i];
+        return o == 0;
+    }
+    ZK_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    ZK_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+    // if v >= p: v -= p   (v < 2p on entry)
+    ZK_HD void reduce_once() {
+        uint32_t t[N], m[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+        uint32_t borrow = sub_n<N>(t, v, m);
+        if (!borrow) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = t[i];
+        }
+    }
+
+    friend ZK_HD Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        add_n<N>(r.v, a.v, b.v);  // p < 2^(32N-1) for all four fields: no carry out
+        r.reduce_once();
+        return r;
+    }
+    friend ZK_HD Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t borrow = sub_n<N>(r.v, a.v, b.v);
+        if (borrow) {
+            uint32_t m[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+            add_n<N>(r.v, r.v, m);
+        }
+        return r;
+    }
+    ZK_HD Fp neg() const {
+        if (is_zero()) return *this;
+        Fp r;
+        uint32_t m[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+        sub_n<N>(r.v, m, v);
+        return r;
+    }
+    ZK_HD Fp dbl() const { return *this + *this; }
+
+    static ZK_HD void mont_mul_portable(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+        // CIOS, one extra limb of headroom; result < 2p before the final subtract
+        uint32_t t[N + 2];
+#pragma unroll
+        for (int i = 0; i < N + 2; ++i) t[i] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            uint64_t c = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                c += (uint64_t)a[j] * b[i] + t[j];
+                t[j] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[N];
+            t[N] = (uint32_t)c;
+            t[N + 1] = (uint32_t)(c >> 32);
+            uint32_t m = t[0] * P::INV;
+            c = (uint64_t)m * P::MOD(0) + t[0];
+            c >>= 32;
+#pragma unroll
+            for (int j = 1; j < N; ++j) {
+                c += (uint64_t)m * P::MOD(j) + t[j];
+                t[j - 1] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[N];
+            t[N - 1] = (uint32_t)c;
+            t[N] = t[N + 1] + (uint32_t)(c >> 32);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = t[i];
+    }
+
+    friend ZK_HD Fp operator*(const Fp& a, const Fp& b) {
+        Fp r;
+#if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
+        uint32_t m[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+        if constexpr (N == 8)
+            mont_mul_raw_8(r.v, a.v, b.v, m, P::INV);
+        else
+            mont_mul_raw_12(r.v, a.v, b.v, m, P::INV);
+#else
+        mont_mul_portable(r.v, a.v, b.v);
+#endif
+        r.reduce_once();
+        return r;
+    }
+    ZK_HD Fp sqr() const { return *this * *this; }
+
+    // canonical integer -> Montgomery and back
+    ZK_HD Fp to_mont() const { return *this * r2(); }
+    ZK_HD Fp from_mont() const {
+        Fp o = zero();
+        o.v[0] = 1;
+        return *this * o;
+    }
+
+    // generic square-and-multiply with a multi-limb exponent (LE 32-bit limbs)
+    ZK_HD Fp pow(const uint32_t* e, int nlimbs) const {
+        Fp r = one();
+        bool started = false;
+        for (int i = nlimbs - 1; i >= 0; --i) {
+            for (int b = 31; b >= 0; --b) {
+                if (started) r = r.sqr();
+                if ((e[i] >> b) & 1) {
+                    r = started ? r * *this : *this;
+                    started = true;
+                }
+            }
+        }
+        return r;
+    }
+    // Fermat inverse (0 -> 0).  Only used off the inner loops (batch inversion amortises it).
+    ZK_HD Fp inverse() const {
+        uint32_t e[N], two[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            e[i] = P::MOD(i);
+            two[i] = (i == 0) ? 2u : 0u;
+        }
+        sub_n<N>(e, e, two);  // p - 2 (BLS12-377 moduli end in ...0001, so the borrow must ripple)
+        return pow(e, N);
+    }
+    static ZK_HD Fp from_u64(uint64_t x) {
+        Fp r = zero();
+        r.v[0] = (uint32_t)x;
+        r.v[1] = (uint32_t)(x >> 32);
+        return r.to_mont();
+    }
+    // lexicographic compare of canonical values: used for ark-serialize's y-sign flag
+    ZK_HD bool canonical_gt(const Fp& b) const {
+        for (int i = N - 1; i >= 0; --i) {
+            if (v[i] != b.v[i]) return v[i] > b.v[i];
+        }
+        return false;
+    }
+};
+
+using Fr377 = Fp<Fr377Params>;
+using Fq377 = Fp<Fq377Params>;
+using Fr381 = Fp<Fr381Params>;
+using Fq381 = Fp<Fq381Params>;
+
+}  // namespace zk
