@@ -1,0 +1,5 @@
+"""B200-native prover path for the AES-128 R1CS circuit of lambdaclass/AES_zero_knowledge_proof_circuit.
+
+Host-side mirror of the reference's public surface (src/lib.rs) over the C ABI in include/zkaes_b200.h.
+"""
+from ._native import CURVE_BLS12_377, CURVE_BLS12_381, Context, ZkAesError, lib  # noqa: F401

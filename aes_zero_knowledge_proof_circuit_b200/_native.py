@@ -1,0 +1,201 @@
+"""ctypes binding of libzkaes_b200.so (the C ABI in include/zkaes_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the symbol
+table, and if no CUDA device is usable `Context()` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkaes_b200.so")
+
+CURVE_BLS12_377 = 377
+CURVE_BLS12_381 = 381
+
+
+class ZkAesError(RuntimeError):
+    """Non-zero status from the C ABI; mirrors the reference's `anyhow::Result` error style (src/helpers/traits.rs:4-20)."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ZkAesError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the prover path)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp = c_void_p
+    sigs = {
+        "zkaes_ctx_create": (c_int, [c_int, POINTER(vp)]),
+        "zkaes_ctx_destroy": (None, [vp]),
+        "zkaes_last_error": (c_char_p, [vp]),
+        "zkaes_ctx_stream": (vp, [vp]),
+        "zkaes_ctx_launches": (c_uint64, [vp]),
+        "zkaes_ctx_sync": (c_int, [vp]),
+        "zkaes_ctx_set_msm_window": (c_int, [vp, c_int]),
+        "zkaes_dev_alloc": (c_int, [vp, c_size_t, POINTER(vp)]),
+        "zkaes_dev_free": (c_int, [vp, vp]),
+        "zkaes_dev_upload": (c_int, [vp, vp, vp, c_size_t]),
+        "zkaes_dev_download": (c_int, [vp, vp, vp, c_size_t]),
+        "zkaes_msm_g1": (c_int, [vp, c_int, vp, vp, c_size_t, vp]),
+        "zkaes_msm_g1_device": (c_int, [vp, c_int, vp, vp, c_size_t, c_int, vp]),
+        "zkaes_msm_g1_windows_bytes": (c_size_t, [vp, c_int, c_size_t]),
+        "zkaes_msm_g1_windows": (c_int, [vp, c_int, vp, vp, c_size_t, c_size_t, c_int, vp]),
+        "zkaes_msm_g1_fold": (c_int, [vp, c_int, vp, c_int, c_size_t, vp]),
+        "zkaes_ntt_fr": (c_int, [vp, c_int, vp, c_uint32, c_int, c_int]),
+        "zkaes_ntt_fr_device": (c_int, [vp, c_int, vp, c_uint32, c_int, c_int]),
+        "zkaes_srs_powers_device": (c_int, [vp, c_int, vp, c_size_t, vp]),
+        "zkaes_selftest_field": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp, vp, c_size_t]),
+        "zkaes_selftest_g1": (c_int, [vp, c_int, c_int, vp, vp, vp, c_size_t]),
+        "zkaes_selftest_host_field": (c_int, [c_int, c_int, c_int, vp, vp, vp, c_size_t]),
+        "zkaes_selftest_host_g1": (c_int, [c_int, c_int, vp, vp, vp, c_size_t]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    lib._zk_symbols = tuple(sigs)
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def _ptr(a):
+    """Pointer to a numpy array / bytes-like / int address."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return c_void_p(a.ctypes.data)
+    if isinstance(a, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(a)), c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    """One prover context bound to one CUDA device (one per process / rank)."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_void_p()
+        rc = lib().zkaes_ctx_create(device, ctypes.byref(self._h))
+        if rc != 0:
+            raise ZkAesError(f"zkaes_ctx_create(device={device}) failed with {rc}: a B200 (sm_100) GPU is required; there is no CPU path")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().zkaes_ctx_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib().zkaes_last_error(self._h)
+            raise ZkAesError(f"libzkaes_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    @property
+    def stream(self) -> int:
+        return lib().zkaes_ctx_stream(self._h) or 0
+
+    @property
+    def launches(self) -> int:
+        return lib().zkaes_ctx_launches(self._h)
+
+    def sync(self):
+        self._check(lib().zkaes_ctx_sync(self._h))
+
+    def set_msm_window(self, bits: int):
+        self._check(lib().zkaes_ctx_set_msm_window(self._h, bits))
+
+    # ---- device memory ----
+    def alloc(self, nbytes: int) -> int:
+        p = c_void_p()
+        self._check(lib().zkaes_dev_alloc(self._h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def free(self, dev: int):
+        self._check(lib().zkaes_dev_free(self._h, c_void_p(dev)))
+
+    def upload(self, dev: int, host: np.ndarray):
+        self._check(lib().zkaes_dev_upload(self._h, c_void_p(dev), _ptr(host), host.nbytes))
+
+    def download(self, host: np.ndarray, dev: int):
+        self._check(lib().zkaes_dev_download(self._h, _ptr(host), c_void_p(dev), host.nbytes))
+
+    # ---- MSM ----
+    def msm_g1(self, curve: int, bases: np.ndarray, scalars: np.ndarray) -> np.ndarray:
+        """bases: (n, 12) uint64 affine Montgomery; scalars: (n, 4) uint64 canonical. Returns (12,) uint64 affine."""
+        n = scalars.shape[0]
+        assert bases.shape == (n, 12) and scalars.shape == (n, 4)
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().zkaes_msm_g1(self._h, curve, _ptr(bases), _ptr(scalars), n, _ptr(out)))
+        return out
+
+    def msm_g1_device(self, curve: int, bases_dev, scalars_dev, n: int, scalars_montgomery: bool = False) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().zkaes_msm_g1_device(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n, int(scalars_montgomery), _ptr(out)))
+        return out
+
+    def msm_g1_windows_bytes(self, curve: int, n_total: int) -> int:
+        return lib().zkaes_msm_g1_windows_bytes(self._h, curve, n_total)
+
+    def msm_g1_windows(self, curve: int, bases_dev, scalars_dev, n_local: int, n_total: int, windows_dev, scalars_montgomery: bool = False):
+        self._check(lib().zkaes_msm_g1_windows(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n_local, n_total,
+                                               int(scalars_montgomery), _ptr(windows_dev)))
+
+    def msm_g1_fold(self, curve: int, gathered_dev, n_ranks: int, n_total: int) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().zkaes_msm_g1_fold(self._h, curve, _ptr(gathered_dev), n_ranks, n_total, _ptr(out)))
+        return out
+
+    # ---- NTT ----
+    def ntt_fr(self, curve: int, data: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+        """data: (n, 4) uint64 Montgomery, n a power of two; transformed copy is returned."""
+        n = data.shape[0]
+        log_n = n.bit_length() - 1
+        assert n == 1 << log_n and data.shape == (n, 4)
+        out = np.ascontiguousarray(data.copy())
+        self._check(lib().zkaes_ntt_fr(self._h, curve, _ptr(out), log_n, int(inverse), int(coset)))
+        return out
+
+    def ntt_fr_device(self, curve: int, data_dev, log_n: int, inverse: bool = False, coset: bool = False):
+        self._check(lib().zkaes_ntt_fr_device(self._h, curve, _ptr(data_dev), log_n, int(inverse), int(coset)))
+
+    # ---- SRS ----
+    def srs_powers_device(self, curve: int, seed32: bytes, n: int, out_dev):
+        assert len(seed32) == 32
+        buf = (c_uint8 * 32).from_buffer_copy(seed32)
+        self._check(lib().zkaes_srs_powers_device(self._h, curve, ctypes.cast(buf, c_void_p), n, _ptr(out_dev)))
+
+    # ---- self tests ----
+    def selftest_field(self, curve: int, field: int, op: int, variant: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        out = np.zeros_like(a)
+        self._check(lib().zkaes_selftest_field(self._h, curve, field, op, variant, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
+    def selftest_g1(self, curve: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        out = np.zeros_like(a)
+        self._check(lib().zkaes_selftest_g1(self._h, curve, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out

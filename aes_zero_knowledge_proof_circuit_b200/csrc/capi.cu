@@ -1,0 +1,274 @@
+// C ABI of libzkaes_b200 (declared in include/zkaes_b200.h).  Thin: argument checking, curve dispatch,
+// host<->device staging.  No CPU fallback anywhere: without a CUDA device zkaes_ctx_create fails.
+#include "../../include/zkaes_b200.h"
+#include "common.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "srs.cuh"
+
+namespace zk {
+template <class F> int selftest_field_asm(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template <class F> int selftest_field_portable(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template <class C> int selftest_g1(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+}
+using namespace zk;
+
+#define NEED_CTX(ctx) \
+    if (!(ctx)) return ZK_ERR_ARG
+#define CURVE_DISPATCH(ctx, curve_id, expr377, expr381)                    \
+    ((curve_id) == 377 ? (expr377) : (curve_id) == 381 ? (expr381) : fail((ctx), ZK_ERR_ARG, "unknown curve_id (use 377 or 381)"))
+
+// ---- MSM ---------------------------------------------------------------------------------------------------
+template <class C>
+static int msm_windows_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n_local, size_t n_total, int mont,
+                            void* windows_dev) {
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits);
+    return msm_window_sums<C>(ctx, bases, scalars, n_local, mont, p, windows_dev);
+}
+template <class C>
+static int msm_fold_impl(zkaes_ctx* ctx, const void* gathered, int n_ranks, size_t n_total, void* out96) {
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits);
+    std::vector<XYZZ<C>> h((size_t)n_ranks * p.W);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), gathered, sizeof(XYZZ<C>) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    Affine<C> r = msm_fold_windows_host<C>(h.data(), n_ranks, p);
+    memcpy(out96, &r, 96);
+    return ZK_OK;
+}
+template <class C>
+static int msm_device_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n, int mont, void* out96) {
+    MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits);
+    DevBuf win;
+    ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * p.W, ctx->stream));
+    ZK_TRY(msm_window_sums<C>(ctx, bases, scalars, n, mont, p, win.p));
+    return msm_fold_impl<C>(ctx, win.p, 1, n, out96);
+}
+template <class C>
+static int msm_host_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n, void* out96) {
+    DevBuf db, ds;
+    ZK_CUDA(ctx, db.alloc(96 * n, ctx->stream));
+    ZK_CUDA(ctx, ds.alloc(32 * n, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(db.p, bases, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ds.p, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_device_impl<C>(ctx, db.p, ds.p, n, 0, out96);
+}
+
+
+extern "C" {
+
+int zkaes_ctx_create(int device_id, zkaes_ctx** out) {
+    if (!out) return ZK_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) return ZK_ERR_CUDA;
+    if (cudaSetDevice(device_id) != cudaSuccess) return ZK_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return ZK_ERR_CUDA;
+    if (prop.major != 10) return ZK_ERR_UNSUPPORTED;  // sm_100a cubins only
+    zkaes_ctx* c = new zkaes_ctx();
+    c->device = device_id;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return ZK_ERR_CUDA;
+    }
+    // keep freed stream-ordered scratch cached in the pool instead of returning it to the driver every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return ZK_OK;
+}
+void zkaes_ctx_destroy(zkaes_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tables) cudaFree(kv.second);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* zkaes_last_error(const zkaes_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* zkaes_ctx_stream(zkaes_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int zkaes_ctx_sync(zkaes_ctx* ctx) {
+    NEED_CTX(ctx);
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits) {
+    NEED_CTX(ctx);
+    if (window_bits < 0 || window_bits > 22 || window_bits == 1 || window_bits == 2) return fail(ctx, ZK_ERR_ARG, "window bits must be 0 or 3..22");
+    ctx->msm_window_bits = window_bits;
+    return ZK_OK;
+}
+
+int zkaes_dev_alloc(zkaes_ctx* ctx, size_t bytes, void** out_dev) {
+    NEED_CTX(ctx);
+    if (!out_dev) return fail(ctx, ZK_ERR_ARG, "null out pointer");
+    ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ZK_CUDA(ctx, cudaMalloc(out_dev, bytes ? bytes : 1));
+    return ZK_OK;
+}
+int zkaes_dev_free(zkaes_ctx* ctx, void* dev) {
+    NEED_CTX(ctx);
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZK_CUDA(ctx, cudaFree(dev));
+    return ZK_OK;
+}
+int zkaes_dev_upload(zkaes_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    NEED_CTX(ctx);
+    ZK_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int zkaes_dev_download(zkaes_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    NEED_CTX(ctx);
+    ZK_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+// ---- MSM (entry points; templates are defined above the extern block) ----
+int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases, const void* scalars, size_t n, void* out96) {
+    NEED_CTX(ctx);
+    if ((n && (!bases || !scalars)) || !out96) return fail(ctx, ZK_ERR_ARG, "msm: null pointer");
+    if (n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "msm: n must be < 2^31");
+    return CURVE_DISPATCH(ctx, curve_id, msm_host_impl<G1_377Params>(ctx, bases, scalars, n, out96),
+                          msm_host_impl<G1_381Params>(ctx, bases, scalars, n, out96));
+}
+int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases, const void* scalars, size_t n, int mont, void* out96) {
+    NEED_CTX(ctx);
+    if ((n && (!bases || !scalars)) || !out96) return fail(ctx, ZK_ERR_ARG, "msm: null pointer");
+    if (n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "msm: n must be < 2^31");
+    return CURVE_DISPATCH(ctx, curve_id, msm_device_impl<G1_377Params>(ctx, bases, scalars, n, mont, out96),
+                          msm_device_impl<G1_381Params>(ctx, bases, scalars, n, mont, out96));
+}
+size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total) {
+    if (!ctx) return 0;
+    int bits = curve_id == 377 ? Fr377Params::BITS : Fr381Params::BITS;
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, bits, ctx->msm_window_bits);
+    return (size_t)p.W * 192;
+}
+int zkaes_msm_g1_windows(zkaes_ctx* ctx, int curve_id, const void* bases, const void* scalars, size_t n_local, size_t n_total,
+                         int mont, void* windows_dev) {
+    NEED_CTX(ctx);
+    if ((n_local && (!bases || !scalars)) || !windows_dev) return fail(ctx, ZK_ERR_ARG, "msm: null pointer");
+    if (n_local >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "msm: n must be < 2^31");
+    return CURVE_DISPATCH(ctx, curve_id, msm_windows_impl<G1_377Params>(ctx, bases, scalars, n_local, n_total, mont, windows_dev),
+                          msm_windows_impl<G1_381Params>(ctx, bases, scalars, n_local, n_total, mont, windows_dev));
+}
+int zkaes_msm_g1_fold(zkaes_ctx* ctx, int curve_id, const void* gathered, int n_ranks, size_t n_total, void* out96) {
+    NEED_CTX(ctx);
+    if (!gathered || !out96 || n_ranks < 1) return fail(ctx, ZK_ERR_ARG, "msm fold: bad arguments");
+    return CURVE_DISPATCH(ctx, curve_id, msm_fold_impl<G1_377Params>(ctx, gathered, n_ranks, n_total, out96),
+                          msm_fold_impl<G1_381Params>(ctx, gathered, n_ranks, n_total, out96));
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------------------
+int zkaes_ntt_fr_device(zkaes_ctx* ctx, int curve_id, void* data, uint32_t log_n, int inverse, int coset) {
+    NEED_CTX(ctx);
+    if (!data) return fail(ctx, ZK_ERR_ARG, "ntt: null pointer");
+    return CURVE_DISPATCH(ctx, curve_id, ntt_device<Fr377Params>(ctx, 377, data, (int)log_n, inverse, coset),
+                          ntt_device<Fr381Params>(ctx, 381, data, (int)log_n, inverse, coset));
+}
+int zkaes_ntt_fr(zkaes_ctx* ctx, int curve_id, void* data_host, uint32_t log_n, int inverse, int coset) {
+    NEED_CTX(ctx);
+    if (!data_host) return fail(ctx, ZK_ERR_ARG, "ntt: null pointer");
+    if (log_n > 30) return fail(ctx, ZK_ERR_ARG, "ntt: log_n out of range");
+    size_t bytes = (size_t)32 << log_n;
+    DevBuf d;
+    ZK_CUDA(ctx, d.alloc(bytes, ctx->stream));
+    ZK_CUDA(ctx, cudaMemcpyAsync(d.p, data_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZK_TRY(zkaes_ntt_fr_device(ctx, curve_id, d.p, log_n, inverse, coset));
+    ZK_CUDA(ctx, cudaMemcpyAsync(data_host, d.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+
+// ---- SRS ---------------------------------------------------------------------------------------------------
+int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[32], size_t n, void* out_bases_dev) {
+    NEED_CTX(ctx);
+    if (!seed32 || (n && !out_bases_dev)) return fail(ctx, ZK_ERR_ARG, "srs: null pointer");
+    return CURVE_DISPATCH(ctx, curve_id, srs_powers_device<G1_377Params>(ctx, seed32, n, out_bases_dev),
+                          srs_powers_device<G1_381Params>(ctx, seed32, n, out_bases_dev));
+}
+
+// ---- self tests ----------------------------------------------------------------------------------------------
+int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int variant, const void* a, const void* b, void* out,
+                         size_t count) {
+    NEED_CTX(ctx);
+    if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
+    if (curve_id != 377 && curve_id != 381) return fail(ctx, ZK_ERR_ARG, "unknown curve_id");
+    int sel = (curve_id == 381 ? 4 : 0) | (field ? 2 : 0) | (variant ? 1 : 0);
+    switch (sel) {
+        case 0: return selftest_field_asm<Fr377>(ctx, op, a, b, out, count);
+        case 1: return selftest_field_portable<Fr377>(ctx, op, a, b, out, count);
+        case 2: return selftest_field_asm<Fq377>(ctx, op, a, b, out, count);
+        case 3: return selftest_field_portable<Fq377>(ctx, op, a, b, out, count);
+        case 4: return selftest_field_asm<Fr381>(ctx, op, a, b, out, count);
+        case 5: return selftest_field_portable<Fr381>(ctx, op, a, b, out, count);
+        case 6: return selftest_field_asm<Fq381>(ctx, op, a, b, out, count);
+        default: return selftest_field_portable<Fq381>(ctx, op, a, b, out, count);
+    }
+}
+int zkaes_selftest_g1(zkaes_ctx* ctx, int curve_id, int op, const void* a, const void* b, void* out, size_t count) {
+    NEED_CTX(ctx);
+    if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
+    return CURVE_DISPATCH(ctx, curve_id, selftest_g1<G1_377Params>(ctx, op, a, b, out, count),
+                          selftest_g1<G1_381Params>(ctx, op, a, b, out, count));
+}
+
+// Host-side (CPU) execution of the same templates: validates the portable arithmetic that the host uses for
+// the final window fold / affine normalisation.  No context or GPU needed.
+int zkaes_selftest_host_field(int curve_id, int field, int op, const void* a, const void* b, void* out, size_t count) {
+    if (!a || !b || !out) return ZK_ERR_ARG;
+    auto run = [&](auto tag) {
+        using F = decltype(tag);
+        const F* x = reinterpret_cast<const F*>(a);
+        const F* y = reinterpret_cast<const F*>(b);
+        F* o = reinterpret_cast<F*>(out);
+        for (size_t i = 0; i < count; ++i) {
+            switch (op) {
+                case 0: o[i] = x[i] + y[i]; break;
+                case 1: o[i] = x[i] - y[i]; break;
+                case 2: o[i] = x[i] * y[i]; break;
+                case 3: o[i] = x[i].inverse(); break;
+                default: o[i] = x[i].neg(); break;
+            }
+        }
+        return ZK_OK;
+    };
+    if (curve_id == 377) return field ? run(Fq377()) : run(Fr377());
+    if (curve_id == 381) return field ? run(Fq381()) : run(Fr381());
+    return ZK_ERR_ARG;
+}
+int zkaes_selftest_host_g1(int curve_id, int op, const void* a, const void* b, void* out, size_t count) {
+    if (!a || !b || !out) return ZK_ERR_ARG;
+    auto run = [&](auto tag) {
+        using C = decltype(tag);
+        const Affine<C>* x = reinterpret_cast<const Affine<C>*>(a);
+        const Affine<C>* y = reinterpret_cast<const Affine<C>*>(b);
+        Affine<C>* o = reinterpret_cast<Affine<C>*>(out);
+        for (size_t i = 0; i < count; ++i) {
+            XYZZ<C> acc = XYZZ<C>::from_affine(x[i]);
+            if (op == 0) {
+                acc.madd(y[i]);
+            } else if (op == 1) {
+                XYZZ<C> q = XYZZ<C>::from_affine(y[i]).dbl();
+                q.add(XYZZ<C>::from_affine(y[i]).neg());
+                acc.add(q);
+            } else {
+                acc = acc.dbl();
+            }
+            o[i] = acc.to_affine();
+        }
+        return ZK_OK;
+    };
+    if (curve_id == 377) return run(G1_377Params());
+    if (curve_id == 381) return run(G1_381Params());
+    return ZK_ERR_ARG;
+}
+
+}  // extern "C"

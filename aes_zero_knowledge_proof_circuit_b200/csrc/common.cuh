@@ -1,0 +1,75 @@
+// Shared host-side plumbing for libzkaes_b200: context, error reporting, stream-ordered scratch memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#define ZK_OK 0
+#define ZK_ERR_ARG (-1)
+#define ZK_ERR_CUDA (-2)
+#define ZK_ERR_STATE (-3)
+#define ZK_ERR_UNSUPPORTED (-4)
+
+struct zkaes_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;  // kernels launched by this library on this context (bench.py's gpu_launches)
+    // cached device tables keyed by (curve, kind, log size)
+    std::map<uint64_t, void*> tables;
+    // tuning knobs (0 = automatic)
+    int msm_window_bits = 0;
+};
+
+namespace zk {
+
+inline int fail(zkaes_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define ZK_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return zk::fail((ctx), ZK_ERR_CUDA,                                                         \
+                            std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                                std::to_string(__LINE__) + ")");                                        \
+    } while (0)
+
+#define ZK_TRY(expr)             \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != ZK_OK) return rc__; \
+    } while (0)
+
+// stream-ordered temporary: freed (stream-ordered) when it leaves scope
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMallocAsync(&p, n, stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace zk

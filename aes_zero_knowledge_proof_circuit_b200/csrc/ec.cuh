@@ -11,6 +11,14 @@
 #pragma once
 #include "ff.cuh"
 
+// Point doubling / full addition are off the inner loop (bucket reduction, rare mixed-add corner cases):
+// keeping them out of line cuts both compile time and instruction-cache footprint of the hot kernels.
+#if defined(__CUDACC__)
+#define ZK_HD_COLD __host__ __device__ __noinline__
+#else
+#define ZK_HD_COLD __attribute__((noinline))
+#endif
+
 namespace zk {
 
 template <class C>
@@ -73,7 +81,7 @@ struct XYZZ {
     }
 
     // 2*P for an affine P (mdbl-2008-s-1, a = 0)
-    static ZK_HD XYZZ dbl_affine(const Affine<C>& p) {
+    static ZK_HD_COLD XYZZ dbl_affine(const Affine<C>& p) {
         if (p.is_inf() || p.y.is_zero()) return inf();
         XYZZ r;
         Fq u = p.y.dbl();
@@ -90,7 +98,7 @@ struct XYZZ {
     }
 
     // dbl-2008-s-1, a = 0
-    ZK_HD XYZZ dbl() const {
+    ZK_HD_COLD XYZZ dbl() const {
         if (is_inf() || y.is_zero()) return inf();
         XYZZ r;
         Fq u = y.dbl();
@@ -135,7 +143,7 @@ struct XYZZ {
     }
 
     // this += o, add-2008-s
-    ZK_HD void add(const XYZZ& o) {
+    ZK_HD_COLD void add(const XYZZ& o) {
         if (o.is_inf()) return;
         if (is_inf()) {
             *this = o;
@@ -171,7 +179,7 @@ struct XYZZ {
     }
 
     // one field inversion; host-side use (window combine, serialisation)
-    ZK_HD Affine<C> to_affine() const {
+    ZK_HD_COLD Affine<C> to_affine() const {
         if (is_inf()) return Affine<C>::inf();
         Affine<C> r;
         Fq izzz = zzz.inverse();          // 1/ZZZ

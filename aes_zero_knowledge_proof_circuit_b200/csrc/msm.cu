@@ -1,0 +1,303 @@
+// K3: G1 multi-scalar multiplication (bucket method) for sm_100a.
+//
+// Replaces ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul(&[G1Affine], &[BigInteger256]) -> G1Projective`
+// (reference Cargo.lock:118-120; reached from src/lib.rs:111 via ark-poly-commit's `commit`/`open`).
+// Same inputs (affine bases, canonical 256-bit scalars), same mathematical result; the schedule is GPU-first:
+//
+//   1. k_msm_count    : signed c-bit digits per scalar, histogram of (window, |digit|) keys      [HBM: 32 B/term]
+//   2. k_scan_*       : exclusive scan of the histogram -> bucket offsets
+//   3. k_msm_scatter  : counting-sort of point indices (sign in bit 31) by bucket key
+//   4. k_msm_accumulate: one thread per bucket, XYZZ += affine (8M+2S), 128-bit coalesced base loads [ALU bound]
+//   5. k_msm_reduce   : per-window sum_k k*B_k by segmented running sums + shared-memory tree
+//   6. k_msm_window_final: fold the per-block partials -> W window sums (XYZZ) on device
+// The c*W doublings of the final Horner fold and the affine normalisation are O(W*c) work and run on the
+// host (portable arithmetic in ff.cuh) because the result is consumed by the host-side transcript anyway.
+// Multi-GPU: each rank runs 1-6 on its point range; window sums are all-gathered and folded (see capi.cu).
+//
+// Large inputs are processed in chunks of at most MSM_CHUNK points so that the sort scratch stays bounded;
+// buckets persist across chunks.
+#include "msm.cuh"
+
+namespace zk {
+
+static constexpr size_t MSM_CHUNK = (size_t)1 << 24;
+
+__host__ MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c) {
+    MsmPlan p;
+    int lg = 0;
+    while (((size_t)2 << lg) <= n) ++lg;  // floor(log2 n), n >= 1
+    int c = forced_c > 0 ? forced_c : lg - 3;
+    if (forced_c <= 0) {
+        if (c > 16) c = 16;
+        if (c < 3) c = 3;
+    }
+    p.c = c;
+    p.W = (fr_bits + 1 + c - 1) / c;
+    p.nbw = 1u << (c - 1);
+    p.nb = p.nbw * (uint32_t)p.W;
+    return p;
+}
+
+__device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int c) {
+    int limb = pos >> 5, off = pos & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+template <class FrP>
+__device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, int mont, uint32_t* s) {
+    const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * i;
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if (mont) {
+        Fp<FrP> f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f.v[k] = s[k];
+        f = f.from_mont();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = f.v[k];
+    }
+}
+
+// pass 1 (scatter == nullptr): histogram.  pass 2: write sorted indices.
+template <class FrP>
+__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, uint32_t idx_base, int mont,
+                                                    MsmPlan p, uint32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    load_scalar<FrP>(scalars, i, mont, s);
+    const uint32_t half = 1u << (p.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < p.W; ++w) {
+        uint32_t d = scalar_bits(s, w * p.c, p.c) + carry;
+        uint32_t neg = 0;
+        if (d > half) {
+            d = (1u << p.c) - d;
+            carry = 1;
+            neg = 1;
+        } else {
+            carry = 0;
+        }
+        if (d) {
+            uint32_t key = (uint32_t)w * p.nbw + d - 1;
+            uint32_t pos = atomicAdd(&counts[key], 1u);
+            if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
+        }
+    }
+}
+
+// ---- exclusive scan over <= 2^22 counters: per-block scan, scan of block sums, add-back -----------------
+static constexpr int SCAN_BS = 1024;
+__global__ void __launch_bounds__(SCAN_BS) k_scan_blocks(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                         uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t sh[SCAN_BS];
+    uint32_t i = blockIdx.x * SCAN_BS + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 1; d < SCAN_BS; d <<= 1) {
+        uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i < n) out[i] = sh[threadIdx.x] - v;  // exclusive
+    if (threadIdx.x == SCAN_BS - 1 && block_sums) block_sums[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ block_offsets) {
+    uint32_t i = blockIdx.x * SCAN_BS + threadIdx.x;
+    if (i < n) out[i] += block_offsets[blockIdx.x];
+}
+
+static int exclusive_scan(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
+    cudaStream_t st = ctx->stream;
+    uint32_t nblk = cdiv(n, SCAN_BS);
+    if (nblk > SCAN_BS * SCAN_BS) return fail(ctx, ZK_ERR_UNSUPPORTED, "scan too large");
+    DevBuf sums, sums2, top;
+    ZK_CUDA(ctx, sums.alloc(sizeof(uint32_t) * nblk, st));
+    k_scan_blocks<<<nblk, SCAN_BS, 0, st>>>(in, out, n, sums.as<uint32_t>());
+    ctx->launches++;
+    if (nblk > 1) {
+        uint32_t nblk2 = cdiv(nblk, SCAN_BS);
+        ZK_CUDA(ctx, sums2.alloc(sizeof(uint32_t) * nblk, st));
+        ZK_CUDA(ctx, top.alloc(sizeof(uint32_t) * nblk2, st));
+        k_scan_blocks<<<nblk2, SCAN_BS, 0, st>>>(sums.as<uint32_t>(), sums2.as<uint32_t>(), nblk, top.as<uint32_t>());
+        ctx->launches++;
+        if (nblk2 > 1) {
+            DevBuf top2;
+            ZK_CUDA(ctx, top2.alloc(sizeof(uint32_t) * nblk2, st));
+            k_scan_blocks<<<1, SCAN_BS, 0, st>>>(top.as<uint32_t>(), top2.as<uint32_t>(), nblk2, nullptr);
+            k_scan_add<<<nblk2, SCAN_BS, 0, st>>>(sums2.as<uint32_t>(), nblk, top2.as<uint32_t>());
+            ctx->launches += 2;
+        }
+        k_scan_add<<<nblk, SCAN_BS, 0, st>>>(out, n, sums2.as<uint32_t>());
+        ctx->launches++;
+    }
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+
+// ---- bucket accumulation ---------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ Affine<C> load_affine(const Affine<C>* bases, uint32_t idx) {
+    Affine<C> r;
+    const uint4* p = reinterpret_cast<const uint4*>(bases + idx);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint4 v = __ldg(p + k);
+        r.x.v[4 * k] = v.x; r.x.v[4 * k + 1] = v.y; r.x.v[4 * k + 2] = v.z; r.x.v[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint4 v = __ldg(p + 3 + k);
+        r.y.v[4 * k] = v.x; r.y.v[4 * k + 1] = v.y; r.y.v[4 * k + 2] = v.z; r.y.v[4 * k + 3] = v.w;
+    }
+    return r;
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<C>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ counts, uint32_t nb,
+                                                        XYZZ<C>* __restrict__ buckets, int first) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t cnt = counts[b];
+    if (cnt == 0) {
+        if (first) buckets[b] = XYZZ<C>::inf();
+        return;
+    }
+    XYZZ<C> acc = first ? XYZZ<C>::inf() : buckets[b];
+    const uint32_t* lst = sorted + offsets[b];
+    for (uint32_t k = 0; k < cnt; ++k) {
+        uint32_t e = lst[k];
+        Affine<C> pt = load_affine<C>(bases, e & 0x7fffffffu);
+        if (e >> 31) pt.y = pt.y.neg();
+        acc.madd(pt);
+    }
+    buckets[b] = acc;
+}
+
+// ---- bucket reduction: S_w = sum_{j<nbw} (j+1) * B[w][j] ---------------------------------------------------
+template <class C>
+__device__ XYZZ<C> mul_small(const XYZZ<C>& p, uint32_t k) {
+    XYZZ<C> r = XYZZ<C>::inf();
+    for (int b = 31 - __clz(k | 1); b >= 0; --b) {
+        r = r.dbl();
+        if ((k >> b) & 1) r.add(p);
+    }
+    return k ? r : XYZZ<C>::inf();
+}
+
+static constexpr int RED_BS = 128;
+// grid: (blocks_per_window, W).  Each thread owns `seg` consecutive buckets of its window.
+template <class C>
+__global__ void __launch_bounds__(RED_BS) k_msm_reduce(const XYZZ<C>* __restrict__ buckets, uint32_t nbw, uint32_t seg,
+                                                       XYZZ<C>* __restrict__ partials) {
+    __shared__ XYZZ<C> sh[RED_BS];
+    uint32_t w = blockIdx.y;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // segment id within window
+    uint32_t lo = t * seg;
+    XYZZ<C> contrib = XYZZ<C>::inf();
+    if (lo < nbw) {
+        uint32_t hi = lo + seg < nbw ? lo + seg : nbw;
+        const XYZZ<C>* B = buckets + (size_t)w * nbw;
+        XYZZ<C> running = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+        for (uint32_t j = hi; j-- > lo;) {
+            running.add(B[j]);
+            acc.add(running);
+        }
+        // sum (j+1) B_j = acc + lo * running      (acc = sum (j-lo+1) B_j)
+        contrib = mul_small<C>(running, lo);
+        contrib.add(acc);
+    }
+    sh[threadIdx.x] = contrib;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            XYZZ<C> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + s]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[(size_t)w * gridDim.x + blockIdx.x] = sh[0];
+}
+
+template <class C>
+__global__ void k_msm_window_final(const XYZZ<C>* __restrict__ partials, uint32_t per_window, XYZZ<C>* __restrict__ out) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= gridDim.x * blockDim.x) return;
+    XYZZ<C> a = XYZZ<C>::inf();
+    for (uint32_t k = 0; k < per_window; ++k) a.add(partials[(size_t)w * per_window + k]);
+    out[w] = a;
+}
+
+template <class C>
+int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
+                    void* d_window_sums) {
+    using FrP = typename C::FrP;
+    cudaStream_t st = ctx->stream;
+    DevBuf counts, offsets, sorted, buckets, partials;
+    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * p.nb, st));
+    ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * p.nb, st));
+    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
+    size_t chunk_max = n < MSM_CHUNK ? n : MSM_CHUNK;
+    ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * chunk_max * p.W, st));
+    const auto* bases = reinterpret_cast<const Affine<C>*>(d_bases);
+    const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
+    if (n == 0) {
+        ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * p.W, st));
+        return ZK_OK;
+    }
+    for (size_t base = 0; base < n; base += MSM_CHUNK) {
+        size_t m = n - base < MSM_CHUNK ? n - base : MSM_CHUNK;
+        const uint32_t* sc = scalars + 8 * base;
+        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
+        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
+                                                        nullptr);
+        ctx->launches++;
+        ZK_TRY(exclusive_scan(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb));
+        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
+        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
+                                                        offsets.as<uint32_t>(), sorted.as<uint32_t>());
+        k_msm_accumulate<C><<<cdiv(p.nb, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
+                                                             counts.as<uint32_t>(), p.nb, buckets.as<XYZZ<C>>(), base == 0);
+        ctx->launches += 2;
+        ZK_CUDA(ctx, cudaGetLastError());
+    }
+    // reduction
+    uint32_t tpw = p.nbw < 2048 ? p.nbw : 2048;  // threads (segments) per window
+    uint32_t seg = p.nbw / tpw;
+    uint32_t bs = tpw < RED_BS ? tpw : RED_BS;
+    uint32_t bpw = tpw / bs;
+    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<C>) * (size_t)bpw * p.W, st));
+    k_msm_reduce<C><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<C>>(), p.nbw, seg, partials.as<XYZZ<C>>());
+    k_msm_window_final<C><<<1, p.W, 0, st>>>(partials.as<XYZZ<C>>(), bpw, reinterpret_cast<XYZZ<C>*>(d_window_sums));
+    ctx->launches += 2;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+
+// Horner fold of window sums (host): total = sum_w 2^(c*w) * S_w, then to affine.
+template <class C>
+Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& p) {
+    XYZZ<C> total = XYZZ<C>::inf();
+    for (int w = p.W - 1; w >= 0; --w) {
+        for (int k = 0; k < p.c; ++k) total = total.dbl();
+        for (int s = 0; s < n_sets; ++s) total.add(sums[(size_t)s * p.W + w]);
+    }
+    return total.to_affine();
+}
+
+template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
+template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
+template Affine<G1_377Params> msm_fold_windows_host<G1_377Params>(const XYZZ<G1_377Params>*, int, const MsmPlan&);
+template Affine<G1_381Params> msm_fold_windows_host<G1_381Params>(const XYZZ<G1_381Params>*, int, const MsmPlan&);
+
+}  // namespace zk

@@ -1,0 +1,26 @@
+// Declarations for the G1 MSM pipeline (msm.cu).
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace zk {
+
+struct MsmPlan {
+    int c;         // window bits (signed digits in [-2^(c-1), 2^(c-1)])
+    int W;         // number of windows = ceil((Fr bits + 1) / c)
+    uint32_t nbw;  // buckets per window = 2^(c-1)
+    uint32_t nb;   // total buckets
+};
+
+MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c);
+
+// Device-resident inputs -> W window sums (XYZZ, device).  scalars: n x 8 u32 (canonical, or Montgomery if scalars_mont).
+template <class C>
+int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
+                    void* d_window_sums);
+
+// Host Horner fold over n_sets sets of W window sums (one set per rank), returns the affine result.
+template <class C>
+Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& p);
+
+}  // namespace zk

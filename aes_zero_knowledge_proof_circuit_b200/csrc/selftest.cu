@@ -1,0 +1,48 @@
+// Self-test instantiation with the production (generated PTX) multiplier + G1 formula checks.
+#define ZK_SELFTEST_NAME(x) x##_asm
+#include "selftest_impl.cuh"
+namespace zk {
+template int selftest_field_asm<Fr377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_asm<Fq377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_asm<Fr381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_asm<Fq381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+
+template <class C>
+__global__ void k_selftest_g1(const Affine<C>* a, const Affine<C>* b, Affine<C>* out, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<C> acc = XYZZ<C>::from_affine(a[i]);
+    if (op == 0) {
+        acc.madd(b[i]);
+    } else if (op == 1) {
+        // make the second operand non-trivially projective: (b + a) - a computed as full adds
+        XYZZ<C> q = XYZZ<C>::from_affine(b[i]);
+        q = q.dbl();              // 2b
+        q.add(XYZZ<C>::from_affine(b[i]).neg());  // 2b - b = b, with ZZ != 1
+        acc.add(q);
+    } else {
+        acc = acc.dbl();
+    }
+    out[i] = acc.to_affine();
+}
+
+template <class C>
+int selftest_g1(zkaes_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+    cudaStream_t st = ctx->stream;
+    DevBuf da, db, dout;
+    size_t bytes = sizeof(Affine<C>) * count;
+    ZK_CUDA(ctx, da.alloc(bytes, st));
+    ZK_CUDA(ctx, db.alloc(bytes, st));
+    ZK_CUDA(ctx, dout.alloc(bytes, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    k_selftest_g1<C><<<cdiv(count, 64), 64, 0, st>>>(da.as<Affine<C>>(), db.as<Affine<C>>(), dout.as<Affine<C>>(), count, op);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    ZK_CUDA(ctx, cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    return ZK_OK;
+}
+template int selftest_g1<G1_377Params>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_g1<G1_381Params>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+}

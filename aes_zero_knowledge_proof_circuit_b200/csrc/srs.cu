@@ -1,0 +1,99 @@
+// Test-SRS generation on the device: out[i] = tau^i * G (fixed-base scalar multiplication).
+//
+// Stands in for ark-poly-commit 0.3.0 `KZG10::setup` (powers_of_g), which the reference reaches through
+// simpleworks::marlin::generate_universal_srs (src/lib.rs:141).  As in the reference (README.md:26) the
+// trapdoor is derived from a seed and is NOT secret: this is a test SRS.
+//
+// Fixed-base method: 8-bit windows, table T[w][d-1] = d * 2^(8w) * G (32 x 255 affine points, built on the
+// device), each output = sum_w T[w][byte_w(tau^i)] with 32 mixed additions, then normalised to affine.
+#include "srs.cuh"
+
+namespace zk {
+
+static constexpr int FB_WINDOWS = 32;
+static constexpr int FB_ROW = 255;
+
+template <class C>
+__global__ void k_fb_rows(Affine<C>* rows) {  // rows[w] = 2^(8w) * G
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= FB_WINDOWS) return;
+    XYZZ<C> p = XYZZ<C>::from_affine(Affine<C>::generator());
+    for (int i = 0; i < 8 * w; ++i) p = p.dbl();
+    rows[w] = p.to_affine();
+}
+template <class C>
+__global__ void k_fb_fill(const Affine<C>* __restrict__ rows, Affine<C>* __restrict__ table) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= FB_WINDOWS * FB_ROW) return;
+    int w = t / FB_ROW, d = t % FB_ROW + 1;
+    XYZZ<C> base = XYZZ<C>::from_affine(rows[w]);
+    XYZZ<C> r = XYZZ<C>::inf();
+    for (int b = 7; b >= 0; --b) {
+        r = r.dbl();
+        if ((d >> b) & 1) r.add(base);
+    }
+    table[t] = r.to_affine();
+}
+
+// scalar_i = lo[i & 1023] * hi[i >> 10]  (Montgomery), converted to canonical bytes
+template <class C>
+__global__ void __launch_bounds__(128) k_fb_mul(const Affine<C>* __restrict__ table, const Fp<typename C::FrP>* __restrict__ pw_lo,
+                                               const Fp<typename C::FrP>* __restrict__ pw_hi, size_t n, Affine<C>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using Fr = Fp<typename C::FrP>;
+    Fr s = pw_lo[i & 1023];
+    if (i >> 10) s = s * pw_hi[i >> 10];
+    s = s.from_mont();
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int w = 0; w < FB_WINDOWS; ++w) {
+        uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+        if (d) acc.madd(table[w * FB_ROW + d - 1]);
+    }
+    out[i] = acc.to_affine();
+}
+
+template <class F>
+__global__ void k_pow_table_srs(F* out, size_t count, F base, int shift) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long e = (unsigned long long)i << shift;
+    F r = F::one(), b = base;
+    while (e) {
+        if (e & 1) r = r * b;
+        b = b.sqr();
+        e >>= 1;
+    }
+    out[i] = r;
+}
+
+template <class C>
+int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out) {
+    using Fr = Fp<typename C::FrP>;
+    cudaStream_t st = ctx->stream;
+    // tau: seed as a 252-bit integer (always < r for both curves), lifted to Montgomery form
+    Fr tau = Fr::zero();
+    for (int i = 0; i < 32; ++i) tau.v[i >> 2] |= (uint32_t)seed32[i] << (8 * (i & 3));
+    tau.v[7] &= 0x0fffffffu;
+    tau = tau.to_mont();
+    DevBuf rows, table, lo, hi;
+    ZK_CUDA(ctx, rows.alloc(sizeof(Affine<C>) * FB_WINDOWS, st));
+    ZK_CUDA(ctx, table.alloc(sizeof(Affine<C>) * FB_WINDOWS * FB_ROW, st));
+    size_t hi_cnt = (n >> 10) + 1;
+    ZK_CUDA(ctx, lo.alloc(sizeof(Fr) * 1024, st));
+    ZK_CUDA(ctx, hi.alloc(sizeof(Fr) * hi_cnt, st));
+    k_fb_rows<C><<<1, FB_WINDOWS, 0, st>>>(rows.as<Affine<C>>());
+    k_fb_fill<C><<<cdiv(FB_WINDOWS * FB_ROW, 64), 64, 0, st>>>(rows.as<Affine<C>>(), table.as<Affine<C>>());
+    k_pow_table_srs<Fr><<<4, 256, 0, st>>>(lo.as<Fr>(), 1024, tau, 0);
+    k_pow_table_srs<Fr><<<cdiv(hi_cnt, 256), 256, 0, st>>>(hi.as<Fr>(), hi_cnt, tau, 10);
+    if (n) k_fb_mul<C><<<cdiv(n, 128), 128, 0, st>>>(table.as<Affine<C>>(), lo.as<Fr>(), hi.as<Fr>(), n,
+                                                     reinterpret_cast<Affine<C>*>(d_out));
+    ctx->launches += 5;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+
+template int srs_powers_device<G1_377Params>(zkaes_ctx*, const uint8_t*, size_t, void*);
+template int srs_powers_device<G1_381Params>(zkaes_ctx*, const uint8_t*, size_t, void*);
+
+}  // namespace zk

@@ -1,0 +1,110 @@
+/* libzkaes_b200 -- C ABI of the B200-native prover path for lambdaclass/AES_zero_knowledge_proof_circuit.
+ *
+ * This is the drop-in boundary.  The reference is a pure-Rust crate with no FFI of its own
+ * (`#![forbid(unsafe_code)]`, src/lib.rs:2); each entry point below names the reference interface it stands
+ * in for.  A Rust `-sys` shim binds exactly these symbols (INTEGRATION.md shows it); tests and bench.py bind
+ * them through ctypes.
+ *
+ * Conventions: return 0 on success, negative on error (never aborts, never throws across the boundary);
+ * zkaes_last_error(ctx) gives the message.  All pointers are caller-owned except opaque handles, which are
+ * released by their matching *_free / *_destroy.  "host" pointers may be pageable.  Calls are blocking
+ * (internally asynchronous on the context's stream).  A context is bound to ONE CUDA device and is not
+ * re-entrant; multi-GPU runs use one process (one context) per GPU and exchange the small MSM partials with
+ * an all-gather (torch.distributed / NCCL) between zkaes_msm_g1_windows and zkaes_msm_g1_fold.
+ *
+ * Wire formats (identical to arkworks 0.3.0 in-memory layouts, little-endian):
+ *   Fr element : 32 B, 4 x u64 limbs, Montgomery form (R = 2^256)             [ark-ff Fp256]
+ *   scalar     : 32 B, 4 x u64 limbs, canonical integer (`into_repr()`)       [ark-ff BigInteger256]
+ *   G1 affine  : 96 B, x || y, each 6 x u64 limbs Montgomery (R = 2^384); x = y = 0 encodes infinity
+ *                (ark-ec's separate `infinity: bool` is mapped by the shim)   [ark-ec GroupAffine]
+ * curve_id: 377 = BLS12-377 (the reference's proving curve, src/lib.rs:47), 381 = BLS12-381.
+ */
+#ifndef ZKAES_B200_H
+#define ZKAES_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKAES_OK 0
+#define ZKAES_ERR_ARG (-1)
+#define ZKAES_ERR_CUDA (-2)
+#define ZKAES_ERR_STATE (-3)
+#define ZKAES_ERR_UNSUPPORTED (-4)
+
+#define ZKAES_CURVE_BLS12_377 377
+#define ZKAES_CURVE_BLS12_381 381
+
+typedef struct zkaes_ctx zkaes_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+/* Creates a context on CUDA device `device_id` (fails loudly if there is no usable GPU: there is no CPU path). */
+int zkaes_ctx_create(int device_id, zkaes_ctx** out);
+void zkaes_ctx_destroy(zkaes_ctx* ctx);
+const char* zkaes_last_error(const zkaes_ctx* ctx);
+/* The CUDA stream the context launches on (a cudaStream_t), so callers can record events on it. */
+void* zkaes_ctx_stream(zkaes_ctx* ctx);
+/* Number of kernels this library has launched on the context so far (bench.py's gpu_launches). */
+uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx);
+/* Blocks until all work queued on the context's stream has finished. */
+int zkaes_ctx_sync(zkaes_ctx* ctx);
+/* Tuning: force the MSM window width (0 = automatic). */
+int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
+
+/* ---- device memory (thin wrappers so non-CUDA hosts can keep inputs resident in HBM) -------------------- */
+int zkaes_dev_alloc(zkaes_ctx* ctx, size_t bytes, void** out_dev);
+int zkaes_dev_free(zkaes_ctx* ctx, void* dev);
+int zkaes_dev_upload(zkaes_ctx* ctx, void* dev, const void* host, size_t bytes);
+int zkaes_dev_download(zkaes_ctx* ctx, void* host, const void* dev, size_t bytes);
+
+/* ---- S4 seam: MSM --------------------------------------------------------------------------------------
+ * Stands in for ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul(&[G1Affine], &[BigInteger256]) -> G1Projective`
+ * (reference Cargo.lock:118-120, reached from src/lib.rs:111).  Result is returned in affine form.
+ */
+/* host buffers in, 96-byte affine result out (host) */
+int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases_host, const void* scalars_host, size_t n, void* out_affine96);
+/* device-resident inputs; scalars_montgomery != 0 means the scalars are Fr elements in Montgomery form (as the
+ * prover's coefficient vectors are) and are converted on the fly */
+int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n,
+                        int scalars_montgomery, void* out_affine96_host);
+/* multi-GPU split: (1) per-rank window sums of this rank's point range, written to a device buffer of
+ * zkaes_msm_g1_windows_bytes(n_total) bytes; the window plan is derived from n_total so all ranks agree.
+ * (2) after an all-gather of those buffers, fold n_ranks sets into the affine result (host). */
+size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total);
+int zkaes_msm_g1_windows(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n_local,
+                         size_t n_total, int scalars_montgomery, void* windows_dev);
+int zkaes_msm_g1_fold(zkaes_ctx* ctx, int curve_id, const void* gathered_windows_dev, int n_ranks, size_t n_total,
+                      void* out_affine96_host);
+
+/* ---- S4 seam: NTT --------------------------------------------------------------------------------------
+ * Stands in for ark-poly 0.3.0 `Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place(&mut Vec<Fr>)`
+ * (reference Cargo.lock:234-236).  In place, natural order in and out, n = 2^log_n Montgomery Fr elements.
+ */
+int zkaes_ntt_fr(zkaes_ctx* ctx, int curve_id, void* data_host, uint32_t log_n, int inverse, int coset);
+int zkaes_ntt_fr_device(zkaes_ctx* ctx, int curve_id, void* data_dev, uint32_t log_n, int inverse, int coset);
+
+/* ---- synthetic G1 bases (test SRS) ---------------------------------------------------------------------
+ * Stands in for the KZG10 setup inside simpleworks::marlin::generate_universal_srs (src/lib.rs:141):
+ * out[i] = tau^i * G for i < n, tau derived from `seed32` -- an INSECURE test SRS exactly like the
+ * reference's (README.md:26).  Output stays on the device (n x 96 B). */
+int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[32], size_t n, void* out_bases_dev);
+
+/* ---- on-device self test of the field / curve arithmetic (used by tests/, not by the product path) -------
+ * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul.  variant: 0 = generated PTX multiplier, 1 = portable CIOS.
+ * a, b, out are host arrays of `count` elements (32 B or 48 B each). */
+int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int variant, const void* a_host, const void* b_host,
+                         void* out_host, size_t count);
+/* out[i] = a[i] + b[i] on G1 (affine 96 B each) through the device XYZZ formulas: op 0 = mixed add, 1 = full add,
+ * 2 = double a[i] */
+int zkaes_selftest_g1(zkaes_ctx* ctx, int curve_id, int op, const void* a_host, const void* b_host, void* out_host, size_t count);
+
+/* The same templates executed on the host CPU (the host uses them for the O(W*c) window fold and the affine
+ * normalisation).  No context / GPU needed.  field op: 0 add, 1 sub, 2 mul, 3 inverse(a), 4 neg(a). */
+int zkaes_selftest_host_field(int curve_id, int field, int op, const void* a, const void* b, void* out, size_t count);
+int zkaes_selftest_host_g1(int curve_id, int op, const void* a, const void* b, void* out, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKAES_B200_H */
