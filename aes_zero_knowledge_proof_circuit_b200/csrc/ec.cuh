@@ -115,14 +115,17 @@ struct XYZZ {
     }
 
     // this += P (affine), madd-2008-s.  Handles P = inf, this = inf, P = +-this.
+    // The ten field products are issued as one chain (Fp::mul_after) so that ptxas keeps a single set of carry
+    // predicates live; see ff.cuh.
     ZK_HD void madd(const Affine<C>& p) {
         if (p.is_inf()) return;
         if (is_inf()) {
             *this = from_affine(p);
             return;
         }
-        Fq u2 = p.x * zz;
-        Fq s2 = p.y * zzz;
+        uint32_t tok = 0;
+        Fq u2 = Fq::mul_after(p.x, zz, tok);
+        Fq s2 = Fq::mul_after(p.y, zzz, tok);
         Fq pp_ = u2 - x;
         Fq r_ = s2 - y;
         if (pp_.is_zero()) {
@@ -132,14 +135,16 @@ struct XYZZ {
                 *this = inf();
             return;
         }
-        Fq pp = pp_.sqr();
-        Fq ppp = pp_ * pp;
-        Fq q = x * pp;
-        Fq x3 = r_.sqr() - ppp - q.dbl();
-        y = r_ * (q - x3) - y * ppp;
+        Fq pp = Fq::mul_after(pp_, pp_, tok);
+        Fq ppp = Fq::mul_after(pp_, pp, tok);
+        Fq q = Fq::mul_after(x, pp, tok);
+        Fq r2 = Fq::mul_after(r_, r_, tok);
+        Fq x3 = r2 - ppp - q.dbl();
+        Fq yp = Fq::mul_after(y, ppp, tok);
+        zz = Fq::mul_after(zz, pp, tok);
+        zzz = Fq::mul_after(zzz, ppp, tok);
+        y = Fq::mul_after(r_, q - x3, tok) - yp;
         x = x3;
-        zz = zz * pp;
-        zzz = zzz * ppp;
     }
 
     // this += o, add-2008-s

@@ -25,6 +25,14 @@ namespace zk {
 
 #if defined(__CUDACC__)
 #include "ff_mont_asm.inc"
+// -p^-1 mod 2^32 per field, read from constant memory on the device ON PURPOSE: when ptxas sees the literal
+// (0xffffffff for three of the four fields) it rewrites m = -t0 and then splits every IMAD.WIDE of the reduction rows
+// into IMAD + IMAD.HI (half rate on sm_100): 11.7 -> ~5 clk/SM per Fq product (profiles/ubench_r1.txt).
+static __constant__ uint32_t zk_c_mont_inv[4] = {Fr377Params::INV, Fq377Params::INV, Fr381Params::INV, Fq381Params::INV};
+// An opaque zero (ptxas cannot fold a constant-bank load) used by Fp::mul_after to order two otherwise independent
+// products: without it ptxas interleaves their carry chains, runs out of the 7 predicate registers and spills carries
+// through P2R/LOP3/ISETP (about one extra ALU instruction per IMAD.WIDE in the madd inner loop).
+static __constant__ uint32_t zk_c_zero = 0;
 #endif
 
 template <int N>
@@ -169,10 +177,11 @@ struct Fp {
         uint32_t m[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+        const uint32_t inv = zk_c_mont_inv[P::FIELD_ID];
         if constexpr (N == 8)
-            mont_mul_raw_8(r.v, a.v, b.v, m, P::INV);
+            mont_mul_raw_8(r.v, a.v, b.v, m, inv, zk_c_zero);
         else
-            mont_mul_raw_12(r.v, a.v, b.v, m, P::INV);
+            mont_mul_raw_12(r.v, a.v, b.v, m, inv, zk_c_zero);
 #else
         mont_mul_portable(r.v, a.v, b.v);
 #endif
@@ -180,6 +189,21 @@ struct Fp {
         return r;
     }
     ZK_HD Fp sqr() const { return *this * *this; }
+
+    // a * b, scheduled after `tok` was produced (device: a false data dependency on b[0]; host: plain product).
+    // `tok` is then replaced by a limb of the result so that calls chain.
+    static ZK_HD Fp mul_after(const Fp& a, const Fp& b, uint32_t& tok) {
+#if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
+        Fp bb = b;
+        bb.v[0] |= tok & zk_c_zero;
+        Fp r = a * bb;
+        tok = r.v[N - 1];
+        return r;
+#else
+        (void)tok;
+        return a * b;
+#endif
+    }
 
     // canonical integer -> Montgomery and back
     ZK_HD Fp to_mont() const { return *this * r2(); }

@@ -160,25 +160,64 @@ __device__ __forceinline__ Affine<C> load_affine(const Affine<C>* bases, uint32_
     return r;
 }
 
+// Work items: bucket b is cut into ceil(count[b] / S) slices of at most S sorted entries, so a heavily loaded bucket
+// (the partially filled top window, repeated scalars, ...) is shared by several threads instead of serialising on one.
+__global__ void __launch_bounds__(256) k_msm_item_counts(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t S,
+                                                         uint32_t* __restrict__ items) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) items[b] = (counts[b] + S - 1) / S;
+}
+
+// one thread per work item: partial[item] = sum of its slice (XYZZ += affine, 8M+2S each)
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<C>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ counts, uint32_t nb,
-                                                        XYZZ<C>* __restrict__ buckets, int first) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t cnt = counts[b];
-    if (cnt == 0) {
-        if (first) buckets[b] = XYZZ<C>::inf();
-        return;
+                                                        const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ item_off, uint32_t nb, uint32_t n_items,
+                                                        uint32_t S, XYZZ<C>* __restrict__ partial) {
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    // bucket = last b with item_off[b] <= it   (item_off is the exclusive scan of items per bucket)
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(item_off + mid) <= it) lo = mid; else hi = mid;
     }
-    XYZZ<C> acc = first ? XYZZ<C>::inf() : buckets[b];
-    const uint32_t* lst = sorted + offsets[b];
+    const uint32_t b = lo;
+    const uint32_t k0 = (it - __ldg(item_off + b)) * S;
+    uint32_t cnt = __ldg(counts + b) - k0;
+    if (cnt > S) cnt = S;
+    const uint32_t* lst = sorted + __ldg(offsets + b) + k0;
+    XYZZ<C> acc = XYZZ<C>::inf();
     for (uint32_t k = 0; k < cnt; ++k) {
-        uint32_t e = lst[k];
+        uint32_t e = __ldg(lst + k);
         Affine<C> pt = load_affine<C>(bases, e & 0x7fffffffu);
         if (e >> 31) pt.y = pt.y.neg();
         acc.madd(pt);
+    }
+    partial[it] = acc;
+}
+
+// one thread per bucket: bucket (+)= its partials
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_merge(const XYZZ<C>* __restrict__ partial, const uint32_t* __restrict__ item_off,
+                                                   const uint32_t* __restrict__ items, uint32_t nb, XYZZ<C>* __restrict__ buckets,
+                                                   int first) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t m = items[b];
+    if (m == 0) {
+        if (first) buckets[b] = XYZZ<C>::inf();
+        return;
+    }
+    const XYZZ<C>* p = partial + item_off[b];
+    XYZZ<C> acc;
+    if (first) {
+        acc = p[0];
+        for (uint32_t k = 1; k < m; ++k) acc.add(p[k]);
+    } else {
+        acc = buckets[b];
+        for (uint32_t k = 0; k < m; ++k) acc.add(p[k]);
     }
     buckets[b] = acc;
 }
@@ -243,12 +282,21 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
                     void* d_window_sums) {
     using FrP = typename C::FrP;
     cudaStream_t st = ctx->stream;
-    DevBuf counts, offsets, sorted, buckets, partials;
+    DevBuf counts, offsets, sorted, buckets, partials, items, item_off, acc_partial;
     ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * p.nb, st));
     ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * p.nb, st));
+    ZK_CUDA(ctx, items.alloc(sizeof(uint32_t) * p.nb, st));
+    ZK_CUDA(ctx, item_off.alloc(sizeof(uint32_t) * p.nb, st));
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
     size_t chunk_max = n < MSM_CHUNK ? n : MSM_CHUNK;
     ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * chunk_max * p.W, st));
+    // slice length: twice the mean bucket load, clamped; #items <= nb + chunk*W/S
+    uint64_t mean = ((uint64_t)chunk_max * p.W + p.nb - 1) / p.nb;
+    uint32_t S = (uint32_t)(2 * mean);
+    if (S < 16) S = 16;
+    if (S > 1024) S = 1024;
+    size_t max_items = (size_t)p.nb + (chunk_max * p.W) / S + 1;
+    ZK_CUDA(ctx, acc_partial.alloc(sizeof(XYZZ<C>) * max_items, st));
     const auto* bases = reinterpret_cast<const Affine<C>*>(d_bases);
     const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
     if (n == 0) {
@@ -266,9 +314,25 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
         k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
                                                         offsets.as<uint32_t>(), sorted.as<uint32_t>());
-        k_msm_accumulate<C><<<cdiv(p.nb, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
-                                                             counts.as<uint32_t>(), p.nb, buckets.as<XYZZ<C>>(), base == 0);
+        k_msm_item_counts<<<cdiv(p.nb, 256), 256, 0, st>>>(counts.as<uint32_t>(), p.nb, S, items.as<uint32_t>());
         ctx->launches += 2;
+        ZK_TRY(exclusive_scan(ctx, items.as<uint32_t>(), item_off.as<uint32_t>(), p.nb));
+        // total item count = last offset + last count (tiny D2H; the launch below needs it for its grid)
+        uint32_t tail[2];
+        ZK_CUDA(ctx, cudaMemcpyAsync(&tail[0], item_off.as<uint32_t>() + (p.nb - 1), 4, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(&tail[1], items.as<uint32_t>() + (p.nb - 1), 4, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        uint32_t n_items = tail[0] + tail[1];
+        if (n_items > max_items) return fail(ctx, ZK_ERR_STATE, "msm: work-item count exceeds its bound");
+        if (n_items) {
+            k_msm_accumulate<C><<<cdiv(n_items, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
+                                                                   counts.as<uint32_t>(), item_off.as<uint32_t>(), p.nb, n_items, S,
+                                                                   acc_partial.as<XYZZ<C>>());
+            ctx->launches++;
+        }
+        k_msm_merge<C><<<cdiv(p.nb, 128), 128, 0, st>>>(acc_partial.as<XYZZ<C>>(), item_off.as<uint32_t>(), items.as<uint32_t>(), p.nb,
+                                                       buckets.as<XYZZ<C>>(), base == 0);
+        ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
     }
     // reduction

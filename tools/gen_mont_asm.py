@@ -24,6 +24,9 @@ class Sim:
         for ins in row:
             op, d, x, y, z = ins
             g = lambda t: env[t] if isinstance(t, str) else t
+            if op == "taint":   # d = d | (x & zero): a scheduling fence, value-preserving because zero == 0
+                env[d] = g(d) | (g(x) & g(y))
+                continue
             if op in ("mul.lo", "mul.hi"):
                 p = g(x) * g(y)
                 env[d] = (p & MASK) if op == "mul.lo" else (p >> 32)
@@ -65,6 +68,10 @@ def rows_for(n):
                 r.append(("mul.hi", f"{O}{j}", f"a{j}", bi, None))
             rows.append(r)
         else:
+            # fence: make this row's head depend on the previous row's last carry-out (E[n-1] is where both of the
+            # previous row's chains ended).  Without it ptxas hoists the heads of all n rows (they only depend on
+            # each other), keeps >7 carry chains live at once and spills carries through P2R/LOP3/ISETP.
+            rows.append([("taint", f"{E}0", f"{E}{n-1}", "zero", None)])
             # S1: fold O[1] (position 0 after the shift) into E[0]; O <- (O >> 2 limbs) + a_odd*bi
             r = [("add.cc", f"{E}0", f"{E}0", f"{O}1", None)]
             for j in range(1, n, 2):
@@ -108,7 +115,7 @@ def rows_for(n):
 
 def simulate(n, a, b, p):
     inv = (-pow(p, -1, 1 << 32)) & MASK
-    env = {"inv": inv}
+    env = {"inv": inv, "zero": 0}
     for k in range(n):
         env[f"a{k}"] = (a >> (32 * k)) & MASK
         env[f"b{k}"] = (b >> (32 * k)) & MASK
@@ -142,7 +149,7 @@ def emit(n, name):
     out.append(f"// GENERATED by tools/gen_mont_asm.py -- do not edit. n={n} 32-bit limbs.")
     out.append(f"// r = a*b/2^{32*n} mod p, result in [0, 2p); caller does the final conditional subtract.")
     out.append(f"__device__ __forceinline__ void {name}(uint32_t* __restrict__ r, const uint32_t* __restrict__ a,")
-    out.append(f"        const uint32_t* __restrict__ b, const uint32_t* __restrict__ p, uint32_t inv) {{")
+    out.append(f"        const uint32_t* __restrict__ b, const uint32_t* __restrict__ p, uint32_t inv, uint32_t zero) {{")
     out.append(f"    uint32_t X[{n}], Y[{n}], m;")
     def ref(t, ops, kinds):
         # map symbol -> %k placeholder, registering operand
@@ -158,7 +165,7 @@ def emit(n, name):
         for op, d, x, y, z in row:
             if d not in written:
                 written.append(d)
-            for t in (x, y, z):
+            for t in ((d, x, y) if op == "taint" else (x, y, z)):
                 if isinstance(t, str) and t not in read:
                     read.append(t)
         # an operand that is written is "+r" if it is read before/at all, else "=r"
@@ -169,12 +176,13 @@ def emit(n, name):
         def cexpr(t):
             if t == "m": return "m"
             if t == "inv": return "inv"
+            if t == "zero": return "zero"
             arr, idx = t[0], int(t[1:])
             return {"X": "X", "Y": "Y", "a": "a", "b": "b", "p": "p", "r": "r"}[arr] + f"[{idx}]"
         # first-use analysis for written symbols
         first_is_write = {}
         for op, d, x, y, z in row:
-            for t in (x, y, z):
+            for t in ((d, x, y) if op == "taint" else (x, y, z)):
                 if isinstance(t, str) and t not in first_is_write:
                     first_is_write[t] = False
             if d not in first_is_write:
@@ -190,7 +198,9 @@ def emit(n, name):
             return f"%{idx[t]}" if isinstance(t, str) else str(t)
         lines = []
         for op, d, x, y, z in row:
-            if op in ("mul.lo", "mul.hi"):
+            if op == "taint":
+                lines.append(f"lop3.b32 {o(d)}, {o(d)}, {o(x)}, {o(y)}, 0xF8;")
+            elif op in ("mul.lo", "mul.hi"):
                 lines.append(f"{op}.u32 {o(d)}, {o(x)}, {o(y)};")
             elif op.startswith("mad"):
                 lines.append(f"{op}.u32 {o(d)}, {o(x)}, {o(y)}, {o(z)};")
