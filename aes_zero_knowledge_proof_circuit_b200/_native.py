@@ -54,6 +54,10 @@ def _load():
         "zkaes_selftest_g1": (c_int, [vp, c_int, c_int, vp, vp, vp, c_size_t]),
         "zkaes_selftest_host_field": (c_int, [c_int, c_int, c_int, vp, vp, vp, c_size_t]),
         "zkaes_selftest_host_g1": (c_int, [c_int, c_int, vp, vp, vp, c_size_t]),
+        "zkaes_circuit_build": (c_int, [c_size_t, POINTER(vp)]),
+        "zkaes_circuit_free": (None, [vp]),
+        "zkaes_circuit_info": (c_int, [vp, vp]),
+        "zkaes_circuit_matrix": (c_int, [vp, c_int, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
@@ -199,3 +203,41 @@ class Context:
         out = np.zeros_like(a)
         self._check(lib().zkaes_selftest_g1(self._h, curve, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+
+CIRCUIT_INFO_FIELDS = ("msg_len", "n_blocks", "num_instance", "num_instance_used", "num_witness", "num_witness_real", "num_constraints",
+                       "nnz_a", "nnz_b", "nnz_c", "wit_key0", "wit_fixed0", "wit_block0", "wit_block_stride", "fixed_instrs", "block_instrs",
+                       "fixed_levels", "block_levels")
+
+
+class Circuit:
+    """Shape of the AES-128-ECB R1CS for a message length (host only; no GPU needed)."""
+
+    def __init__(self, msg_len: int):
+        self._h = c_void_p()
+        rc = lib().zkaes_circuit_build(msg_len, ctypes.byref(self._h))
+        if rc != 0:
+            raise ZkAesError(f"zkaes_circuit_build({msg_len}) failed with {rc}: message length must be a non-zero multiple of 16")
+        info = np.zeros(len(CIRCUIT_INFO_FIELDS), dtype=np.uint64)
+        assert lib().zkaes_circuit_info(self._h, _ptr(info)) == 0
+        self.info = {k: int(v) for k, v in zip(CIRCUIT_INFO_FIELDS, info)}
+
+    def matrix(self, which: int):
+        """-> (row_ptr, col, coeff) CSR arrays of A (0), B (1) or C (2)"""
+        nnz = self.info[("nnz_a", "nnz_b", "nnz_c")[which]]
+        row_ptr = np.zeros(self.info["num_constraints"] + 1, dtype=np.uint32)
+        col = np.zeros(nnz, dtype=np.uint32)
+        coeff = np.zeros(nnz, dtype=np.int8)
+        assert lib().zkaes_circuit_matrix(self._h, which, _ptr(row_ptr), _ptr(col), _ptr(coeff)) == 0
+        return row_ptr, col, coeff
+
+    def close(self):
+        if self._h:
+            lib().zkaes_circuit_free(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -5,6 +5,9 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "srs.cuh"
+#include "circuit.h"
+#include <cstring>
+#include <stdexcept>
 
 namespace zk {
 template <class F> int selftest_field_asm(zkaes_ctx*, int, const void*, const void*, void*, size_t);
@@ -269,6 +272,43 @@ int zkaes_selftest_host_g1(int curve_id, int op, const void* a, const void* b, v
     if (curve_id == 377) return run(G1_377Params());
     if (curve_id == 381) return run(G1_381Params());
     return ZK_ERR_ARG;
+}
+
+// ---- circuit shape (host only) -----------------------------------------------------------------------------------
+struct zkaes_circuit {
+    zk::AesCircuit c;
+};
+int zkaes_circuit_build(size_t msg_len, zkaes_circuit** out) {
+    if (!out) return ZK_ERR_ARG;
+    *out = nullptr;
+    zkaes_circuit* h = new zkaes_circuit();
+    try {
+        zk::build_aes_circuit(msg_len, h->c);
+    } catch (const std::exception&) {
+        delete h;
+        return ZK_ERR_ARG;
+    }
+    *out = h;
+    return ZK_OK;
+}
+void zkaes_circuit_free(zkaes_circuit* c) { delete c; }
+int zkaes_circuit_info(const zkaes_circuit* h, uint64_t info[ZKAES_CIRCUIT_INFO_WORDS]) {
+    if (!h || !info) return ZK_ERR_ARG;
+    const zk::AesCircuit& c = h->c;
+    uint64_t v[ZKAES_CIRCUIT_INFO_WORDS] = {c.msg_len, c.n_blocks, c.num_instance, c.num_instance_used, c.num_witness, c.num_witness_real,
+                                            c.num_constraints, c.a.nnz(), c.b.nnz(), c.c.nnz(), c.wit_key0, c.wit_fixed0, c.wit_block0,
+                                            c.wit_block_stride, c.fixed_prog.instrs.size(), c.block_prog.instrs.size(),
+                                            c.fixed_prog.level_start.size() - 1, c.block_prog.level_start.size() - 1};
+    memcpy(info, v, sizeof(v));
+    return ZK_OK;
+}
+int zkaes_circuit_matrix(const zkaes_circuit* h, int which, uint32_t* row_ptr, uint32_t* col, int8_t* coeff) {
+    if (!h || which < 0 || which > 2 || !row_ptr || !col || !coeff) return ZK_ERR_ARG;
+    const zk::CsrMatrix& m = which == 0 ? h->c.a : which == 1 ? h->c.b : h->c.c;
+    memcpy(row_ptr, m.row_ptr.data(), m.row_ptr.size() * sizeof(uint32_t));
+    memcpy(col, m.col.data(), m.col.size() * sizeof(uint32_t));
+    memcpy(coeff, m.coeff.data(), m.coeff.size());
+    return ZK_OK;
 }
 
 }  // extern "C"

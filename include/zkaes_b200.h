@@ -104,6 +104,22 @@ int zkaes_selftest_g1(zkaes_ctx* ctx, int curve_id, int op, const void* a_host, 
 int zkaes_selftest_host_field(int curve_id, int field, int op, const void* a, const void* b, void* out, size_t count);
 int zkaes_selftest_host_g1(int curve_id, int op, const void* a, const void* b, void* out, size_t count);
 
+/* ---- circuit shape (host only, no GPU needed) ------------------------------------------------------------------
+ * The R1CS that the reference obtains by running `encrypt_and_generate_constraints` (src/lib.rs:176-293) against
+ * arkworks' constraint system, after Marlin's padding.  Used by zkaes_synthesize_keys; exposed so that tests can
+ * compare the shape with the oracle's gadget model (variable order, rows of A/B/C, witness program).
+ * info[]: 0 msg_len, 1 n_blocks, 2 num_instance (padded), 3 num_instance_used, 4 num_witness, 5 num_witness_real,
+ *         6 num_constraints, 7 nnz(A), 8 nnz(B), 9 nnz(C), 10 first key-bit witness, 11 first key-schedule witness,
+ *         12 first block witness, 13 witnesses per block, 14 fixed-program instrs, 15 block-program instrs,
+ *         16 fixed-program levels, 17 block-program levels */
+typedef struct zkaes_circuit zkaes_circuit;
+#define ZKAES_CIRCUIT_INFO_WORDS 18
+int zkaes_circuit_build(size_t msg_len, zkaes_circuit** out);
+void zkaes_circuit_free(zkaes_circuit* c);
+int zkaes_circuit_info(const zkaes_circuit* c, uint64_t info[ZKAES_CIRCUIT_INFO_WORDS]);
+/* which: 0 = A, 1 = B, 2 = C.  row_ptr: num_constraints + 1 entries; col / coeff: nnz entries. */
+int zkaes_circuit_matrix(const zkaes_circuit* c, int which, uint32_t* row_ptr, uint32_t* col, int8_t* coeff);
+
 #ifdef __cplusplus
 }
 #endif

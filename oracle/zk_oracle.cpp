@@ -849,6 +849,173 @@ int orc_dft_naive(int curve, const u64* in, u64* out, int log_n, int coset) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vector primitives over Fr used by the Marlin oracle (oracle/marlin_oracle.py): the polynomial
+// arithmetic that ark-poly 0.3.0 DensePolynomial / Evaluations and ark-ff batch_inversion provide
+// to ark-marlin's prover rounds.  Plain loops; parallel where it is embarrassingly so.
+// ---------------------------------------------------------------------------------------------
+// op 0 add, 1 sub, 2 mul; b is broadcast when nb == 1
+int orc_fr_vec(int curve, int op, const u64* a, size_t na, const u64* b, size_t nb, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp || (nb != na && nb != 1)) return -1;
+    const Curve& C = *Cp;
+    const Fr* A = (const Fr*)a;
+    const Fr* B = (const Fr*)b;
+    Fr* O = (Fr*)out;
+    parallel_for((long long)na, 4096, [&](long long i) {
+        const Fr& y = B[nb == 1 ? 0 : i];
+        O[i] = op == 0 ? f_add<4>(RF, A[i], y) : op == 1 ? f_sub<4>(RF, A[i], y) : f_mul<4>(RF, A[i], y);
+    });
+    return 0;
+}
+// ark-ff batch_inversion semantics: zeros are left as zeros
+int orc_fr_batch_inv(int curve, const u64* a, u64* out, size_t n) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    const Fr* A = (const Fr*)a;
+    Fr* O = (Fr*)out;
+    const size_t CH = 1 << 14;
+    parallel_for((long long)((n + CH - 1) / CH), 1, [&](long long c) {
+        size_t lo = (size_t)c * CH, hi = std::min(n, lo + CH);
+        std::vector<Fr> pre(hi - lo);
+        Fr acc = f_one<4>(RF);
+        for (size_t i = lo; i < hi; ++i) {
+            pre[i - lo] = acc;
+            if (!A[i].is_zero()) acc = f_mul<4>(RF, acc, A[i]);
+        }
+        Fr inv = f_inv<4>(RF, acc);
+        for (size_t i = hi; i-- > lo;) {
+            if (A[i].is_zero()) { O[i] = A[i]; continue; }
+            Fr ai = A[i];
+            O[i] = f_mul<4>(RF, inv, pre[i - lo]);
+            inv = f_mul<4>(RF, inv, ai);
+        }
+    });
+    return 0;
+}
+// Horner evaluation of sum c_i x^i
+int orc_fr_poly_eval(int curve, const u64* coeffs, size_t n, const u64* x, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    const Fr* A = (const Fr*)coeffs;
+    Fr X;
+    memcpy(X.v, x, 32);
+    // chunked Horner: value = sum_c x^(c*CH) * horner(chunk c)
+    const size_t CH = 1 << 14;
+    size_t nch = (n + CH - 1) / CH;
+    std::vector<Fr> part(nch ? nch : 1, f_zero<4>());
+    parallel_for((long long)nch, 1, [&](long long c) {
+        size_t lo = (size_t)c * CH, hi = std::min(n, lo + CH);
+        Fr acc = f_zero<4>();
+        for (size_t i = hi; i-- > lo;) acc = f_add<4>(RF, f_mul<4>(RF, acc, X), A[i]);
+        part[c] = acc;
+    });
+    u64 e[1] = {CH};
+    Fr xc = f_pow<4>(RF, X, e, 1);
+    Fr acc = f_zero<4>();
+    for (size_t c = nch; c-- > 0;) acc = f_add<4>(RF, f_mul<4>(RF, acc, xc), part[c]);
+    memcpy(out, acc.v, 32);
+    return 0;
+}
+// out[i] = c * base^i
+int orc_fr_powers(int curve, const u64* base, const u64* c, size_t n, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    Fr g, c0;
+    memcpy(g.v, base, 32);
+    memcpy(c0.v, c, 32);
+    Fr* O = (Fr*)out;
+    const size_t CH = 4096;
+    parallel_for((long long)((n + CH - 1) / CH), 1, [&](long long ch) {
+        size_t lo = (size_t)ch * CH, hi = std::min(n, lo + CH);
+        u64 e[1] = {lo};
+        Fr p = f_mul<4>(RF, c0, f_pow<4>(RF, g, e, 1));
+        for (size_t i = lo; i < hi; ++i) {
+            O[i] = p;
+            p = f_mul<4>(RF, p, g);
+        }
+    });
+    return 0;
+}
+// quotient of p(X) / (X - z) (synthetic division, remainder dropped): n coefficients in, n-1 out
+int orc_fr_div_linear(int curve, const u64* coeffs, size_t n, const u64* z, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    if (n < 2) return 0;
+    const Fr* A = (const Fr*)coeffs;
+    Fr* Q = (Fr*)out;
+    Fr Z;
+    memcpy(Z.v, z, 32);
+    Fr acc = A[n - 1];
+    Q[n - 2] = acc;
+    for (size_t i = n - 1; i-- > 1;) {
+        acc = f_add<4>(RF, f_mul<4>(RF, acc, Z), A[i]);
+        Q[i - 1] = acc;
+    }
+    return 0;
+}
+// out[i] = scalars[i] * pts[i]   (canonical scalars, affine points in/out)
+int orc_g1_mul(int curve, const u64* pts, const u64* scalars, size_t n, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    parallel_for((long long)n, 4, [&](long long i) {
+        Aff b = load_aff(pts + 12 * i);
+        Jac r = scalar_mul(C, b, scalars + 4 * i);
+        store_aff(out + 12 * i, jac_to_affine(C, r));
+    });
+    return 0;
+}
+// test SRS: out[i] = tau^i * G, i < n (tau canonical).  Fixed-base windows of 8 bits, like the product's srs.cu,
+// but written independently: table T[w][d] = d * 2^(8w) * G built by repeated addition.
+int orc_g1_srs(int curve, const u64* tau, size_t n, u64* out) {
+    const Curve* Cp = curve_by_id(curve);
+    if (!Cp) return -1;
+    const Curve& C = *Cp;
+    Aff g;
+    g.x = C.gx; g.y = C.gy; g.inf = false;
+    std::vector<Aff> table(32 * 256);
+    Jac base = jac_zero(C);
+    jac_add_mixed(C, base, g);
+    for (int w = 0; w < 32; ++w) {
+        Aff b = jac_to_affine(C, base);
+        Jac acc = jac_zero(C);
+        table[w * 256].inf = true;
+        for (int d = 1; d < 256; ++d) {
+            jac_add_mixed(C, acc, b);
+            table[w * 256 + d] = jac_to_affine(C, acc);
+        }
+        for (int k = 0; k < 8; ++k) jac_double(C, base);
+    }
+    Fr t;
+    memcpy(t.v, tau, 32);
+    Fr tm = f_to_mont<4>(RF, t);
+    const size_t CH = 256;
+    parallel_for((long long)((n + CH - 1) / CH), 1, [&](long long ch) {
+        size_t lo = (size_t)ch * CH, hi = std::min(n, lo + CH);
+        u64 e[1] = {lo};
+        Fr p = f_pow<4>(RF, tm, e, 1);
+        std::vector<Jac> buf(hi - lo);
+        for (size_t i = lo; i < hi; ++i) {
+            Fr s = f_from_mont<4>(RF, p);
+            Jac acc = jac_zero(C);
+            for (int w = 0; w < 32; ++w) {
+                unsigned d = (unsigned)((s.v[w >> 3] >> (8 * (w & 7))) & 0xff);
+                if (d) jac_add_mixed(C, acc, table[w * 256 + d]);
+            }
+            buf[i - lo] = acc;
+            p = f_mul<4>(RF, p, tm);
+        }
+        for (size_t i = lo; i < hi; ++i) store_aff(out + 12 * i, jac_to_affine(C, buf[i - lo]));
+    });
+    return 0;
+}
+
 // ---- AES (byte level) ----
 void orc_aes_sbox(uint8_t out[256]) { memcpy(out, sbox(), 256); }
 void orc_aes_add_round_key(const uint8_t* in, const uint8_t* key, uint8_t* out) { aes_add_round_key(in, key, out); }
