@@ -58,6 +58,7 @@ def _load():
         "zkaes_circuit_free": (None, [vp]),
         "zkaes_circuit_info": (c_int, [vp, vp]),
         "zkaes_circuit_matrix": (c_int, [vp, c_int, vp, vp, vp]),
+        "zkaes_witness_aes128_ecb": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
@@ -192,6 +193,18 @@ class Context:
         assert len(seed32) == 32
         buf = (c_uint8 * 32).from_buffer_copy(seed32)
         self._check(lib().zkaes_srs_powers_device(self._h, curve, ctypes.cast(buf, c_void_p), n, _ptr(out_dev)))
+
+    # ---- K1: witness generation ----
+    def witness_aes128_ecb(self, circuit: "Circuit", msg: bytes, key: bytes, want_assignment: bool = True):
+        """-> (ciphertext bytes, assignment uint8 array [instance | witness] or None)"""
+        assert len(key) == 16
+        ct = np.zeros(len(msg), dtype=np.uint8)
+        nvar = circuit.info["num_instance"] + circuit.info["num_witness"]
+        z = np.zeros(nvar, dtype=np.uint8) if want_assignment else None
+        m = np.frombuffer(bytes(msg), dtype=np.uint8)
+        k = np.frombuffer(bytes(key), dtype=np.uint8)
+        self._check(lib().zkaes_witness_aes128_ecb(self._h, circuit._h, _ptr(m), len(msg), _ptr(k), _ptr(ct), _ptr(z)))
+        return ct.tobytes(), z
 
     # ---- self tests ----
     def selftest_field(self, curve: int, field: int, op: int, variant: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:

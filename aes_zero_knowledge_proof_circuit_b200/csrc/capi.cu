@@ -6,6 +6,7 @@
 #include "ntt.cuh"
 #include "srs.cuh"
 #include "circuit.h"
+#include "witness.cuh"
 #include <cstring>
 #include <stdexcept>
 
@@ -309,6 +310,39 @@ int zkaes_circuit_matrix(const zkaes_circuit* h, int which, uint32_t* row_ptr, u
     memcpy(col, m.col.data(), m.col.size() * sizeof(uint32_t));
     memcpy(coeff, m.coeff.data(), m.coeff.size());
     return ZK_OK;
+}
+
+int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* h, const uint8_t* msg, size_t msg_len, const uint8_t key[16],
+                             uint8_t* ct_out, uint8_t* assignment_out) {
+    NEED_CTX(ctx);
+    if (!h || !msg || !key || !ct_out) return fail(ctx, ZK_ERR_ARG, "witness: null pointer");
+    const zk::AesCircuit& c = h->c;
+    if (msg_len != c.msg_len) return fail(ctx, ZK_ERR_ARG, "witness: message length differs from the circuit's");
+    cudaStream_t st = ctx->stream;
+    WitnessDev w;
+    int rc = witness_upload(ctx, c, w);
+    if (rc != ZK_OK) {
+        witness_free(w);
+        return rc;
+    }
+    size_t nvar = (size_t)c.num_instance + c.num_witness;
+    DevBuf dmsg, dkey, dz, dct;
+    auto body = [&]() -> int {
+        ZK_CUDA(ctx, dmsg.alloc(msg_len, st));
+        ZK_CUDA(ctx, dkey.alloc(16, st));
+        ZK_CUDA(ctx, dz.alloc(nvar, st));
+        ZK_CUDA(ctx, dct.alloc(msg_len, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(dmsg.p, msg, msg_len, cudaMemcpyHostToDevice, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(dkey.p, key, 16, cudaMemcpyHostToDevice, st));
+        ZK_TRY(witness_generate(ctx, c, w, dmsg.as<uint8_t>(), dkey.as<uint8_t>(), dz.as<uint8_t>(), dct.as<uint8_t>()));
+        ZK_CUDA(ctx, cudaMemcpyAsync(ct_out, dct.p, msg_len, cudaMemcpyDeviceToHost, st));
+        if (assignment_out) ZK_CUDA(ctx, cudaMemcpyAsync(assignment_out, dz.p, nvar, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        return ZK_OK;
+    };
+    rc = body();
+    witness_free(w);
+    return rc;
 }
 
 }  // extern "C"

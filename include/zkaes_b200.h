@@ -120,6 +120,15 @@ int zkaes_circuit_info(const zkaes_circuit* c, uint64_t info[ZKAES_CIRCUIT_INFO_
 /* which: 0 = A, 1 = B, 2 = C.  row_ptr: num_constraints + 1 entries; col / coeff: nnz entries. */
 int zkaes_circuit_matrix(const zkaes_circuit* c, int which, uint32_t* row_ptr, uint32_t* col, int8_t* coeff);
 
+/* ---- K1: AES-128-ECB witness generation -----------------------------------------------------------------------
+ * Stands in for the value side of the reference's circuit synthesis in encrypt() (src/lib.rs:66-98, 176-293): runs
+ * the block program of `c` for every 16-byte block on the device.  msg_len must equal the circuit's length.
+ * ct_out (msg_len bytes, host) receives the ciphertext; assignment_out (nullable, host, num_instance + num_witness
+ * bytes) receives the full variable assignment, one byte per variable (all variables of this circuit are bits), in
+ * R1CS column order [instance | witness]. */
+int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* c, const uint8_t* msg, size_t msg_len, const uint8_t key[16],
+                             uint8_t* ct_out, uint8_t* assignment_out);
+
 #ifdef __cplusplus
 }
 #endif
