@@ -59,6 +59,11 @@ def _load():
         "zkaes_circuit_info": (c_int, [vp, vp]),
         "zkaes_circuit_matrix": (c_int, [vp, c_int, vp, vp, vp]),
         "zkaes_witness_aes128_ecb": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp]),
+        "zkaes_synthesize_keys": (c_int, [vp, c_size_t, vp, vp, POINTER(vp)]),
+        "zkaes_pk_free": (None, [vp]),
+        "zkaes_pk_info": (c_int, [vp, vp]),
+        "zkaes_pk_vk_bytes": (c_int, [vp, vp, POINTER(c_size_t)]),
+        "zkaes_encrypt": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp, vp, POINTER(c_size_t)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
@@ -254,3 +259,63 @@ class Circuit:
             self.close()
         except Exception:
             pass
+
+
+PK_INFO_FIELDS = ("msg_len", "num_constraints", "num_variables", "nnz_a", "nnz_b", "nnz_c", "h", "k", "x", "max_degree", "num_instance_used")
+
+
+class ProvingKey:
+    """Device-resident proving key (SRS powers, matrices, index polynomials) for one plaintext length."""
+
+    def __init__(self, ctx: Context, handle):
+        self._ctx = ctx
+        self._h = handle
+        info = np.zeros(len(PK_INFO_FIELDS), dtype=np.uint64)
+        assert lib().zkaes_pk_info(self._h, _ptr(info)) == 0
+        self.info = {k: int(v) for k, v in zip(PK_INFO_FIELDS, info)}
+
+    def vk_bytes(self) -> bytes:
+        n = c_size_t(0)
+        assert lib().zkaes_pk_vk_bytes(self._h, None, ctypes.byref(n)) == 0
+        buf = np.zeros(n.value, dtype=np.uint8)
+        assert lib().zkaes_pk_vk_bytes(self._h, _ptr(buf), ctypes.byref(n)) == 0
+        return buf.tobytes()
+
+    def close(self):
+        if self._h:
+            lib().zkaes_pk_free(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _seed(b):
+    assert len(b) == 32
+    return np.frombuffer(bytes(b), dtype=np.uint8)
+
+
+def _synthesize_keys(self, plaintext_length: int, tau_seed: bytes, gamma_seed: bytes) -> ProvingKey:
+    h = c_void_p()
+    self._check(lib().zkaes_synthesize_keys(self._h, plaintext_length, _ptr(_seed(tau_seed)), _ptr(_seed(gamma_seed)), ctypes.byref(h)))
+    return ProvingKey(self, h)
+
+
+def _encrypt(self, pk: ProvingKey, message: bytes, secret_key: bytes, zk_seed: bytes):
+    """-> (ciphertext bytes, proof bytes)"""
+    assert len(secret_key) == 16
+    n = c_size_t(0)
+    m = np.frombuffer(bytes(message), dtype=np.uint8)
+    k = np.frombuffer(bytes(secret_key), dtype=np.uint8)
+    ct = np.zeros(max(len(message), 1), dtype=np.uint8)
+    self._check(lib().zkaes_encrypt(self._h, pk._h, _ptr(m), len(message), _ptr(k), _ptr(_seed(zk_seed)), _ptr(ct), None, ctypes.byref(n)))
+    proof = np.zeros(n.value, dtype=np.uint8)
+    self._check(lib().zkaes_encrypt(self._h, pk._h, _ptr(m), len(message), _ptr(k), _ptr(_seed(zk_seed)), _ptr(ct), _ptr(proof), ctypes.byref(n)))
+    return ct[: len(message)].tobytes(), proof[: n.value].tobytes()
+
+
+Context.synthesize_keys = _synthesize_keys
+Context.encrypt = _encrypt

@@ -7,6 +7,7 @@
 #include "srs.cuh"
 #include "circuit.h"
 #include "witness.cuh"
+#include "prover.cuh"
 #include <cstring>
 #include <stdexcept>
 
@@ -343,6 +344,63 @@ int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* h, const uint8
     rc = body();
     witness_free(w);
     return rc;
+}
+
+// ---- keys + encrypt ------------------------------------------------------------------------------------------------
+int zkaes_synthesize_keys(zkaes_ctx* ctx, size_t plaintext_len, const uint8_t tau_seed32[32], const uint8_t gamma_seed32[32], zkaes_pk** out) {
+    NEED_CTX(ctx);
+    if (!tau_seed32 || !gamma_seed32 || !out) return fail(ctx, ZK_ERR_ARG, "synthesize_keys: null pointer");
+    *out = nullptr;
+    zk::zkaes_pk_impl* p = nullptr;
+    int rc;
+    try {
+        rc = zk::pk_synthesize(ctx, plaintext_len, tau_seed32, gamma_seed32, &p);
+    } catch (const std::exception& e) {
+        return fail(ctx, ZK_ERR_STATE, std::string("synthesize_keys: ") + e.what());
+    }
+    if (rc != ZK_OK) return rc;
+    *out = reinterpret_cast<zkaes_pk*>(p);
+    return ZK_OK;
+}
+void zkaes_pk_free(zkaes_pk* pk) { zk::pk_free(reinterpret_cast<zk::zkaes_pk_impl*>(pk)); }
+int zkaes_pk_info(const zkaes_pk* pk, uint64_t info[ZKAES_PK_INFO_WORDS]) {
+    if (!pk || !info) return ZK_ERR_ARG;
+    zk::pk_info(reinterpret_cast<const zk::zkaes_pk_impl*>(pk), info);
+    return ZK_OK;
+}
+int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len) {
+    if (!pk || !len) return ZK_ERR_ARG;
+    const std::vector<uint8_t>& v = zk::pk_vk_bytes(reinterpret_cast<const zk::zkaes_pk_impl*>(pk));
+    if (out) {
+        if (*len < v.size()) return ZK_ERR_ARG;
+        memcpy(out, v.data(), v.size());
+    }
+    *len = v.size();
+    return ZK_OK;
+}
+int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed32[32],
+                  uint8_t* ct_out, uint8_t* proof_out, size_t* proof_len) {
+    NEED_CTX(ctx);
+    if (!pk || !msg || !key || !zk_seed32 || !ct_out || !proof_len) return fail(ctx, ZK_ERR_ARG, "encrypt: null pointer");
+    // 3 rounds of commitments (4 + 3 + 2, two of them with a shifted part), 7 evaluations, 3 empty messages, 2 opening proofs
+    const size_t need = 8 + (8 + 4 * 49) + (8 + 3 * 49 + 48) + (8 + 2 * 49 + 48) + 8 + 7 * 32 + 8 + 3 + 8 + (48 + 33) + (48 + 1) + 1;
+    if (!proof_out) {
+        *proof_len = need;
+        return ZK_OK;
+    }
+    if (*proof_len < need) return fail(ctx, ZK_ERR_ARG, "encrypt: proof buffer too small");
+    std::vector<uint8_t> proof;
+    int rc;
+    try {
+        rc = zk::pk_encrypt(ctx, reinterpret_cast<const zk::zkaes_pk_impl*>(pk), msg, msg_len, key, zk_seed32, ct_out, proof);
+    } catch (const std::exception& e) {
+        return fail(ctx, ZK_ERR_STATE, std::string("encrypt: ") + e.what());
+    }
+    if (rc != ZK_OK) return rc;
+    if (proof.size() > *proof_len) return fail(ctx, ZK_ERR_STATE, "encrypt: proof larger than its bound");
+    memcpy(proof_out, proof.data(), proof.size());
+    *proof_len = proof.size();
+    return ZK_OK;
 }
 
 }  // extern "C"

@@ -359,6 +359,21 @@ Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& 
     return total.to_affine();
 }
 
+template <class C>
+int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out) {
+    MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits);
+    DevBuf win;
+    ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * p.W, ctx->stream));
+    ZK_TRY(msm_window_sums<C>(ctx, d_bases, d_scalars, n, scalars_mont, p, win.p));
+    std::vector<XYZZ<C>> h(p.W);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win.p, sizeof(XYZZ<C>) * p.W, cudaMemcpyDeviceToHost, ctx->stream));
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = msm_fold_windows_host<C>(h.data(), 1, p);
+    return ZK_OK;
+}
+template int msm_to_affine<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_377Params>*);
+template int msm_to_affine<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_381Params>*);
+
 template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
 template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
 template Affine<G1_377Params> msm_fold_windows_host<G1_377Params>(const XYZZ<G1_377Params>*, int, const MsmPlan&);

@@ -1,0 +1,772 @@
+// The Marlin prover for the AES-128-ECB circuit, device-resident: key synthesis (indexer) and encrypt() (prove).
+//
+// Stands in for what the reference reaches through simpleworks::marlin (third-party, un-vendored):
+//   synthesize_keys  src/lib.rs:138-174 -> generate_universal_srs + generate_proving_and_verifying_keys
+//                    (ark-poly-commit 0.3.0 KZG10::setup / MarlinKZG10::trim, ark-marlin 0.3.0 ahp/indexer.rs)
+//   encrypt          src/lib.rs:60-114  -> generate_proof (ark-marlin 0.3.0 lib.rs::prove, ahp/prover.rs three rounds,
+//                    ark-poly-commit 0.3.0 marlin_pc commit / open_combinations)
+// Orchestration, the Fiat-Shamir transcript and the O(1)-size group / field scalars run on the host; every vector of
+// size |H| or |K| lives in HBM and is only touched by kernels: K1 (witness.cu), K2 (ntt.cu), K3 (msm.cu) and the
+// elementwise passes of polyops.cu.  The proving key (matrices, index polynomials, SRS powers) is uploaded once by
+// zkaes_synthesize_keys and stays resident; encrypt() moves msg_len + 48 bytes down and ~1 KB of proof up.
+#include "prover.cuh"
+
+#include <algorithm>
+#include <stdexcept>
+#include <thread>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "srs.cuh"
+#include "transcript.h"
+
+namespace zk {
+
+namespace {
+using C = G1_377Params;
+using Fr = FrS;
+using Fq = Fp<Fq377Params>;
+using Aff = Affine<C>;
+using XY = XYZZ<C>;
+constexpr int CURVE = 377;
+
+// ---- host scalars ------------------------------------------------------------------------------------------------------
+Fr fr_from_seed(const uint8_t seed32[32]) {  // csrc/srs.cu convention: LE integer, top 4 bits cleared
+    Fr t = Fr::zero();
+    for (int i = 0; i < 32; ++i) t.v[i >> 2] |= (uint32_t)seed32[i] << (8 * (i & 3));
+    t.v[7] &= 0x0fffffffu;
+    return t.to_mont();
+}
+Fr fr_pow_u64(Fr b, uint64_t e) {
+    Fr r = Fr::one();
+    while (e) {
+        if (e & 1) r = r * b;
+        b = b.sqr();
+        e >>= 1;
+    }
+    return r;
+}
+Fr domain_gen(int log_n) {
+    Fr g;
+    for (int i = 0; i < 8; ++i) g.v[i] = Fr377Params::ROOT(i);
+    for (int i = log_n; i < Fr377Params::TWO_ADICITY; ++i) g = g.sqr();
+    return g;
+}
+Fr coset_gen() {
+    Fr g;
+    for (int i = 0; i < 8; ++i) g.v[i] = Fr377Params::GEN(i);
+    return g;
+}
+Fr vanishing(const Fr& x, size_t n) { return fr_pow_u64(x, n) - Fr::one(); }
+// u_H(x, y) = (v_H(x) - v_H(y)) / (x - y), x != y
+Fr bivariate_u(const Fr& x, const Fr& y, size_t n) { return (vanishing(x, n) - vanishing(y, n)) * (x - y).inverse(); }
+void fr_canonical_bytes(const Fr& x, uint8_t out[32]) {
+    Fr c = x.from_mont();
+    memcpy(out, c.v, 32);
+}
+Fr fr_rand(ChaCha20Rng& rng) {
+    uint64_t w[4];
+    fr_rand_raw<Fr377Params>(rng, w);
+    Fr r;
+    memcpy(r.v, w, 32);
+    return r;
+}
+Fr fr_from_u128(uint64_t lo, uint64_t hi) {
+    Fr r = Fr::zero();
+    r.v[0] = (uint32_t)lo; r.v[1] = (uint32_t)(lo >> 32); r.v[2] = (uint32_t)hi; r.v[3] = (uint32_t)(hi >> 32);
+    return r.to_mont();
+}
+Fr sample_outside_domain(ChaCha20Rng& rng, size_t n) {
+    for (;;) {
+        Fr t = fr_rand(rng);
+        if (!vanishing(t, n).is_zero()) return t;
+    }
+}
+
+// ---- host group arithmetic (O(1) points per proof) ---------------------------------------------------------------------
+Aff g1_add(const Aff& a, const Aff& b) {
+    XY t = XY::from_affine(a);
+    t.madd(b);
+    return t.to_affine();
+}
+Aff g1_mul(const Aff& p, const Fr& s_mont) {
+    Fr s = s_mont.from_mont();
+    XY acc = XY::inf();
+    for (int i = 255; i >= 0; --i) {
+        acc = acc.dbl();
+        if ((s.v[i >> 5] >> (i & 31)) & 1) acc.madd(p);
+    }
+    return acc.to_affine();
+}
+// ark-ff ToBytes for GroupAffine: x || y canonical LE || infinity flag
+void g1_to_bytes(const Aff& p, std::vector<uint8_t>& out) {
+    uint8_t b[97];
+    if (p.is_inf()) {
+        memset(b, 0, 97);
+        b[48] = 1;  // y = 1
+        b[96] = 1;
+    } else {
+        Fq x = p.x.from_mont(), y = p.y.from_mont();
+        memcpy(b, x.v, 48);
+        memcpy(b + 48, y.v, 48);
+        b[96] = 0;
+    }
+    out.insert(out.end(), b, b + 97);
+}
+// ark-serialize 0.3.0 compressed GroupAffine: x canonical LE, bit 7 of the last byte = "y > -y", bit 6 = infinity
+void g1_serialize(const Aff& p, std::vector<uint8_t>& out) {
+    uint8_t b[48];
+    if (p.is_inf()) {
+        memset(b, 0, 48);
+        b[47] |= 1 << 6;
+    } else {
+        Fq x = p.x.from_mont(), y = p.y.from_mont(), ny = p.y.neg().from_mont();
+        memcpy(b, x.v, 48);
+        if (y.canonical_gt(ny)) b[47] |= 1 << 7;
+    }
+    out.insert(out.end(), b, b + 48);
+}
+struct Comm {
+    Aff comm;
+    bool has_shifted = false;
+    Aff shifted;
+};
+void comm_to_bytes(const Comm& c, std::vector<uint8_t>& out) {  // ToBytes of marlin_pc::Commitment
+    g1_to_bytes(c.comm, out);
+    out.push_back(c.has_shifted ? 1 : 0);
+    g1_to_bytes(c.has_shifted ? c.shifted : Aff::inf(), out);
+}
+void put_u64(std::vector<uint8_t>& out, uint64_t v) {
+    for (int i = 0; i < 8; ++i) out.push_back((uint8_t)(v >> (8 * i)));
+}
+void put_fr(std::vector<uint8_t>& out, const Fr& x) {
+    uint8_t b[32];
+    fr_canonical_bytes(x, b);
+    out.insert(out.end(), b, b + 32);
+}
+
+size_t next_pow2(size_t v) {
+    size_t n = 1;
+    while (n < v) n <<= 1;
+    return n;
+}
+int log2_exact(size_t n) {
+    int l = 0;
+    while (((size_t)1 << l) < n) ++l;
+    return l;
+}
+
+// small blinding polynomials live on the host (degree <= 2)
+struct Blind {
+    std::vector<Fr> c;
+    Fr eval(const Fr& x) const {
+        Fr acc = Fr::zero();
+        for (size_t i = c.size(); i-- > 0;) acc = acc * x + c[i];
+        return acc;
+    }
+    void add_scaled(const Fr& s, const Blind& o) {
+        if (o.c.size() > c.size()) c.resize(o.c.size(), Fr::zero());
+        for (size_t i = 0; i < o.c.size(); ++i) c[i] = c[i] + s * o.c[i];
+    }
+    bool is_zero() const {
+        for (const Fr& x : c)
+            if (!x.is_zero()) return false;
+        return true;
+    }
+    // quotient by (X - z)
+    Blind div_linear(const Fr& z) const {
+        Blind q;
+        if (c.size() < 2) return q;
+        q.c.resize(c.size() - 1);
+        Fr acc = Fr::zero();
+        for (size_t i = c.size(); i-- > 1;) {
+            acc = acc * z + c[i];
+            q.c[i - 1] = acc;
+        }
+        return q;
+    }
+};
+
+template <class T>
+cudaError_t dev_upload(T** dst, const std::vector<T>& src, cudaStream_t st) {
+    cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(src.size() * sizeof(T), 16));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+}  // namespace
+
+struct zkaes_pk_impl {
+    AesCircuit circ;
+    size_t h = 0, k = 0, x = 0, D = 0;
+    int log_h = 0, log_k = 0, log_x = 0;
+    size_t nnz[3] = {0, 0, 0};
+    // device-resident
+    uint32_t *csr_ptr[3] = {}, *csr_col[3] = {};
+    int8_t* csr_cf[3] = {};
+    uint32_t *csc_ptr[3] = {}, *csc_row[3] = {};
+    int8_t* csc_cf[3] = {};
+    uint32_t *krow[3] = {}, *kcol[3] = {};
+    int8_t* kcoef[3] = {};
+    Fr* elems_h = nullptr;
+    Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
+    Aff* srs = nullptr;     // tau^i G, i <= D
+    Aff gamma_g[3];         // gamma tau^i G (host)
+    Aff index_comms[12];
+    std::vector<uint8_t> vk_bytes;
+    WitnessDev wit;
+    ~zkaes_pk_impl() {
+        for (int m = 0; m < 3; ++m) {
+            cudaFree(csr_ptr[m]); cudaFree(csr_col[m]); cudaFree(csr_cf[m]);
+            cudaFree(csc_ptr[m]); cudaFree(csc_row[m]); cudaFree(csc_cf[m]);
+            cudaFree(krow[m]); cudaFree(kcol[m]); cudaFree(kcoef[m]);
+        }
+        for (int i = 0; i < 12; ++i) cudaFree(idx_poly[i]);
+        cudaFree(elems_h);
+        cudaFree(srs);
+        witness_free(wit);
+    }
+};
+
+namespace {
+
+int ntt(zkaes_ctx* ctx, Fr* data, int log_n, bool inverse, bool coset) { return ntt_device<Fr377Params>(ctx, CURVE, data, log_n, inverse, coset); }
+
+// commit(poly) through the device MSM: sum coeffs[i] * srs[offset + i]
+int msm_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, Aff* out) {
+    if (offset + n > pk.D + 1) return fail(ctx, ZK_ERR_STATE, "commit: polynomial exceeds the SRS");
+    return msm_to_affine<C>(ctx, pk.srs + offset, coeffs, n, /*scalars_mont=*/1, out);
+}
+// KZG10::commit with an optional hiding polynomial of degree hiding_bound + 1 (three draws for hiding_bound = 1)
+int kzg_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, bool hiding, ChaCha20Rng& zk, Aff* out,
+               Blind* blind) {
+    ZK_TRY(msm_commit(ctx, pk, coeffs, n, offset, out));
+    blind->c.clear();
+    if (hiding) {
+        for (int i = 0; i < 3; ++i) blind->c.push_back(fr_rand(zk));
+        for (int i = 0; i < 3; ++i) *out = g1_add(*out, g1_mul(pk.gamma_g[i], blind->c[i]));
+    }
+    return ZK_OK;
+}
+struct Committed {
+    Comm comm;
+    Blind rand, shifted_rand;
+};
+// marlin_pc commit of one labeled polynomial (degree bound -> extra commitment on the shifted powers)
+int pc_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, long bound, bool hiding, ChaCha20Rng& zk, Committed* out) {
+    ZK_TRY(kzg_commit(ctx, pk, coeffs, n, 0, hiding, zk, &out->comm.comm, &out->rand));
+    out->comm.has_shifted = bound >= 0;
+    if (bound >= 0) ZK_TRY(kzg_commit(ctx, pk, coeffs, n, pk.D - (size_t)bound, hiding, zk, &out->comm.shifted, &out->shifted_rand));
+    return ZK_OK;
+}
+
+// DensePolynomial::rand(3|H| + 2 zk - 3) from the zk rng, generated by several host threads (ChaCha is counter based) and
+// compacted in stream order: identical to sequential Fr::rand draws.
+void sample_mask(ChaCha20Rng& zk, size_t count, std::vector<Fr>& out) {
+    out.resize(count);
+    size_t have = 0;
+    constexpr int shave = 256 - Fr377Params::BITS;
+    uint64_t mod[4];
+    for (int i = 0; i < 4; ++i) mod[i] = (uint64_t)Fr377Params::MOD(2 * i) | ((uint64_t)Fr377Params::MOD(2 * i + 1) << 32);
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    while (have < count) {
+        size_t need = count - have;
+        size_t cand = need * 2 + 64;  // acceptance is ~0.58
+        cand = (cand + 1) & ~(size_t)1;  // whole ChaCha blocks hold two candidates (8 u64)
+        if (zk.pos & 7) {  // not block aligned (only after scalar draws): fall back to aligning through single draws
+            out[have++] = fr_rand(zk);
+            continue;
+        }
+        std::vector<uint64_t> buf(cand * 4);
+        std::vector<uint8_t> ok(cand);
+        uint64_t blk0 = zk.pos >> 3;
+        auto work = [&](size_t lo, size_t hi) {
+            uint32_t w[16];
+            for (size_t b = lo; b < hi; ++b) {  // block b holds candidates 2b, 2b+1
+                chacha20_block(zk.key, blk0 + b, w);
+                for (int c = 0; c < 2; ++c) {
+                    uint64_t* o = &buf[(2 * b + c) * 4];
+                    for (int i = 0; i < 4; ++i) o[i] = (uint64_t)w[8 * c + 2 * i] | ((uint64_t)w[8 * c + 2 * i + 1] << 32);
+                    o[3] &= ~0ull >> shave;
+                    bool lt = false;
+                    for (int i = 3; i >= 0; --i)
+                        if (o[i] != mod[i]) {
+                            lt = o[i] < mod[i];
+                            break;
+                        }
+                    ok[2 * b + c] = lt;
+                }
+            }
+        };
+        size_t nblk = cand / 2;
+        std::vector<std::thread> th;
+        size_t per = (nblk + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; ++t) {
+            size_t lo = t * per, hi = std::min(nblk, lo + per);
+            if (lo < hi) th.emplace_back(work, lo, hi);
+        }
+        for (auto& t : th) t.join();
+        size_t used = 0;
+        for (size_t c = 0; c < cand && have < count; ++c) {
+            used = c + 1;
+            if (ok[c]) memcpy(out[have++].v, &buf[c * 4], 32);
+        }
+        zk.pos += used * 4;
+        zk.cur_block = ~0ull;
+    }
+}
+
+}  // namespace
+
+// ======================================================================================================================
+// synthesize_keys
+// ======================================================================================================================
+int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], const uint8_t gamma_seed[32], zkaes_pk_impl** out) {
+    *out = nullptr;
+    std::unique_ptr<zkaes_pk_impl> pkp(new zkaes_pk_impl());
+    zkaes_pk_impl& pk = *pkp;
+    try {
+        build_aes_circuit(msg_len, pk.circ);
+    } catch (const std::exception& e) {
+        return fail(ctx, ZK_ERR_ARG, std::string("synthesize_keys: ") + e.what());
+    }
+    const AesCircuit& c = pk.circ;
+    cudaStream_t st = ctx->stream;
+    const CsrMatrix* M[3] = {&c.a, &c.b, &c.c};
+    for (int m = 0; m < 3; ++m) pk.nnz[m] = M[m]->nnz();
+    // ark-marlin balance_matrices swaps rows while A is the denser matrix; for this circuit nnz(A) < nnz(B) so it is the identity
+    if (pk.nnz[0] >= pk.nnz[1]) return fail(ctx, ZK_ERR_UNSUPPORTED, "synthesize_keys: matrix A denser than B (balance_matrices not implemented)");
+    size_t nnz_max = std::max(pk.nnz[0], std::max(pk.nnz[1], pk.nnz[2]));
+    pk.h = next_pow2(c.num_constraints);
+    pk.k = next_pow2(nnz_max);
+    pk.x = c.num_instance;
+    pk.log_h = log2_exact(pk.h); pk.log_k = log2_exact(pk.k); pk.log_x = log2_exact(pk.x);
+    if (pk.log_k + 2 > 30) return fail(ctx, ZK_ERR_UNSUPPORTED, "synthesize_keys: |K| too large for this build (4|K| NTT limit 2^30)");
+    // AHPForR1CS::max_degree with zk_bound = 1
+    pk.D = std::max(std::max(2 * pk.h - 1, 3 * pk.h - 1), std::max(pk.h, 3 * pk.k - 3));
+    const size_t h = pk.h, k = pk.k, x = pk.x;
+
+    // ---- SRS: tau^i G on the device, gamma tau^i G (i < 3) on the host -----------------------------------------------
+    ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * (pk.D + 1)));
+    ZK_TRY(srs_powers_device<C>(ctx, tau_seed, pk.D + 1, pk.srs));
+    Fr tau = fr_from_seed(tau_seed), gamma = fr_from_seed(gamma_seed);
+    Fr gt = gamma;
+    for (int i = 0; i < 3; ++i) {
+        pk.gamma_g[i] = g1_mul(Aff::generator(), gt);
+        gt = gt * tau;
+    }
+
+    // ---- matrices: CSR, CSC (for t), K-domain arithmetisation indices -------------------------------------------------
+    const size_t period = h / x;
+    auto reindex = [&](size_t j) -> uint32_t {
+        if (j < x) return (uint32_t)(j * period);
+        size_t i = j - x;
+        return (uint32_t)(i + i / (period - 1) + 1);
+    };
+    const size_t nvar = (size_t)c.num_instance + c.num_witness;
+    for (int m = 0; m < 3; ++m) {
+        const CsrMatrix& A = *M[m];
+        ZK_CUDA(ctx, dev_upload(&pk.csr_ptr[m], A.row_ptr, st));
+        ZK_CUDA(ctx, dev_upload(&pk.csr_col[m], A.col, st));
+        ZK_CUDA(ctx, dev_upload(&pk.csr_cf[m], A.coeff, st));
+        std::vector<uint32_t> cptr(nvar + 1, 0), crow(A.nnz());
+        std::vector<int8_t> ccf(A.nnz());
+        for (uint32_t cc : A.col) cptr[cc + 1]++;
+        for (size_t j = 0; j < nvar; ++j) cptr[j + 1] += cptr[j];
+        std::vector<uint32_t> fill(cptr.begin(), cptr.end() - 1);
+        std::vector<uint32_t> krow(k, 0), kcol(k, 0);
+        std::vector<int8_t> kcf(k, 0);
+        size_t nrows = A.row_ptr.size() - 1;
+        for (size_t r = 0; r < nrows; ++r)
+            for (uint32_t e = A.row_ptr[r]; e < A.row_ptr[r + 1]; ++e) {
+                uint32_t p = fill[A.col[e]]++;
+                crow[p] = (uint32_t)r;
+                ccf[p] = A.coeff[e];
+                krow[e] = reindex(A.col[e]);  // row(kappa): the VARIABLE's element (arithmetisation of M^*)
+                kcol[e] = (uint32_t)r;        // col(kappa): the CONSTRAINT's element
+                kcf[e] = A.coeff[e];
+            }
+        ZK_CUDA(ctx, dev_upload(&pk.csc_ptr[m], cptr, st));
+        ZK_CUDA(ctx, dev_upload(&pk.csc_row[m], crow, st));
+        ZK_CUDA(ctx, dev_upload(&pk.csc_cf[m], ccf, st));
+        ZK_CUDA(ctx, dev_upload(&pk.krow[m], krow, st));
+        ZK_CUDA(ctx, dev_upload(&pk.kcol[m], kcol, st));
+        ZK_CUDA(ctx, dev_upload(&pk.kcoef[m], kcf, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
+    }
+    ZK_TRY(witness_upload(ctx, c, pk.wit));
+
+    // ---- index polynomials (ahp/indexer.rs arithmetize_matrix) and their commitments ---------------------------------
+    ZK_CUDA(ctx, cudaMalloc((void**)&pk.elems_h, sizeof(Fr) * h));
+    ZK_TRY(po_powers(ctx, pk.elems_h, h, domain_gen(pk.log_h), Fr::one()));
+    Fr hinv = Fr::from_u64(h).inverse();
+    for (int m = 0; m < 3; ++m) {
+        Fr** P = &pk.idx_poly[4 * m];
+        for (int j = 0; j < 4; ++j) ZK_CUDA(ctx, cudaMalloc((void**)&P[j], sizeof(Fr) * k));
+        ZK_TRY(po_gather(ctx, P[0], pk.elems_h, pk.krow[m], k));
+        ZK_TRY(po_gather(ctx, P[1], pk.elems_h, pk.kcol[m], k));
+        // val = M / u_H(row, row), u_H(y, y) = |H| y^(|H|-1) = |H| / y
+        ZK_TRY(po_gather_scaled(ctx, P[2], pk.elems_h, pk.krow[m], pk.kcoef[m], hinv, k));
+        ZK_TRY(po_vec(ctx, 2, P[3], P[0], P[1], k));
+        for (int j = 0; j < 4; ++j) {
+            ZK_TRY(ntt(ctx, P[j], pk.log_k, true, false));
+            ZK_TRY(msm_commit(ctx, pk, P[j], k, 0, &pk.index_comms[4 * m + j]));
+        }
+    }
+    // IndexVerifierKey ToBytes: index_info (3 x u64) || 12 commitments
+    pk.vk_bytes.clear();
+    put_u64(pk.vk_bytes, nvar);
+    put_u64(pk.vk_bytes, c.num_constraints);
+    put_u64(pk.vk_bytes, nnz_max);
+    for (int i = 0; i < 12; ++i) {
+        Comm cm;
+        cm.comm = pk.index_comms[i];
+        comm_to_bytes(cm, pk.vk_bytes);
+    }
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = pkp.release();
+    return ZK_OK;
+}
+
+void pk_free(zkaes_pk_impl* pk) { delete pk; }
+const std::vector<uint8_t>& pk_vk_bytes(const zkaes_pk_impl* pk) { return pk->vk_bytes; }
+void pk_info(const zkaes_pk_impl* pk, uint64_t info[ZK_PK_INFO_WORDS]) {
+    const AesCircuit& c = pk->circ;
+    uint64_t v[ZK_PK_INFO_WORDS] = {c.msg_len, c.num_constraints, (uint64_t)c.num_instance + c.num_witness, pk->nnz[0], pk->nnz[1], pk->nnz[2],
+                                    pk->h, pk->k, pk->x, pk->D, c.num_instance_used};
+    memcpy(info, v, sizeof(v));
+}
+
+// ======================================================================================================================
+// encrypt(): witness + prove
+// ======================================================================================================================
+int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed[32],
+               uint8_t* ct_out, std::vector<uint8_t>& proof) {
+    const zkaes_pk_impl& pk = *pkp;
+    const AesCircuit& c = pk.circ;
+    if (msg_len != c.msg_len) return fail(ctx, ZK_ERR_ARG, "encrypt: message length differs from the proving key's");
+    cudaStream_t st = ctx->stream;
+    const size_t h = pk.h, k = pk.k, x = pk.x, D = pk.D;
+    const size_t nvar = (size_t)c.num_instance + c.num_witness;
+    ChaCha20Rng zk(zk_seed);
+
+    // ---- K1: witness ---------------------------------------------------------------------------------------------------
+    DevBuf dmsg, dkey, dz, dct;
+    ZK_CUDA(ctx, dmsg.alloc(msg_len, st));
+    ZK_CUDA(ctx, dkey.alloc(16, st));
+    ZK_CUDA(ctx, dz.alloc(nvar, st));
+    ZK_CUDA(ctx, dct.alloc(msg_len, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(dmsg.p, msg, msg_len, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(dkey.p, key, 16, cudaMemcpyHostToDevice, st));
+    ZK_TRY(witness_generate(ctx, c, pk.wit, dmsg.as<uint8_t>(), dkey.as<uint8_t>(), dz.as<uint8_t>(), dct.as<uint8_t>()));
+    ZK_CUDA(ctx, cudaMemcpyAsync(ct_out, dct.p, msg_len, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint8_t* z = dz.as<uint8_t>();
+
+    // ---- Fiat-Shamir seed: protocol name || index vk || public input (unformatted: without the leading one, zero padded)
+    std::vector<uint8_t> seed(pk.vk_bytes.size() + 11 + 32 * (x - 1));
+    memcpy(seed.data(), "MARLIN-2019", 11);
+    memcpy(seed.data() + 11, pk.vk_bytes.data(), pk.vk_bytes.size());
+    {
+        uint8_t* p = seed.data() + 11 + pk.vk_bytes.size();
+        memset(p, 0, 32 * (x - 1));
+        for (size_t i = 0; i < 8 * msg_len; ++i) p[32 * i] = (ct_out[i >> 3] >> (i & 7)) & 1;  // byte_to_field_array (src/helpers/mod.rs:84-93)
+    }
+    FiatShamirRng fs(seed);
+
+    // ---- first round -----------------------------------------------------------------------------------------------------
+    DevBuf x_poly, x_evals, wbuf, w_poly, za, zb, mask, rem;
+    ZK_CUDA(ctx, x_poly.alloc(sizeof(Fr) * x, st));
+    ZK_TRY(po_bits_to_fr(ctx, x_poly.as<Fr>(), z, x));  // formatted input = the instance section of z
+    ZK_TRY(ntt(ctx, x_poly.as<Fr>(), pk.log_x, true, false));
+    ZK_CUDA(ctx, x_evals.alloc(sizeof(Fr) * h, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(x_evals.p, 0, sizeof(Fr) * h, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(x_evals.p, x_poly.p, sizeof(Fr) * x, cudaMemcpyDeviceToDevice, st));
+    ZK_TRY(ntt(ctx, x_evals.as<Fr>(), pk.log_h, false, false));
+    ZK_CUDA(ctx, wbuf.alloc(sizeof(Fr) * (h + 1), st));
+    ZK_TRY(po_w_evals(ctx, wbuf.as<Fr>(), z, x_evals.as<Fr>(), h, h / x, c.num_instance, c.num_witness));
+    x_evals.release();
+    ZK_TRY(ntt(ctx, wbuf.as<Fr>(), pk.log_h, true, false));
+    ZK_CUDA(ctx, cudaMemsetAsync(wbuf.as<Fr>() + h, 0, sizeof(Fr), st));
+    Fr r_w = fr_rand(zk), r_a = fr_rand(zk), r_b = fr_rand(zk);
+    ZK_TRY(po_add_vanishing(ctx, wbuf.as<Fr>(), h, r_w));
+    const size_t len_w = h + 1 - x;
+    ZK_CUDA(ctx, w_poly.alloc(sizeof(Fr) * len_w, st));
+    ZK_CUDA(ctx, rem.alloc(sizeof(Fr) * h, st));
+    ZK_TRY(po_divide_vanishing(ctx, wbuf.as<Fr>(), h + 1, x, w_poly.as<Fr>(), rem.as<Fr>()));
+    wbuf.release();
+    ZK_CUDA(ctx, za.alloc(sizeof(Fr) * (h + 1), st));
+    ZK_CUDA(ctx, zb.alloc(sizeof(Fr) * (h + 1), st));
+    DevBuf* zab[2] = {&za, &zb};
+    const Fr r_ab[2] = {r_a, r_b};
+    for (int m = 0; m < 2; ++m) {
+        Fr* p = zab[m]->as<Fr>();
+        ZK_TRY(po_spmv_bits(ctx, p, pk.csr_ptr[m], pk.csr_col[m], pk.csr_cf[m], z, c.num_constraints, h));
+        ZK_TRY(ntt(ctx, p, pk.log_h, true, false));
+        ZK_CUDA(ctx, cudaMemsetAsync(p + h, 0, sizeof(Fr), st));
+        ZK_TRY(po_add_vanishing(ctx, p, h, r_ab[m]));
+    }
+    // mask polynomial: degree 3|H| + 2 zk - 3; force sum over H to zero by fixing the constant term
+    const size_t len_mask = 3 * h;
+    std::vector<Fr> mask_h;
+    sample_mask(zk, len_mask, mask_h);
+    mask_h[0] = (mask_h[h] + mask_h[2 * h]).neg();
+    ZK_CUDA(ctx, mask.alloc(sizeof(Fr) * len_mask, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(mask.p, mask_h.data(), sizeof(Fr) * len_mask, cudaMemcpyHostToDevice, st));
+    Committed c_w, c_za, c_zb, c_mask;
+    ZK_TRY(pc_commit(ctx, pk, w_poly.as<Fr>(), len_w, -1, true, zk, &c_w));
+    ZK_TRY(pc_commit(ctx, pk, za.as<Fr>(), h + 1, -1, true, zk, &c_za));
+    ZK_TRY(pc_commit(ctx, pk, zb.as<Fr>(), h + 1, -1, true, zk, &c_zb));
+    ZK_TRY(pc_commit(ctx, pk, mask.as<Fr>(), len_mask, -1, false, zk, &c_mask));
+    {
+        std::vector<uint8_t> b;
+        for (const Committed* cm : {&c_w, &c_za, &c_zb, &c_mask}) comm_to_bytes(cm->comm, b);
+        fs.absorb(b);
+    }
+    Fr alpha = sample_outside_domain(fs.rng, h);
+    Fr eta[3] = {fr_rand(fs.rng), fr_rand(fs.rng), fr_rand(fs.rng)};
+
+    // ---- second round ------------------------------------------------------------------------------------------------------
+    const Fr vh_alpha = vanishing(alpha, h);
+    DevBuf ra, tpoly, zpoly, tmp;
+    ZK_CUDA(ctx, ra.alloc(sizeof(Fr) * h, st));
+    ZK_CUDA(ctx, tmp.alloc(sizeof(Fr) * h, st));
+    ZK_TRY(po_rsub_scalar(ctx, tmp.as<Fr>(), pk.elems_h, alpha, h));
+    ZK_TRY(po_batch_inverse(ctx, ra.as<Fr>(), tmp.as<Fr>(), h));
+    ZK_TRY(po_scale(ctx, ra.as<Fr>(), ra.as<Fr>(), vh_alpha, h));  // r(alpha, h_i) = v_H(alpha) / (alpha - h_i)
+    tmp.release();
+    ZK_CUDA(ctx, tpoly.alloc(sizeof(Fr) * h, st));
+    CscView csc[3];
+    for (int m = 0; m < 3; ++m) csc[m] = CscView{pk.csc_ptr[m], pk.csc_row[m], pk.csc_cf[m]};
+    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), nvar, h, x));
+    ZK_TRY(ntt(ctx, tpoly.as<Fr>(), pk.log_h, true, false));
+    ZK_TRY(ntt(ctx, ra.as<Fr>(), pk.log_h, true, false));  // r_alpha polynomial
+    ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));
+    ZK_TRY(po_z_poly(ctx, zpoly.as<Fr>(), w_poly.as<Fr>(), len_w, x_poly.as<Fr>(), x));
+    // products on the 4|H| domain
+    const size_t n4 = 4 * h;
+    const int log4h = pk.log_h + 2;
+    DevBuf e_ra, e_za, e_zb, e_t, e_z;
+    auto to_evals4 = [&](DevBuf& dst, const Fr* src, size_t len) -> int {
+        ZK_CUDA(ctx, dst.alloc(sizeof(Fr) * n4, st));
+        ZK_CUDA(ctx, cudaMemsetAsync(dst.as<Fr>() + len, 0, sizeof(Fr) * (n4 - len), st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(dst.p, src, sizeof(Fr) * len, cudaMemcpyDeviceToDevice, st));
+        return ntt(ctx, dst.as<Fr>(), log4h, false, false);
+    };
+    ZK_TRY(to_evals4(e_ra, ra.as<Fr>(), h));
+    ZK_TRY(to_evals4(e_za, za.as<Fr>(), h + 1));
+    ZK_TRY(to_evals4(e_zb, zb.as<Fr>(), h + 1));
+    ZK_TRY(to_evals4(e_t, tpoly.as<Fr>(), h));
+    ZK_TRY(to_evals4(e_z, zpoly.as<Fr>(), h + 1));
+    ra.release();
+    zpoly.release();
+    ZK_TRY(po_round2(ctx, e_ra.as<Fr>(), e_ra.as<Fr>(), e_za.as<Fr>(), e_zb.as<Fr>(), e_t.as<Fr>(), e_z.as<Fr>(), eta, n4));
+    e_za.release(); e_zb.release(); e_t.release(); e_z.release();
+    ZK_TRY(ntt(ctx, e_ra.as<Fr>(), log4h, true, false));  // rhs coefficients (degree <= 3|H| + 1)
+    ZK_TRY(po_vec(ctx, 0, e_ra.as<Fr>(), e_ra.as<Fr>(), mask.as<Fr>(), len_mask));  // q_1 = mask + rhs
+    DevBuf h1, xg1;
+    ZK_CUDA(ctx, h1.alloc(sizeof(Fr) * (n4 - h), st));
+    ZK_CUDA(ctx, xg1.alloc(sizeof(Fr) * h, st));
+    ZK_TRY(po_divide_vanishing(ctx, e_ra.as<Fr>(), n4, h, h1.as<Fr>(), xg1.as<Fr>()));
+    e_ra.release();
+    const Fr* g1 = xg1.as<Fr>() + 1;  // q_1 = h_1 v_H + X g_1
+    const size_t len_g1 = h - 1, len_h1 = 2 * h + 1;
+    Committed c_t, c_g1, c_h1;
+    ZK_TRY(pc_commit(ctx, pk, tpoly.as<Fr>(), h, -1, false, zk, &c_t));
+    ZK_TRY(pc_commit(ctx, pk, g1, len_g1, (long)(h - 2), true, zk, &c_g1));
+    ZK_TRY(pc_commit(ctx, pk, h1.as<Fr>(), len_h1, -1, true, zk, &c_h1));
+    {
+        std::vector<uint8_t> b;
+        for (const Committed* cm : {&c_t, &c_g1, &c_h1}) comm_to_bytes(cm->comm, b);
+        fs.absorb(b);
+    }
+    Fr beta = sample_outside_domain(fs.rng, h);
+
+    // ---- third round -------------------------------------------------------------------------------------------------------
+    const Fr vh_beta = vanishing(beta, h);
+    const Fr vv = vh_alpha * vh_beta;
+    const Fr hinv = Fr::from_u64(h).inverse();
+    DevBuf fpoly, den, inv;
+    ZK_CUDA(ctx, fpoly.alloc(sizeof(Fr) * k, st));
+    ZK_CUDA(ctx, den.alloc(sizeof(Fr) * k, st));
+    ZK_CUDA(ctx, inv.alloc(sizeof(Fr) * k, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(fpoly.p, 0, sizeof(Fr) * k, st));
+    for (int m = 0; m < 3; ++m) {
+        ZK_TRY(po_den_k(ctx, den.as<Fr>(), pk.elems_h, pk.krow[m], pk.kcol[m], alpha, beta, k));
+        ZK_TRY(po_batch_inverse(ctx, inv.as<Fr>(), den.as<Fr>(), k));
+        ZK_TRY(po_gather_fma(ctx, fpoly.as<Fr>(), pk.elems_h, pk.krow[m], pk.kcoef[m], inv.as<Fr>(), eta[m] * hinv * vv, k));
+    }
+    den.release(); inv.release();
+    ZK_TRY(ntt(ctx, fpoly.as<Fr>(), pk.log_k, true, false));
+    const Fr* g2 = fpoly.as<Fr>() + 1;  // f = X g_2 + t(beta) / |K|
+    const size_t len_g2 = k - 1;
+    // h_2 = (a - b f) / v_K on the coset g * B, |B| = 4|K|
+    const size_t k4 = 4 * k;
+    const int log4k = pk.log_k + 2;
+    DevBuf dden[3], dval[3], t_col, t_rc, f4;
+    auto to_coset4 = [&](DevBuf& dst, const Fr* src, size_t len) -> int {
+        if (!dst.p) ZK_CUDA(ctx, dst.alloc(sizeof(Fr) * k4, st));
+        ZK_CUDA(ctx, cudaMemsetAsync(dst.as<Fr>() + len, 0, sizeof(Fr) * (k4 - len), st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(dst.p, src, sizeof(Fr) * len, cudaMemcpyDeviceToDevice, st));
+        return ntt(ctx, dst.as<Fr>(), log4k, false, true);
+    };
+    const Fr ab = alpha * beta;
+    for (int m = 0; m < 3; ++m) {
+        Fr* const* P = &pk.idx_poly[4 * m];
+        ZK_TRY(to_coset4(dden[m], P[0], k));
+        ZK_TRY(to_coset4(t_col, P[1], k));
+        ZK_TRY(to_coset4(t_rc, P[3], k));
+        ZK_TRY(po_den_coset(ctx, dden[m].as<Fr>(), t_col.as<Fr>(), t_rc.as<Fr>(), alpha, beta, ab, k4));
+        ZK_TRY(to_coset4(dval[m], P[2], k));
+    }
+    t_rc.release();
+    ZK_TRY(to_coset4(f4, fpoly.as<Fr>(), k));
+    Fr vkinv[4];
+    {
+        Fr gk = fr_pow_u64(coset_gen(), k), w4 = fr_pow_u64(domain_gen(log4k), k), cur = gk;
+        for (int i = 0; i < 4; ++i) {
+            vkinv[i] = (cur - Fr::one()).inverse();
+            cur = cur * w4;
+        }
+    }
+    const Fr* vals[3] = {dval[0].as<Fr>(), dval[1].as<Fr>(), dval[2].as<Fr>()};
+    const Fr* dens[3] = {dden[0].as<Fr>(), dden[1].as<Fr>(), dden[2].as<Fr>()};
+    Fr* h2 = t_col.as<Fr>();
+    ZK_TRY(po_round3(ctx, h2, vals, dens, f4.as<Fr>(), eta, vv, vkinv, k4));
+    for (int m = 0; m < 3; ++m) {
+        dden[m].release();
+        dval[m].release();
+    }
+    f4.release();
+    ZK_TRY(ntt(ctx, h2, log4k, true, true));
+    const size_t len_h2 = 3 * k - 3;
+    Committed c_g2, c_h2;
+    ZK_TRY(pc_commit(ctx, pk, g2, len_g2, (long)(k - 2), false, zk, &c_g2));
+    ZK_TRY(pc_commit(ctx, pk, h2, len_h2, -1, false, zk, &c_h2));
+    {
+        std::vector<uint8_t> b;
+        for (const Committed* cm : {&c_g2, &c_h2}) comm_to_bytes(cm->comm, b);
+        fs.absorb(b);
+    }
+    Fr gamma = fr_rand(fs.rng);
+
+    // ---- evaluations (sorted by label: a_denom b_denom c_denom g_1 g_2 t z_b) ---------------------------------------------
+    Fr ev_g1, ev_g2, ev_t, ev_zb, ev_den[3];
+    ZK_TRY(po_eval(ctx, g1, len_g1, beta, &ev_g1));
+    ZK_TRY(po_eval(ctx, g2, len_g2, gamma, &ev_g2));
+    ZK_TRY(po_eval(ctx, tpoly.as<Fr>(), h, beta, &ev_t));
+    ZK_TRY(po_eval(ctx, zb.as<Fr>(), h + 1, beta, &ev_zb));
+    for (int m = 0; m < 3; ++m) {
+        Fr er, ec, erc;
+        ZK_TRY(po_eval(ctx, pk.idx_poly[4 * m + 0], k, gamma, &er));
+        ZK_TRY(po_eval(ctx, pk.idx_poly[4 * m + 1], k, gamma, &ec));
+        ZK_TRY(po_eval(ctx, pk.idx_poly[4 * m + 3], k, gamma, &erc));
+        ev_den[m] = ab - alpha * er - beta * ec + erc;
+    }
+    const Fr evals[7] = {ev_den[0], ev_den[1], ev_den[2], ev_g1, ev_g2, ev_t, ev_zb};
+    {
+        std::vector<uint8_t> b;
+        for (const Fr& e : evals) put_fr(b, e);
+        fs.absorb(b);
+    }
+    uint64_t lo = fs.rng.next_u64(), hi = fs.rng.next_u64();
+    const Fr ch = fr_from_u128(lo, hi);
+    Fr chp[6];
+    chp[0] = Fr::one();
+    for (int i = 1; i < 6; ++i) chp[i] = chp[i - 1] * ch;
+
+    // ---- openings (marlin_pc open_combinations -> batch_open per query point) ------------------------------------------
+    // beta: g_1 [ch^0, shifted ch^1], outer_sumcheck [ch^2], t [ch^3], z_b [ch^4]
+    Aff w_beta, w_gamma;
+    Fr rv_beta;
+    {
+        // x(beta) for the constant term is not part of the opened polynomial (constants are dropped by open_combinations)
+        const Fr r_ab_beta = bivariate_u(alpha, beta, h);
+        const Fr vx_beta = vanishing(beta, x);
+        const Fr c_za_lc = r_ab_beta * (eta[0] + eta[2] * ev_zb);
+        const Fr c_w_lc = (ev_t * vx_beta).neg();
+        const Fr c_h1_lc = vh_beta.neg();
+        DevBuf P;
+        ZK_CUDA(ctx, P.alloc(sizeof(Fr) * len_mask, st));
+        ZK_TRY(po_scale(ctx, P.as<Fr>(), mask.as<Fr>(), chp[2], len_mask));                 // ch^2 * mask
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), za.as<Fr>(), chp[2] * c_za_lc, h + 1));
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), w_poly.as<Fr>(), chp[2] * c_w_lc, len_w));
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), h1.as<Fr>(), chp[2] * c_h1_lc, len_h1));
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), g1, chp[0], len_g1));
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), tpoly.as<Fr>(), chp[3], h));
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), zb.as<Fr>(), chp[4], h + 1));
+        Blind r;
+        r.add_scaled(chp[0], c_g1.rand);
+        r.add_scaled(chp[2] * c_za_lc, c_za.rand);
+        r.add_scaled(chp[2] * c_w_lc, c_w.rand);
+        r.add_scaled(chp[2] * c_h1_lc, c_h1.rand);
+        r.add_scaled(chp[4], c_zb.rand);
+        DevBuf Q;
+        ZK_CUDA(ctx, Q.alloc(sizeof(Fr) * len_mask, st));
+        ZK_TRY(po_div_linear(ctx, P.as<Fr>(), len_mask, beta, Q.as<Fr>()));
+        ZK_TRY(msm_commit(ctx, pk, Q.as<Fr>(), len_mask - 1, 0, &w_beta));
+        Blind rw = r.div_linear(beta);
+        for (size_t i = 0; i < rw.c.size(); ++i) w_beta = g1_add(w_beta, g1_mul(pk.gamma_g[i], rw.c[i]));
+        rv_beta = r.eval(beta);
+        // shifted part: witness of g_1 alone on the powers from D - (|H| - 2), times ch^1
+        ZK_TRY(po_div_linear(ctx, g1, len_g1, beta, Q.as<Fr>()));
+        Aff sw;
+        ZK_TRY(msm_commit(ctx, pk, Q.as<Fr>(), len_g1 - 1, D - (h - 2), &sw));
+        Blind srw = c_g1.shifted_rand.div_linear(beta);
+        for (size_t i = 0; i < srw.c.size(); ++i) sw = g1_add(sw, g1_mul(pk.gamma_g[i], srw.c[i]));
+        w_beta = g1_add(w_beta, g1_mul(sw, chp[1]));
+        rv_beta = rv_beta + chp[1] * c_g1.shifted_rand.eval(beta);
+    }
+    // gamma: a_denom [ch^0], b_denom [ch^1], c_denom [ch^2], g_2 [ch^3, shifted ch^4], inner_sumcheck [ch^5]; nothing is hiding
+    {
+        const Fr vk_gamma = vanishing(gamma, k);
+        const size_t len_p = len_h2;
+        DevBuf P;
+        ZK_CUDA(ctx, P.alloc(sizeof(Fr) * len_p, st));
+        ZK_TRY(po_scale(ctx, P.as<Fr>(), h2, (chp[5] * vk_gamma).neg(), len_p));
+        const Fr inner_c[3] = {eta[0] * ev_den[1] * ev_den[2] * vv, eta[1] * ev_den[0] * ev_den[2] * vv, eta[2] * ev_den[1] * ev_den[0] * vv};
+        for (int m = 0; m < 3; ++m) {
+            ZK_TRY(po_axpy(ctx, P.as<Fr>(), pk.idx_poly[4 * m + 2], chp[5] * inner_c[m], k));
+            ZK_TRY(po_axpy(ctx, P.as<Fr>(), pk.idx_poly[4 * m + 0], (chp[m] * alpha).neg(), k));
+            ZK_TRY(po_axpy(ctx, P.as<Fr>(), pk.idx_poly[4 * m + 1], (chp[m] * beta).neg(), k));
+            ZK_TRY(po_axpy(ctx, P.as<Fr>(), pk.idx_poly[4 * m + 3], chp[m], k));
+        }
+        ZK_TRY(po_axpy(ctx, P.as<Fr>(), g2, chp[3], len_g2));
+        DevBuf Q;
+        ZK_CUDA(ctx, Q.alloc(sizeof(Fr) * len_p, st));
+        ZK_TRY(po_div_linear(ctx, P.as<Fr>(), len_p, gamma, Q.as<Fr>()));
+        ZK_TRY(msm_commit(ctx, pk, Q.as<Fr>(), len_p - 1, 0, &w_gamma));
+        ZK_TRY(po_div_linear(ctx, g2, len_g2, gamma, Q.as<Fr>()));
+        Aff sw;
+        ZK_TRY(msm_commit(ctx, pk, Q.as<Fr>(), len_g2 - 1, D - (k - 2), &sw));
+        w_gamma = g1_add(w_gamma, g1_mul(sw, chp[4]));
+    }
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+
+    // ---- ark-serialize 0.3.0 CanonicalSerialize of ark_marlin::Proof ----------------------------------------------------------
+    proof.clear();
+    put_u64(proof, 3);
+    const std::vector<const Committed*> rounds[3] = {{&c_w, &c_za, &c_zb, &c_mask}, {&c_t, &c_g1, &c_h1}, {&c_g2, &c_h2}};
+    for (const auto& rnd : rounds) {
+        put_u64(proof, rnd.size());
+        for (const Committed* cm : rnd) {
+            g1_serialize(cm->comm.comm, proof);
+            proof.push_back(cm->comm.has_shifted ? 1 : 0);
+            if (cm->comm.has_shifted) g1_serialize(cm->comm.shifted, proof);
+        }
+    }
+    put_u64(proof, 7);
+    for (const Fr& e : evals) put_fr(proof, e);
+    put_u64(proof, 3);
+    proof.push_back(0); proof.push_back(0); proof.push_back(0);  // three ProverMsg::EmptyMessage
+    put_u64(proof, 2);
+    g1_serialize(w_beta, proof);
+    proof.push_back(1);
+    put_fr(proof, rv_beta);
+    g1_serialize(w_gamma, proof);
+    proof.push_back(0);  // random_v = None
+    proof.push_back(0);  // BatchLCProof.evals = None
+    return ZK_OK;
+}
+
+}  // namespace zk

@@ -129,6 +129,29 @@ int zkaes_circuit_matrix(const zkaes_circuit* c, int which, uint32_t* row_ptr, u
 int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* c, const uint8_t* msg, size_t msg_len, const uint8_t key[16],
                              uint8_t* ct_out, uint8_t* assignment_out);
 
+/* ---- S1/S3 seam: keys and encrypt() ------------------------------------------------------------------------------
+ * zkaes_synthesize_keys stands in for `synthesize_keys(plaintext_length)` (src/lib.rs:138-174): test SRS from the two
+ * seeds (tau, gamma: INSECURE, like the reference's -- README.md:26), circuit shape, Marlin index, all left resident in
+ * HBM behind the opaque handle.  Unlike the reference's hard-coded bounds (src/lib.rs:141) the SRS is sized for the
+ * requested length.
+ * zkaes_encrypt stands in for `encrypt(message, secret_key, proving_key)` (src/lib.rs:60-114): witness generation and
+ * the Marlin proof.  `zk_seed32` seeds the prover's zero-knowledge randomness (the reference draws it from
+ * simpleworks::marlin::generate_rand(); an explicit seed makes runs reproducible).  ct_out receives msg_len bytes.
+ * proof_out may be NULL to query the size; *proof_len is in/out (capacity in, bytes written out).  The bytes are the
+ * ark-serialize 0.3.0 CanonicalSerialize form of ark_marlin::Proof (what `deserialize_proof`, src/lib.rs:52, reads).
+ * info[]: 0 msg_len, 1 num_constraints, 2 num_variables, 3-5 nnz(A,B,C), 6 |H|, 7 |K|, 8 |X|, 9 SRS max degree,
+ *         10 instance variables used. */
+typedef struct zkaes_pk zkaes_pk;
+#define ZKAES_PK_INFO_WORDS 11
+int zkaes_synthesize_keys(zkaes_ctx* ctx, size_t plaintext_len, const uint8_t tau_seed32[32], const uint8_t gamma_seed32[32], zkaes_pk** out);
+void zkaes_pk_free(zkaes_pk* pk);
+int zkaes_pk_info(const zkaes_pk* pk, uint64_t info[ZKAES_PK_INFO_WORDS]);
+/* Verifying-key bytes as they enter the Fiat-Shamir transcript: index info (3 x u64 LE) || 12 index commitments
+ * (ark-ff ToBytes of marlin_pc::Commitment, 195 bytes each).  out may be NULL to query the size. */
+int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len);
+int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed32[32],
+                  uint8_t* ct_out, uint8_t* proof_out, size_t* proof_len);
+
 #ifdef __cplusplus
 }
 #endif

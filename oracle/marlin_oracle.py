@@ -810,3 +810,123 @@ def verify(idx: Index, srs: SRS, public_input, proof) -> bool:
         if not (lhs == rhs).all():
             return False
     return True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Wire formats read back (ark-serialize 0.3.0 CanonicalDeserialize) + a verifier set-up that needs no indexer run
+# ---------------------------------------------------------------------------------------------------------------
+def _fq_sqrt(a: int):
+    """Tonelli-Shanks in Fq (q = 1 mod 2^46)"""
+    a %= Q
+    if a == 0:
+        return 0
+    if pow(a, (Q - 1) // 2, Q) != 1:
+        return None
+    s, t = 0, Q - 1
+    while t % 2 == 0:
+        s += 1
+        t //= 2
+    z = 2
+    while pow(z, (Q - 1) // 2, Q) != Q - 1:
+        z += 1
+    m, c, tt, r = s, pow(z, t, Q), pow(a, t, Q), pow(a, (t + 1) // 2, Q)
+    while tt != 1:
+        i, t2 = 0, tt
+        while t2 != 1:
+            t2 = t2 * t2 % Q
+            i += 1
+        b = pow(c, 1 << (m - i - 1), Q)
+        m, c = i, b * b % Q
+        tt, r = tt * c % Q, r * b % Q
+    return r
+
+
+def _xy_to_affine(x: int, y: int):
+    return np.concatenate([ints_to_limbs([x * RQ % Q], 6)[0], ints_to_limbs([y * RQ % Q], 6)[0]])
+
+
+def g1_deserialize_compressed(b: bytes):
+    assert len(b) == 48
+    flags = b[47] >> 6
+    if flags & 1:
+        return INF.copy()
+    x = int.from_bytes(b[:47] + bytes([b[47] & 0x3F]), "little")
+    y = _fq_sqrt((x * x * x + 1) % Q)  # BLS12-377 G1: y^2 = x^3 + 1
+    if y is None:
+        raise ValueError("not on the curve")
+    if (y > (Q - y) % Q) != bool(flags & 2):
+        y = (Q - y) % Q
+    return _xy_to_affine(x, y)
+
+
+def g1_from_bytes_uncompressed(b: bytes):
+    assert len(b) == 97
+    if b[96]:
+        return INF.copy()
+    return _xy_to_affine(int.from_bytes(b[:48], "little"), int.from_bytes(b[48:96], "little"))
+
+
+def deserialize_proof(data: bytes):
+    pos = 0
+
+    def u64():
+        nonlocal pos
+        v = struct.unpack_from("<Q", data, pos)[0]
+        pos += 8
+        return v
+
+    def take(n):
+        nonlocal pos
+        v = data[pos:pos + n]
+        pos += n
+        return v
+
+    rounds = []
+    for _ in range(u64()):
+        rnd = []
+        for _ in range(u64()):
+            comm = g1_deserialize_compressed(take(48))
+            shifted = g1_deserialize_compressed(take(48)) if take(1)[0] else None
+            rnd.append((comm, shifted))
+        rounds.append(rnd)
+    evaluations = [int.from_bytes(take(32), "little") for _ in range(u64())]
+    for _ in range(u64()):  # prover messages
+        if take(1)[0]:
+            for _ in range(u64()):
+                take(32)
+    pc = []
+    for _ in range(u64()):
+        w = g1_deserialize_compressed(take(48))
+        rv = int.from_bytes(take(32), "little") if take(1)[0] else None
+        pc.append({"w": w, "random_v": rv})
+    if take(1)[0]:
+        raise ValueError("unexpected BatchLCProof.evals")
+    assert pos == len(data), "trailing bytes"
+    return {"commitments": rounds, "evaluations": evaluations, "pc_proof": pc}
+
+
+def index_from_vk_bytes(vk: bytes, num_instance_padded: int) -> Index:
+    """Verifier-side index: sizes + the 12 index commitments, read from IndexVerifierKey's ToBytes form."""
+    nvar, ncons, nnz = struct.unpack_from("<QQQ", vk, 0)
+    comms = [g1_from_bytes_uncompressed(vk[24 + 195 * i: 24 + 195 * i + 97]) for i in range(12)]
+    dh, dk, dx = Domain(ncons), Domain(nnz), Domain(num_instance_padded)
+    idx = Index(nvar, ncons, nnz, num_instance_padded, [], [], [], {}, dh, dk, dx, ahp_max_degree(dh.size, dk.size), comms)
+    idx._vk_raw = vk
+    idx.vk_bytes = lambda: vk
+    return idx
+
+
+class SparseSRS:
+    """The handful of SRS elements the verifier touches, derived from the trapdoor (test SRS)."""
+
+    def __init__(self, max_degree: int, tau_seed: bytes, gamma_seed: bytes):
+        self.max_degree = max_degree
+        self.tau, self.gamma = seed_to_scalar(tau_seed), seed_to_scalar(gamma_seed)
+        self.powers_of_gamma_g = orc().g1_mul_gen(CURVE, ints_to_limbs([self.gamma], 4))
+        self._cache = {}
+        self.powers_of_g = self
+
+    def __getitem__(self, i: int):
+        if i not in self._cache:
+            self._cache[i] = orc().g1_mul_gen(CURVE, ints_to_limbs([pow(self.tau, i, P)], 4))[0]
+        return self._cache[i]

@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/marlin_proof_16B.json with the CPU oracle (oracle/marlin_oracle.py): index + proof for the
+reference's own end-to-end case (tests/integration_tests.rs:313-337: FIPS-197 key / plaintext) under fixed seeds.
+Takes ~2 minutes on 8 cores.  The GPU parity test compares the product's proof bytes with this fixture."""
+import hashlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import marlin_oracle as mo  # noqa: E402
+from oracle import r1cs_model as model  # noqa: E402
+
+KEY = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+MSG = bytes.fromhex("3243f6a8885a308d313198a2e0370734")
+TAU_SEED, GAMMA_SEED, ZK_SEED = bytes(range(32)), bytes(range(1, 33)), bytes([7] * 32)
+
+
+def main():
+    t0 = time.time()
+    cs, ct = model.synthesize(MSG, KEY)
+    A, B, C = cs.matrices()
+    r1cs = mo.R1CS(A, B, C, len(cs.inst_vals), len(cs.wit_vals))
+    idx0 = mo.index_r1cs(r1cs)
+    srs = mo.SRS.generate(idx0.max_degree, TAU_SEED, GAMMA_SEED)
+    idx = mo.index_r1cs(r1cs, srs)
+    proof, pb = mo.prove(idx, srs, r1cs, cs.inst_vals, cs.wit_vals, ZK_SEED)
+    pub = [(b >> i) & 1 for b in ct for i in range(8)]
+    assert mo.verify(idx, srs, pub, proof), "oracle verifier rejected the oracle proof"
+    bad = list(pub)
+    bad[9] ^= 1
+    assert not mo.verify(idx, srs, bad, proof), "oracle verifier accepted a wrong ciphertext"
+    out = {
+        "generator": "tools/gen_golden_proof.py (oracle/marlin_oracle.py; CPU restatement -- NOT output of the Rust reference)",
+        "message": MSG.hex(), "key": KEY.hex(), "ciphertext": ct.hex(),
+        "tau_seed": TAU_SEED.hex(), "gamma_seed": GAMMA_SEED.hex(), "zk_seed": ZK_SEED.hex(),
+        "h": idx.domain_h.size, "k": idx.domain_k.size, "x": idx.domain_x.size, "max_degree": idx.max_degree,
+        "vk_sha256": hashlib.sha256(idx.vk_bytes()).hexdigest(), "vk_len": len(idx.vk_bytes()),
+        "proof": pb.hex(),
+    }
+    path = os.path.join(ROOT, "tests", "golden", "marlin_proof_16B.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path, "in %.0f s" % (time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
