@@ -38,6 +38,8 @@ def _load():
         "zkaes_ctx_launches": (c_uint64, [vp]),
         "zkaes_ctx_sync": (c_int, [vp]),
         "zkaes_ctx_set_msm_window": (c_int, [vp, c_int]),
+        "zkaes_ctx_profile": (c_int, [vp, c_int]),
+        "zkaes_ctx_profile_read": (c_int, [vp, vp]),
         "zkaes_dev_alloc": (c_int, [vp, c_size_t, POINTER(vp)]),
         "zkaes_dev_free": (c_int, [vp, vp]),
         "zkaes_dev_upload": (c_int, [vp, vp, vp, c_size_t]),
@@ -135,6 +137,15 @@ class Context:
 
     def sync(self):
         self._check(lib().zkaes_ctx_sync(self._h))
+
+    def profile(self, enable: bool):
+        self._check(lib().zkaes_ctx_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """-> dict(launches, ms, terms, madds) of the MSM bucket-accumulation kernel since the last read"""
+        out = np.zeros(4, dtype=np.float64)
+        self._check(lib().zkaes_ctx_profile_read(self._h, _ptr(out)))
+        return {"launches": int(out[0]), "ms": float(out[1]), "terms": float(out[2]), "madds": float(out[3])}
 
     def set_msm_window(self, bits: int):
         self._check(lib().zkaes_ctx_set_msm_window(self._h, bits))

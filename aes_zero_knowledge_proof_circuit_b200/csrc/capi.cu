@@ -102,6 +102,32 @@ int zkaes_ctx_sync(zkaes_ctx* ctx) {
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZK_OK;
 }
+int zkaes_ctx_profile(zkaes_ctx* ctx, int enable) {
+    NEED_CTX(ctx);
+    ctx->prof = enable != 0;
+    return ZK_OK;
+}
+int zkaes_ctx_profile_read(zkaes_ctx* ctx, double out[4]) {
+    NEED_CTX(ctx);
+    if (!out) return fail(ctx, ZK_ERR_ARG, "profile_read: null pointer");
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0, terms = 0, madds = 0;
+    for (auto& sp : ctx->prof_spans) {
+        float t = 0;
+        cudaEventElapsedTime(&t, sp.e0, sp.e1);
+        ms += t;
+        terms += (double)sp.terms;
+        madds += (double)sp.madds;
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    out[0] = (double)ctx->prof_spans.size();
+    out[1] = ms;
+    out[2] = terms;
+    out[3] = madds;
+    ctx->prof_spans.clear();
+    return ZK_OK;
+}
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits) {
     NEED_CTX(ctx);
     if (window_bits < 0 || window_bits > 22 || window_bits == 1 || window_bits == 2) return fail(ctx, ZK_ERR_ARG, "window bits must be 0 or 3..22");

@@ -22,6 +22,14 @@ struct zkaes_ctx {
     std::map<uint64_t, void*> tables;
     // tuning knobs (0 = automatic)
     int msm_window_bits = 0;
+    // optional per-kernel timing of the dominant kernel (bench.py's roofline): CUDA events around every bucket
+    // accumulation launch, resolved by zkaes_ctx_profile_read
+    bool prof = false;
+    struct ProfSpan {
+        cudaEvent_t e0, e1;
+        uint64_t terms, madds;
+    };
+    std::vector<ProfSpan> prof_spans;
 };
 
 namespace zk {

@@ -114,7 +114,7 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
     if (i < n) out[i] += block_offsets[blockIdx.x];
 }
 
-static int exclusive_scan(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
+int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n) {
     cudaStream_t st = ctx->stream;
     uint32_t nblk = cdiv(n, SCAN_BS);
     if (nblk > SCAN_BS * SCAN_BS) return fail(ctx, ZK_ERR_UNSUPPORTED, "scan too large");
@@ -310,13 +310,13 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
                                                         nullptr);
         ctx->launches++;
-        ZK_TRY(exclusive_scan(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb));
+        ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb));
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
         k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
                                                         offsets.as<uint32_t>(), sorted.as<uint32_t>());
         k_msm_item_counts<<<cdiv(p.nb, 256), 256, 0, st>>>(counts.as<uint32_t>(), p.nb, S, items.as<uint32_t>());
         ctx->launches += 2;
-        ZK_TRY(exclusive_scan(ctx, items.as<uint32_t>(), item_off.as<uint32_t>(), p.nb));
+        ZK_TRY(exclusive_scan_u32(ctx, items.as<uint32_t>(), item_off.as<uint32_t>(), p.nb));
         // total item count = last offset + last count (tiny D2H; the launch below needs it for its grid)
         uint32_t tail[2];
         ZK_CUDA(ctx, cudaMemcpyAsync(&tail[0], item_off.as<uint32_t>() + (p.nb - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -325,10 +325,22 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         uint32_t n_items = tail[0] + tail[1];
         if (n_items > max_items) return fail(ctx, ZK_ERR_STATE, "msm: work-item count exceeds its bound");
         if (n_items) {
+            zkaes_ctx::ProfSpan span{};
+            if (ctx->prof) {
+                cudaEventCreate(&span.e0);
+                cudaEventCreate(&span.e1);
+                cudaEventRecord(span.e0, st);
+            }
             k_msm_accumulate<C><<<cdiv(n_items, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
                                                                    counts.as<uint32_t>(), item_off.as<uint32_t>(), p.nb, n_items, S,
                                                                    acc_partial.as<XYZZ<C>>());
             ctx->launches++;
+            if (ctx->prof) {
+                cudaEventRecord(span.e1, st);
+                span.terms = m;
+                span.madds = (uint64_t)m * p.W;  // upper bound: zero digits are skipped
+                ctx->prof_spans.push_back(span);
+            }
         }
         k_msm_merge<C><<<cdiv(p.nb, 128), 128, 0, st>>>(acc_partial.as<XYZZ<C>>(), item_off.as<uint32_t>(), items.as<uint32_t>(), p.nb,
                                                        buckets.as<XYZZ<C>>(), base == 0);

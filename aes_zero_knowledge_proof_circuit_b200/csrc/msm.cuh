@@ -23,6 +23,9 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
 template <class C>
 Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& p);
 
+// out[i] = sum_{j < i} in[j]  (n <= 2^30)
+int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n);
+
 // Whole MSM: device-resident bases / scalars -> affine result on the host (window sums on the device, Horner fold on the host).
 template <class C>
 int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out);

@@ -162,34 +162,59 @@ __global__ void k_divide_vanishing(const F* c, size_t len, size_t n, F* q, F* re
     }
     st_fr(rem + i, i < len ? acc + ld_fr(c + i) : acc);
 }
-__global__ void k_t_evals(F* out, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha, size_t nvar, size_t period,
-                          size_t x) {
+__device__ __forceinline__ size_t reindex_by_subdomain(size_t j, size_t period, size_t x) {  // EvaluationDomain::reindex_by_subdomain
+    if (j < x) return j * period;
+    size_t i = j - x;
+    return i + i / (period - 1) + 1;
+}
+__device__ __forceinline__ F t_term(const F& t, int v) {
+    if (v == 1) return t;
+    if (v == -1) return t.neg();
+    return mul_small(t, v);
+}
+// light columns: one thread per variable
+__global__ void __launch_bounds__(128) k_t_evals(F* out, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha,
+                                                 const uint8_t* __restrict__ heavy, size_t nvar, size_t period, size_t x) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nvar) return;
+    if (j >= nvar || heavy[j]) return;
     F tot = F::zero();
     const CscView* ms[3] = {&a, &b, &c};
     const F etas[3] = {eta_a, eta_b, eta_c};
 #pragma unroll
     for (int mi = 0; mi < 3; ++mi) {
         const CscView& m = *ms[mi];
+        const uint32_t lo = m.ptr[j], hi = m.ptr[j + 1];
+        if (hi == lo) continue;
         F s = F::zero();
-        for (uint32_t e = m.ptr[j]; e < m.ptr[j + 1]; ++e) {
-            F t = ld_fr(r_alpha + m.row[e]);
-            int v = m.coeff[e];
-            if (v == 1) s = s + t;
-            else if (v == -1) s = s - t;
-            else s = s + mul_small(t, v);
-        }
-        if (m.ptr[j + 1] > m.ptr[j]) tot = tot + s * etas[mi];
+        for (uint32_t e = lo; e < hi; ++e) s = s + t_term(ld_fr(r_alpha + m.row[e]), m.coeff[e]);
+        tot = tot + s * etas[mi];
     }
-    // EvaluationDomain::reindex_by_subdomain
-    size_t idx;
-    if (j < x) idx = j * period;
-    else {
-        size_t i = j - x;
-        idx = i + i / (period - 1) + 1;
+    st_fr(out + reindex_by_subdomain(j, period, x), tot);
+}
+// heavy columns (the constant one, key and round-key bits: touched by every ECB block): one CTA per variable
+__global__ void __launch_bounds__(256) k_t_evals_heavy(F* out, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha,
+                                                       const uint32_t* __restrict__ heavy_cols, size_t period, size_t x) {
+    __shared__ F sh[256];
+    const size_t j = heavy_cols[blockIdx.x];
+    F tot = F::zero();
+    const CscView* ms[3] = {&a, &b, &c};
+    const F etas[3] = {eta_a, eta_b, eta_c};
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi) {
+        const CscView& m = *ms[mi];
+        const uint32_t lo = m.ptr[j], hi = m.ptr[j + 1];
+        if (hi == lo) continue;
+        F s = F::zero();
+        for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) s = s + t_term(ld_fr(r_alpha + m.row[e]), m.coeff[e]);
+        tot = tot + s * etas[mi];
     }
-    st_fr(out + idx, tot);
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fr(out + reindex_by_subdomain(j, period, x), sh[0]);
 }
 __global__ void k_round2(F* out, const F* ra, const F* za, const F* zb, const F* t, const F* z, F eta_a, F eta_b, F eta_c, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,6 +286,7 @@ __global__ void k_z_poly(F* out, const F* w, size_t len_w, const F* xp, size_t x
     if (i < x) v = v + ld_fr(xp + i);
     st_fr(out + i, v);
 }
+__global__ void k_mask_fix(F* c, size_t n) { st_fr(c, (ld_fr(c + n) + ld_fr(c + 2 * n)).neg()); }
 __global__ void k_bits_to_fr(F* out, const uint8_t* bits, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_fr(out + i, bits[i] ? F::one() : F::zero());
@@ -320,9 +346,15 @@ int po_divide_vanishing(zkaes_ctx* ctx, const F* c, size_t len, size_t n, F* q, 
     LAUNCH(ctx, k_divide_vanishing, n, TB, c, len, n, q, rem);
     return ZK_OK;
 }
-int po_t_evals(zkaes_ctx* ctx, F* out, const CscView m[3], const F eta[3], const F* r_alpha, size_t nvar, size_t h, size_t x) {
+int po_t_evals(zkaes_ctx* ctx, F* out, const CscView m[3], const F eta[3], const F* r_alpha, const uint8_t* heavy_flag,
+               const uint32_t* heavy_cols, size_t n_heavy, size_t nvar, size_t h, size_t x) {
     ZK_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(F) * h, ctx->stream));
-    LAUNCH(ctx, k_t_evals, nvar, 128, out, m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, nvar, h / x, x);
+    LAUNCH(ctx, k_t_evals, nvar, 128, out, m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, heavy_flag, nvar, h / x, x);
+    if (n_heavy) {
+        k_t_evals_heavy<<<(unsigned)n_heavy, 256, 0, ctx->stream>>>(out, m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, heavy_cols, h / x, x);
+        ctx->launches++;
+        ZK_CUDA(ctx, cudaGetLastError());
+    }
     return ZK_OK;
 }
 int po_round2(zkaes_ctx* ctx, F* out, const F* ra, const F* za, const F* zb, const F* t, const F* z, const F eta[3], size_t n) {
@@ -405,6 +437,12 @@ int po_div_linear(zkaes_ctx* ctx, const F* c, size_t n, const F& z, F* q) {
 }
 int po_z_poly(zkaes_ctx* ctx, F* out, const F* w, size_t len_w, const F* x_poly, size_t x) {
     LAUNCH(ctx, k_z_poly, len_w + x, TB, out, w, len_w, x_poly, x);
+    return ZK_OK;
+}
+int po_mask_fix(zkaes_ctx* ctx, F* c, size_t n) {
+    k_mask_fix<<<1, 1, 0, ctx->stream>>>(c, n);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
     return ZK_OK;
 }
 int po_bits_to_fr(zkaes_ctx* ctx, F* out, const uint8_t* bits, size_t n) { LAUNCH(ctx, k_bits_to_fr, n, TB, out, bits, n); return ZK_OK; }

@@ -47,7 +47,9 @@ struct CscView {
     const uint32_t* row;
     const int8_t* coeff;
 };
-int po_t_evals(zkaes_ctx* ctx, FrS* out, const CscView m[3], const FrS eta[3], const FrS* r_alpha, size_t nvar, size_t h, size_t x);
+// Columns with many entries (heavy_flag[j] != 0, listed in heavy_cols) get one CTA each instead of one thread.
+int po_t_evals(zkaes_ctx* ctx, FrS* out, const CscView m[3], const FrS eta[3], const FrS* r_alpha, const uint8_t* heavy_flag,
+               const uint32_t* heavy_cols, size_t n_heavy, size_t nvar, size_t h, size_t x);
 // out = ra * (eta_a * za + eta_b * zb + eta_c * za * zb) - t * z
 int po_round2(zkaes_ctx* ctx, FrS* out, const FrS* ra, const FrS* za, const FrS* zb, const FrS* t, const FrS* z, const FrS eta[3], size_t n);
 // den = ab - alpha * row - beta * col + rc   (in place into row)
@@ -61,6 +63,8 @@ int po_eval(zkaes_ctx* ctx, const FrS* coeffs, size_t n, const FrS& x, FrS* out_
 int po_div_linear(zkaes_ctx* ctx, const FrS* c, size_t n, const FrS& z, FrS* q);
 // z(X) = w(X) * (X^x - 1) + x_poly(X): out has len_w + x entries
 int po_z_poly(zkaes_ctx* ctx, FrS* out, const FrS* w, size_t len_w, const FrS* x_poly, size_t x);
+// c[0] = -(c[n] + c[2n])   (mask polynomial: make the sum over H vanish)
+int po_mask_fix(zkaes_ctx* ctx, FrS* c, size_t n);
 // bits (one byte each) -> Montgomery 0 / 1
 int po_bits_to_fr(zkaes_ctx* ctx, FrS* out, const uint8_t* bits, size_t n);
 

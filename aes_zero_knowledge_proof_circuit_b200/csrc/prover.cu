@@ -12,6 +12,9 @@
 #include "prover.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <thread>
 
@@ -187,6 +190,21 @@ struct Blind {
     }
 };
 
+// ZKAES_TRACE=1: wall-clock per prover phase on stderr (development aid; synchronises the stream at phase boundaries)
+struct PhaseTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTrace(cudaStream_t s) : on(getenv("ZKAES_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[zkaes] %-28s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 template <class T>
 cudaError_t dev_upload(T** dst, const std::vector<T>& src, cudaStream_t st) {
     cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(src.size() * sizeof(T), 16));
@@ -208,6 +226,9 @@ struct zkaes_pk_impl {
     int8_t* csc_cf[3] = {};
     uint32_t *krow[3] = {}, *kcol[3] = {};
     int8_t* kcoef[3] = {};
+    uint8_t* heavy_flag = nullptr;  // per variable: column has > HEAVY_COL entries over A, B, C
+    uint32_t* heavy_cols = nullptr;
+    size_t n_heavy = 0;
     Fr* elems_h = nullptr;
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
     Aff* srs = nullptr;     // tau^i G, i <= D
@@ -223,10 +244,14 @@ struct zkaes_pk_impl {
         }
         for (int i = 0; i < 12; ++i) cudaFree(idx_poly[i]);
         cudaFree(elems_h);
+        cudaFree(heavy_flag);
+        cudaFree(heavy_cols);
         cudaFree(srs);
         witness_free(wit);
     }
 };
+
+int fr_rand_device(zkaes_ctx* ctx, ChaCha20Rng& rng, FrS* out, size_t count);  // rng.cu
 
 namespace {
 
@@ -258,62 +283,6 @@ int pc_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t 
     out->comm.has_shifted = bound >= 0;
     if (bound >= 0) ZK_TRY(kzg_commit(ctx, pk, coeffs, n, pk.D - (size_t)bound, hiding, zk, &out->comm.shifted, &out->shifted_rand));
     return ZK_OK;
-}
-
-// DensePolynomial::rand(3|H| + 2 zk - 3) from the zk rng, generated by several host threads (ChaCha is counter based) and
-// compacted in stream order: identical to sequential Fr::rand draws.
-void sample_mask(ChaCha20Rng& zk, size_t count, std::vector<Fr>& out) {
-    out.resize(count);
-    size_t have = 0;
-    constexpr int shave = 256 - Fr377Params::BITS;
-    uint64_t mod[4];
-    for (int i = 0; i < 4; ++i) mod[i] = (uint64_t)Fr377Params::MOD(2 * i) | ((uint64_t)Fr377Params::MOD(2 * i + 1) << 32);
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    while (have < count) {
-        size_t need = count - have;
-        size_t cand = need * 2 + 64;  // acceptance is ~0.58
-        cand = (cand + 1) & ~(size_t)1;  // whole ChaCha blocks hold two candidates (8 u64)
-        if (zk.pos & 7) {  // not block aligned (only after scalar draws): fall back to aligning through single draws
-            out[have++] = fr_rand(zk);
-            continue;
-        }
-        std::vector<uint64_t> buf(cand * 4);
-        std::vector<uint8_t> ok(cand);
-        uint64_t blk0 = zk.pos >> 3;
-        auto work = [&](size_t lo, size_t hi) {
-            uint32_t w[16];
-            for (size_t b = lo; b < hi; ++b) {  // block b holds candidates 2b, 2b+1
-                chacha20_block(zk.key, blk0 + b, w);
-                for (int c = 0; c < 2; ++c) {
-                    uint64_t* o = &buf[(2 * b + c) * 4];
-                    for (int i = 0; i < 4; ++i) o[i] = (uint64_t)w[8 * c + 2 * i] | ((uint64_t)w[8 * c + 2 * i + 1] << 32);
-                    o[3] &= ~0ull >> shave;
-                    bool lt = false;
-                    for (int i = 3; i >= 0; --i)
-                        if (o[i] != mod[i]) {
-                            lt = o[i] < mod[i];
-                            break;
-                        }
-                    ok[2 * b + c] = lt;
-                }
-            }
-        };
-        size_t nblk = cand / 2;
-        std::vector<std::thread> th;
-        size_t per = (nblk + nt - 1) / nt;
-        for (unsigned t = 0; t < nt; ++t) {
-            size_t lo = t * per, hi = std::min(nblk, lo + per);
-            if (lo < hi) th.emplace_back(work, lo, hi);
-        }
-        for (auto& t : th) t.join();
-        size_t used = 0;
-        for (size_t c = 0; c < cand && have < count; ++c) {
-            used = c + 1;
-            if (ok[c]) memcpy(out[have++].v, &buf[c * 4], 32);
-        }
-        zk.pos += used * 4;
-        zk.cur_block = ~0ull;
-    }
 }
 
 }  // namespace
@@ -364,8 +333,10 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         return (uint32_t)(i + i / (period - 1) + 1);
     };
     const size_t nvar = (size_t)c.num_instance + c.num_witness;
+    std::vector<uint32_t> col_total(nvar, 0);
     for (int m = 0; m < 3; ++m) {
         const CsrMatrix& A = *M[m];
+        for (uint32_t cc : A.col) col_total[cc]++;
         ZK_CUDA(ctx, dev_upload(&pk.csr_ptr[m], A.row_ptr, st));
         ZK_CUDA(ctx, dev_upload(&pk.csr_col[m], A.col, st));
         ZK_CUDA(ctx, dev_upload(&pk.csr_cf[m], A.coeff, st));
@@ -393,6 +364,20 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         ZK_CUDA(ctx, dev_upload(&pk.kcol[m], kcol, st));
         ZK_CUDA(ctx, dev_upload(&pk.kcoef[m], kcf, st));
         ZK_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
+    }
+    {
+        constexpr uint32_t HEAVY_COL = 128;
+        std::vector<uint8_t> flag(nvar, 0);
+        std::vector<uint32_t> cols;
+        for (size_t j = 0; j < nvar; ++j)
+            if (col_total[j] > HEAVY_COL) {
+                flag[j] = 1;
+                cols.push_back((uint32_t)j);
+            }
+        pk.n_heavy = cols.size();
+        ZK_CUDA(ctx, dev_upload(&pk.heavy_flag, flag, st));
+        ZK_CUDA(ctx, dev_upload(&pk.heavy_cols, cols, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
     }
     ZK_TRY(witness_upload(ctx, c, pk.wit));
 
@@ -449,6 +434,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const size_t h = pk.h, k = pk.k, x = pk.x, D = pk.D;
     const size_t nvar = (size_t)c.num_instance + c.num_witness;
     ChaCha20Rng zk(zk_seed);
+    PhaseTrace tr(st);
 
     // ---- K1: witness ---------------------------------------------------------------------------------------------------
     DevBuf dmsg, dkey, dz, dct;
@@ -463,6 +449,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     const uint8_t* z = dz.as<uint8_t>();
 
+    tr.mark("witness");
     // ---- Fiat-Shamir seed: protocol name || index vk || public input (unformatted: without the leading one, zero padded)
     std::vector<uint8_t> seed(pk.vk_bytes.size() + 11 + 32 * (x - 1));
     memcpy(seed.data(), "MARLIN-2019", 11);
@@ -474,6 +461,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     }
     FiatShamirRng fs(seed);
 
+    tr.mark("fs seed");
     // ---- first round -----------------------------------------------------------------------------------------------------
     DevBuf x_poly, x_evals, wbuf, w_poly, za, zb, mask, rem;
     ZK_CUDA(ctx, x_poly.alloc(sizeof(Fr) * x, st));
@@ -506,13 +494,13 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         ZK_CUDA(ctx, cudaMemsetAsync(p + h, 0, sizeof(Fr), st));
         ZK_TRY(po_add_vanishing(ctx, p, h, r_ab[m]));
     }
+    tr.mark("r1: w, z_a, z_b polys");
     // mask polynomial: degree 3|H| + 2 zk - 3; force sum over H to zero by fixing the constant term
     const size_t len_mask = 3 * h;
-    std::vector<Fr> mask_h;
-    sample_mask(zk, len_mask, mask_h);
-    mask_h[0] = (mask_h[h] + mask_h[2 * h]).neg();
     ZK_CUDA(ctx, mask.alloc(sizeof(Fr) * len_mask, st));
-    ZK_CUDA(ctx, cudaMemcpyAsync(mask.p, mask_h.data(), sizeof(Fr) * len_mask, cudaMemcpyHostToDevice, st));
+    ZK_TRY(fr_rand_device(ctx, zk, mask.as<Fr>(), len_mask));
+    ZK_TRY(po_mask_fix(ctx, mask.as<Fr>(), h));  // mask[0] = -(mask[|H|] + mask[2|H|])
+    tr.mark("r1: mask sample+upload");
     Committed c_w, c_za, c_zb, c_mask;
     ZK_TRY(pc_commit(ctx, pk, w_poly.as<Fr>(), len_w, -1, true, zk, &c_w));
     ZK_TRY(pc_commit(ctx, pk, za.as<Fr>(), h + 1, -1, true, zk, &c_za));
@@ -523,6 +511,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         for (const Committed* cm : {&c_w, &c_za, &c_zb, &c_mask}) comm_to_bytes(cm->comm, b);
         fs.absorb(b);
     }
+    tr.mark("r1: 4 commitments");
     Fr alpha = sample_outside_domain(fs.rng, h);
     Fr eta[3] = {fr_rand(fs.rng), fr_rand(fs.rng), fr_rand(fs.rng)};
 
@@ -538,11 +527,12 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, tpoly.alloc(sizeof(Fr) * h, st));
     CscView csc[3];
     for (int m = 0; m < 3; ++m) csc[m] = CscView{pk.csc_ptr[m], pk.csc_row[m], pk.csc_cf[m]};
-    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), nvar, h, x));
+    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), pk.heavy_flag, pk.heavy_cols, pk.n_heavy, nvar, h, x));
     ZK_TRY(ntt(ctx, tpoly.as<Fr>(), pk.log_h, true, false));
     ZK_TRY(ntt(ctx, ra.as<Fr>(), pk.log_h, true, false));  // r_alpha polynomial
     ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));
     ZK_TRY(po_z_poly(ctx, zpoly.as<Fr>(), w_poly.as<Fr>(), len_w, x_poly.as<Fr>(), x));
+    tr.mark("r2: r_alpha, t, z polys");
     // products on the 4|H| domain
     const size_t n4 = 4 * h;
     const int log4h = pk.log_h + 2;
@@ -571,6 +561,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     e_ra.release();
     const Fr* g1 = xg1.as<Fr>() + 1;  // q_1 = h_1 v_H + X g_1
     const size_t len_g1 = h - 1, len_h1 = 2 * h + 1;
+    tr.mark("r2: products + division");
     Committed c_t, c_g1, c_h1;
     ZK_TRY(pc_commit(ctx, pk, tpoly.as<Fr>(), h, -1, false, zk, &c_t));
     ZK_TRY(pc_commit(ctx, pk, g1, len_g1, (long)(h - 2), true, zk, &c_g1));
@@ -580,6 +571,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         for (const Committed* cm : {&c_t, &c_g1, &c_h1}) comm_to_bytes(cm->comm, b);
         fs.absorb(b);
     }
+    tr.mark("r2: 3 commitments");
     Fr beta = sample_outside_domain(fs.rng, h);
 
     // ---- third round -------------------------------------------------------------------------------------------------------
@@ -600,6 +592,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_TRY(ntt(ctx, fpoly.as<Fr>(), pk.log_k, true, false));
     const Fr* g2 = fpoly.as<Fr>() + 1;  // f = X g_2 + t(beta) / |K|
     const size_t len_g2 = k - 1;
+    tr.mark("r3: f");
     // h_2 = (a - b f) / v_K on the coset g * B, |B| = 4|K|
     const size_t k4 = 4 * k;
     const int log4k = pk.log_k + 2;
@@ -640,6 +633,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     f4.release();
     ZK_TRY(ntt(ctx, h2, log4k, true, true));
     const size_t len_h2 = 3 * k - 3;
+    tr.mark("r3: h_2 on the coset");
     Committed c_g2, c_h2;
     ZK_TRY(pc_commit(ctx, pk, g2, len_g2, (long)(k - 2), false, zk, &c_g2));
     ZK_TRY(pc_commit(ctx, pk, h2, len_h2, -1, false, zk, &c_h2));
@@ -648,6 +642,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         for (const Committed* cm : {&c_g2, &c_h2}) comm_to_bytes(cm->comm, b);
         fs.absorb(b);
     }
+    tr.mark("r3: 2 commitments");
     Fr gamma = fr_rand(fs.rng);
 
     // ---- evaluations (sorted by label: a_denom b_denom c_denom g_1 g_2 t z_b) ---------------------------------------------
@@ -675,6 +670,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     chp[0] = Fr::one();
     for (int i = 1; i < 6; ++i) chp[i] = chp[i - 1] * ch;
 
+    tr.mark("evaluations");
     // ---- openings (marlin_pc open_combinations -> batch_open per query point) ------------------------------------------
     // beta: g_1 [ch^0, shifted ch^1], outer_sumcheck [ch^2], t [ch^3], z_b [ch^4]
     Aff w_beta, w_gamma;
@@ -717,6 +713,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         w_beta = g1_add(w_beta, g1_mul(sw, chp[1]));
         rv_beta = rv_beta + chp[1] * c_g1.shifted_rand.eval(beta);
     }
+    tr.mark("opening at beta");
     // gamma: a_denom [ch^0], b_denom [ch^1], c_denom [ch^2], g_2 [ch^3, shifted ch^4], inner_sumcheck [ch^5]; nothing is hiding
     {
         const Fr vk_gamma = vanishing(gamma, k);
@@ -743,6 +740,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     }
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
 
+    tr.mark("opening at gamma");
     // ---- ark-serialize 0.3.0 CanonicalSerialize of ark_marlin::Proof ----------------------------------------------------------
     proof.clear();
     put_u64(proof, 3);

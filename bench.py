@@ -1,18 +1,23 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the B200-native prover path (contract: see the task's bench section).
+"""bench.py -- headline benchmark of the B200-native prover path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--msg-len BYTES] [--workload prove|msm] [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input.  For N > 1 the driver launches this file
-under torch.distributed.run (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+Metric (BASELINE.json): encrypt() prove time and constraints/s.  One "step" = one encrypt(): AES-128-ECB witness
+generation + Marlin proof of one synthetic message through the C ABI (host buffers in, ciphertext + proof bytes out).
+The proving key (test SRS, matrices, index polynomials) is resident in HBM before the timed region, exactly as the
+reference passes an already-synthesised ProvingKey to encrypt() (src/lib.rs:60-64).
 
-Workloads (config.workload):
-  msm22   : one BLS12-377 G1 MSM of 2^22 terms (BASELINE.json configs[4] sweep point named by north_star's
-            "2^22-point MSM" target).  Bases = test-SRS powers tau^i*G resident in HBM, scalars uniform in [0, r).
-            N > 1: bases/scalars sharded by point range, per-rank window sums all-gathered over NCCL, folded.
-The `value` leg times the device-resident call; the `e2e` leg times the host-buffer C-ABI call (pinned host inputs,
-H2D inside the timed region, 96-byte result back).  `cpu_baseline` / `--impl reference` time the CPU oracle
-(oracle/liboracle.so: restatement of ark-ec 0.3.0's Pippenger with all host threads) on a bounded sample.
+    value        constraints/s, timed with CUDA events on the library's stream (host orchestration between kernels included)
+    e2e          the same metric by wall clock around the C-ABI call: message + key H2D and ciphertext + proof D2H inside
+    roofline     the dominant kernel, the MSM bucket accumulation (k_msm_accumulate): bracketed by CUDA events inside the
+                 library during the timed steps; achieved = 128 B x MSM terms / kernel time
+    cpu_baseline the CPU oracle's Marlin prover (oracle/marlin_oracle.py, restating ark-marlin 0.3.0 over the oracle's
+                 C++ MSM/NTT with all host threads) on a bounded sample: the first 2^14 constraints of the same R1CS
+--impl reference times that CPU prover on the same sample, one proof per step (the reference itself is Rust with
+un-vendored crates; this image has no cargo, so the oracle port is the only CPU implementation of the path here).
+
+--workload msm: one 2^log_n-term BLS12-377 G1 MSM per step (BASELINE.json configs[4] sweep), N > 1 shards by point range.
 """
 import argparse
 import json
@@ -29,14 +34,13 @@ sys.path.insert(0, ROOT)
 
 CURVE = 377
 FR_BITS = 253
-SEED_TAU = bytes(range(32))
+SEED_TAU, SEED_GAMMA, SEED_ZK = bytes(range(32)), bytes(range(1, 33)), bytes([7] * 32)
+AES_KEY = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")  # FIPS-197 (SURVEY.md 8(d) synthetic inputs)
+MADD_PEAK_PER_S = 2.48e9  # XYZZ += affine on one B200, tools/ubench.cu (profiles/ubench_r1.txt)
 
 
-# ------------------------------------------------------------------------------------------------------------
-def msm_fq_mul_count(n, c, W):
-    """Algorithmic field multiplications of the bucket method: n*W mixed adds (10 Fq mul each) +
-    2 * 2^(c-1) * W full adds for the running-sum reduction (14 each) + (W-1)*c doublings (9 each)."""
-    return n * W * 10 + 2 * (1 << (c - 1)) * W * 14 + (W - 1) * c * 9
+def synth_message(n):
+    return bytes((i * 131 + 7) & 0xFF for i in range(n))
 
 
 def load_peaks():
@@ -96,110 +100,186 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def synth_scalars_host(n, seed):
-    from tests.oracle_lib import rand_fr
-
-    return rand_fr(np.random.default_rng(seed), CURVE, n)
-
-
-def cpu_msm_sample(log_n, threads=None):
-    """Time the CPU oracle (ark-ec 0.3.0 Pippenger restatement) on 2^log_n terms.  Returns (seconds, cores)."""
-    from tests.oracle_lib import Oracle
-
-    orc = Oracle()
-    if threads:
-        orc.lib.orc_set_threads(threads)
-    n = 1 << log_n
-    bases = orc.g1_walk(CURVE, 12345, 7, n)
-    scalars = synth_scalars_host(n, 99)
-    orc.g1_msm(CURVE, bases[:1024], scalars[:1024])  # warm
-    t0 = time.perf_counter()
-    orc.g1_msm(CURVE, bases, scalars)
-    return time.perf_counter() - t0, orc.threads()
+# CPU side: the oracle prover on a bounded sample of the same R1CS
+# ------------------------------------------------------------------------------------------------------------
+SAMPLE_LOG_CONSTRAINTS = 14
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path.  The reference is Rust with un-vendored crates and this image has no
-    cargo, so this is the CPU restatement (oracle port), all host threads, on a bounded sample of the workload."""
+class CpuSample:
+    """First 2^14 constraints of the 16-byte AES R1CS (every constraint only touches earlier variables, so the prefix
+    with the real wire values is a satisfied R1CS of its own), indexed once; each prove() is one full Marlin proof."""
+
+    def __init__(self):
+        from oracle import marlin_oracle as mo
+        from oracle import r1cs_model as model
+
+        self.mo = mo
+        cs, _ = model.synthesize(bytes.fromhex("3243f6a8885a308d313198a2e0370734"), AES_KEY)
+        n = 1 << SAMPLE_LOG_CONSTRAINTS
+        A, B, C = cs.matrices()
+        ninst = len(cs.inst_vals)
+        A, B, C = A[:n], B[:n], C[:n]
+        top = max(c for m in (A, B, C) for row in m for c, _ in row)
+        nwit = top - ninst + 1
+        # only the constant-one instance variable is referenced by the prefix: renumber witnesses down to column 1..
+        shift = ninst - 1
+        fix = lambda m: [[(c - shift if c >= ninst else c, v) for c, v in row] for row in m]
+        assert all(c == 0 or c >= ninst for m in (A, B, C) for row in m for c, _ in row)
+        self.r1cs = mo.R1CS(fix(A), fix(B), fix(C), 1, nwit)
+        self.inst, self.wit = [1], list(cs.wit_vals[:nwit])
+        self.n_constraints = n
+        idx0 = mo.index_r1cs(self.r1cs)
+        self.srs = mo.SRS.generate(idx0.max_degree, SEED_TAU, SEED_GAMMA)
+        self.idx = mo.index_r1cs(self.r1cs, self.srs)
+        self.cores = mo.orc().threads()
+
+    def prove(self):
+        t0 = time.perf_counter()
+        _, pb = self.mo.prove(self.idx, self.srs, self.r1cs, self.inst, self.wit, SEED_ZK)
+        return time.perf_counter() - t0, pb
+
+    def describe(self):
+        return (f"one Marlin proof of the first 2^{SAMPLE_LOG_CONSTRAINTS} constraints of the AES-128 R1CS (|H|={self.idx.domain_h.size}, "
+                f"|K|={self.idx.domain_k.size}); CPU restatement of ark-marlin 0.3.0 (oracle port), std::thread MSM/NTT on all cores")
+
+
+def run_reference(args, rank):
     if rank != 0:
         return
-    log_n = 18
+    s = CpuSample()
     times = []
     for i in range(args.warmup + args.steps):
-        dt, cores = cpu_msm_sample(log_n)
+        dt, _ = s.prove()
         if i >= args.warmup:
             times.append(dt)
     dt = float(np.mean(times))
-    val = (1 << log_n) / dt
+    val = s.n_constraints / dt
     line = {
-        "impl": "reference", "metric": "msm_terms_per_s", "value": val, "unit": "G1 terms/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64x6 Montgomery (Fq, 377-bit)", "data": "synthetic",
-        "config": {"workload": "msm22", "curve": "BLS12-377", "log_n": 22},
-        "cpu_baseline": {"value": val, "unit": "G1 terms/s", "cores": cores, "kind": "port",
-                         "sample": f"one 2^{log_n}-term MSM per step (CPU restatement of ark-ec 0.3.0 Pippenger, std::thread over windows)"},
-        "e2e": {"value": val, "unit": "G1 terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "encrypt_prove_constraints_per_s", "value": val, "unit": "constraints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64x4 / u64x6 Montgomery (BLS12-377 Fr / Fq integers)", "data": "synthetic",
+        "config": {"workload": f"encrypt() prove, {args.msg_len}-byte message, AES-128-ECB R1CS, Marlin/BLS12-377", "msg_len": args.msg_len},
+        "cpu_baseline": {"value": val, "unit": "constraints/s", "cores": s.cores, "kind": "port", "sample": s.describe()},
+        "e2e": {"value": val, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="msm22")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log-n", type=int, default=22)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+def bench_prove(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
     import aes_zero_knowledge_proof_circuit_b200 as zk
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the prover path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = zk.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream)
+    msg_len = args.msg_len
+    msg = synth_message(msg_len)
+    t0 = time.perf_counter()
+    pk = ctx.synthesize_keys(msg_len, SEED_TAU, SEED_GAMMA)
+    setup_s = time.perf_counter() - t0
+    n_constraints = pk.info["num_constraints"]
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    for _ in range(args.warmup):
+        ct, proof = ctx.encrypt(pk, msg, AES_KEY, SEED_ZK)
+    barrier()
+    l0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    ctx.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ct, proof = ctx.encrypt(pk, msg, AES_KEY, SEED_ZK)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - l0
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        pk.close()
+        return None
+    ms_per_step = dev_ms / args.steps
+    e2e_ms = wall_ms / args.steps
+    # N independent replicas prove N messages per step (the prover is not sharded across GPUs yet: DESIGN.md, multi-GPU)
+    units = n_constraints * world
+    peak, peak_src = load_peaks()
+    acc_ms = prof["ms"] / max(prof["launches"], 1)
+    alg_bytes = 128.0 * prof["terms"] / max(prof["launches"], 1)
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    line = {
+        "metric": "encrypt_prove_constraints_per_s", "value": units / (ms_per_step * 1e-3), "unit": "constraints/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "dtype": "u32x8 / u32x12 Montgomery (BLS12-377 Fr / Fq integers)", "data": "synthetic",
+        "config": {"workload": f"encrypt() prove, {msg_len}-byte message ({msg_len // 16} ECB blocks), AES-128-ECB R1CS, Marlin/BLS12-377",
+                   "msg_len": msg_len, "constraints": n_constraints, "H": pk.info["h"], "K": pk.info["k"], "srs_points": pk.info["max_degree"] + 1,
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one proof per GPU per step)",
+                   "cache": "per-step working set (index polynomials + SRS + round buffers) exceeds the 126 MB L2; no flush needed",
+                   "key_setup_s": setup_s, "proof_bytes": len(proof)},
+        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate (MSM bucket accumulation, XYZZ += affine)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "launches_per_step": prof["launches"] / args.steps, "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "share_of_step": prof["ms"] / dev_ms if dev_ms else None,
+                     "alu": {"madds_per_s": prof["madds"] / (prof["ms"] * 1e-3) if prof["ms"] else 0.0, "madd_peak_per_s": MADD_PEAK_PER_S,
+                             "frac": (prof["madds"] / (prof["ms"] * 1e-3) / MADD_PEAK_PER_S) if prof["ms"] else 0.0,
+                             "note": "the kernel is integer-ALU bound (10 Fq products per mixed addition); the HBM fraction is reported as the contract asks"}},
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "constraints/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": msg_len + 16 + 32,
+                "d2h_bytes_per_step": msg_len + len(proof)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    pk.close()
+    return line
+
+
+def bench_msm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import aes_zero_knowledge_proof_circuit_b200 as zk
+    from oracle.cpu import rand_fr
+
+    ctx = zk.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream)
     log_n = args.log_n
     n_total = 1 << log_n
     n_local = n_total // world
     lo = rank * n_local
-    # ---- resident inputs: this rank's point range of the test SRS and of the scalar vector --------------------
     all_bases = torch.empty(n_total * 96, dtype=torch.uint8, device="cuda")
     ctx.srs_powers_device(CURVE, SEED_TAU, n_total, all_bases)
     ctx.sync()
     bases = all_bases[lo * 96:(lo + n_local) * 96].clone()
     del all_bases
-    scal_host_full = synth_scalars_host(n_total, 2024)
-    scal_host = np.ascontiguousarray(scal_host_full[lo:lo + n_local])
+    scal_host = np.ascontiguousarray(rand_fr(np.random.default_rng(2024), CURVE, n_total)[lo:lo + n_local])
     scalars = torch.from_numpy(scal_host.view(np.int64)).cuda()
     wbytes = ctx.msm_g1_windows_bytes(CURVE, n_total)
     win = torch.zeros(wbytes, dtype=torch.uint8, device="cuda")
     gathered = torch.zeros(world * wbytes, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
-    def step_device():
+    def step():
         ctx.msm_g1_windows(CURVE, bases, scalars, n_local, n_total, win)
         if world > 1:
-            ctx.sync()  # the library's stream -> torch's stream hand-off
+            ctx.sync()
             dist.all_gather_into_tensor(gathered, win)
             torch.cuda.synchronize()
             return ctx.msm_g1_fold(CURVE, gathered, world, n_total)
@@ -211,108 +291,85 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
-    # ---- device-resident leg ---------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        res = step_device()
+        step()
     barrier()
     l0 = ctx.launches
+    ctx.profile(True)
+    ctx.profile_read()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record(stream)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = step_device()
-    e1.record(stream)
-    e1.synchronize()
+        step()
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    dev_ms = e0.elapsed_time(e1)
+    ms = (time.perf_counter() - t0) * 1e3
+    prof = ctx.profile_read()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches - l0
-    ms = max(dev_ms, 0.0)
-    # multi-GPU steps hop between the library's stream and torch's: use the wall clock between the device-synchronised
-    # barriers there (it bounds the event time from above)
     if world > 1:
-        ms = wall_ms
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per_step = ms / args.steps
-
-    # ---- dominant kernel alone (roofline) -- the bucket accumulation, timed with events on the library's stream ----
-    # measured through the windows call minus nothing: we time the whole windows pipeline and report the accumulate
-    # share from the committed ncu launch list (profiles/); achieved is computed on the whole device-side MSM.
-    for _ in range(2):
-        ctx.msm_g1_windows(CURVE, bases, scalars, n_local, n_total, win)
-    ctx.sync()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    for _ in range(args.steps):
-        ctx.msm_g1_windows(CURVE, bases, scalars, n_local, n_total, win)
-    k1.record(stream)
-    k1.synchronize()
-    win_ms = k0.elapsed_time(k1) / args.steps
-
-    # ---- e2e leg: host buffers through the C ABI (H2D of bases+scalars inside the timed region) ------------------
-    e2e = None
-    if world == 1:
-        hb = torch.empty(n_total * 96, dtype=torch.uint8).pin_memory()
-        hb.copy_(bases.cpu())
-        hs = torch.from_numpy(scal_host.view(np.int64)).pin_memory()
-        hb_np = hb.numpy().view(np.uint64).reshape(n_total, 12)
-        hs_np = hs.numpy().view(np.uint64).reshape(n_total, 4)
-        for _ in range(2):
-            r2 = ctx.msm_g1(CURVE, hb_np, hs_np)
-        ctx.sync()
-        t0 = time.perf_counter()
-        e2e_steps = max(3, args.steps // 2)
-        for _ in range(e2e_steps):
-            r2 = ctx.msm_g1(CURVE, hb_np, hs_np)
-        ctx.sync()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        assert (r2 == res).all(), "host-buffer and device-resident MSM disagree"
-        e2e = {"value": n_total / (e2e_ms * 1e-3), "unit": "G1 terms/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": n_total * 128, "d2h_bytes_per_step": 96 + 192 * (wbytes // 192)}
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
+        return None
+    ms_per_step = ms / args.steps
     peak, peak_src = load_peaks()
-    alg_bytes = 128 * n_local
-    achieved = alg_bytes / (win_ms * 1e-3) / 1e9
-    c_bits = None
-    W = wbytes // 192
-    # plan: W = ceil((253+1)/c)
-    for c in range(3, 24):
-        if (FR_BITS + 1 + c - 1) // c == W:
-            c_bits = c
-    fq_muls = msm_fq_mul_count(n_local, c_bits, W)
-    line = {
-        "metric": "msm_terms_per_s", "value": n_total / (ms_per_step * 1e-3), "unit": "G1 terms/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u32x12 Montgomery (Fq, 377-bit integer)", "data": "synthetic",
-        "config": {"workload": args.workload, "curve": "BLS12-377", "log_n": log_n, "window_bits": c_bits, "windows": W,
-                   "inputs": "test-SRS powers + uniform scalars, resident in HBM; 537 MB per pass > 126 MB L2 (no flush needed)",
-                   "parallelism": f"point-range x{world}"},
-        "roofline": {"bound": "hbm", "kernel": "msm window-sum pipeline (digits+sort+accumulate+reduce), accumulate dominant",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": win_ms,
-                     "alu": {"fq_mul_per_launch": fq_muls, "fq_mul_per_s": fq_muls / (win_ms * 1e-3),
-                             "note": "integer-ALU bound: see profiles/ubench for the measured IMAD peak"}},
-        "e2e": e2e if e2e else {"value": None, "unit": "G1 terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                                "note": "e2e leg runs at N=1 only"},
+    acc_ms = prof["ms"] / max(prof["launches"], 1)
+    alg_bytes = 128.0 * prof["terms"] / max(prof["launches"], 1)
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else 0.0
+    return {
+        "metric": "msm_terms_per_s", "value": n_total / (ms_per_step * 1e-3), "unit": "G1 terms/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x12 Montgomery (Fq, 377-bit integer)", "data": "synthetic",
+        "config": {"workload": f"BLS12-377 G1 MSM 2^{log_n}", "log_n": log_n, "parallelism": f"point-range x{world}, NCCL all-gather of window sums",
+                   "cache": f"{128 * n_local >> 20} MiB of bases+scalars per pass > 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "avg_launch_ms": acc_ms,
+                     "alu": {"madds_per_s": prof["madds"] / (prof["ms"] * 1e-3) if prof["ms"] else 0.0, "madd_peak_per_s": MADD_PEAK_PER_S}},
+        "e2e": {"value": None, "unit": "G1 terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "sweep workload: device-resident only"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1:
-        dt, cores = cpu_msm_sample(16)
-        line["cpu_baseline"] = {"value": (1 << 16) / dt, "unit": "G1 terms/s", "cores": cores, "kind": "port",
-                                "sample": "one 2^16-term MSM (CPU restatement of ark-ec 0.3.0 Pippenger; the reference is Rust and cannot be built here)"}
-    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm"])
+    ap.add_argument("--msg-len", type=int, default=256)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=22)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the prover path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = (bench_prove if args.workload == "prove" else bench_msm)(args, rank, world, local_rank)
+    if rank == 0:
+        if args.workload == "prove" and world == 1 and not args.no_cpu_baseline:
+            s = CpuSample()
+            dt, _ = s.prove()
+            line["cpu_baseline"] = {"value": s.n_constraints / dt, "unit": "constraints/s", "cores": s.cores, "kind": "port", "sample": s.describe()}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

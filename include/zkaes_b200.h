@@ -49,6 +49,11 @@ void* zkaes_ctx_stream(zkaes_ctx* ctx);
 uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx);
 /* Blocks until all work queued on the context's stream has finished. */
 int zkaes_ctx_sync(zkaes_ctx* ctx);
+/* Per-kernel timing of the dominant kernel (the MSM bucket accumulation) for bench.py's roofline: when enabled, every
+ * launch is bracketed by CUDA events on the context's stream.  profile_read synchronises and returns
+ * out = {launches, total ms, total MSM terms, total mixed additions (upper bound)} since the last read, then resets. */
+int zkaes_ctx_profile(zkaes_ctx* ctx, int enable);
+int zkaes_ctx_profile_read(zkaes_ctx* ctx, double out[4]);
 /* Tuning: force the MSM window width (0 = automatic). */
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
 
