@@ -46,6 +46,7 @@ def _load():
         "zkaes_dev_download": (c_int, [vp, vp, vp, c_size_t]),
         "zkaes_msm_g1": (c_int, [vp, c_int, vp, vp, c_size_t, vp]),
         "zkaes_msm_g1_device": (c_int, [vp, c_int, vp, vp, c_size_t, c_int, vp]),
+        "zkaes_msm_g1_prepare_bases": (c_int, [vp, c_int, vp, c_size_t]),
         "zkaes_msm_g1_windows_bytes": (c_size_t, [vp, c_int, c_size_t]),
         "zkaes_msm_g1_windows": (c_int, [vp, c_int, vp, vp, c_size_t, c_size_t, c_int, vp]),
         "zkaes_msm_g1_fold": (c_int, [vp, c_int, vp, c_int, c_size_t, vp]),
@@ -174,17 +175,23 @@ class Context:
         self._check(lib().zkaes_msm_g1(self._h, curve, _ptr(bases), _ptr(scalars), n, _ptr(out)))
         return out
 
-    def msm_g1_device(self, curve: int, bases_dev, scalars_dev, n: int, scalars_montgomery: bool = False) -> np.ndarray:
+    def msm_g1_device(self, curve: int, bases_dev, scalars_dev, n: int, scalars_montgomery: bool = False, bases_prepared: bool = False) -> np.ndarray:
         out = np.zeros(12, dtype=np.uint64)
-        self._check(lib().zkaes_msm_g1_device(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n, int(scalars_montgomery), _ptr(out)))
+        flags = int(scalars_montgomery) | (2 if bases_prepared else 0)
+        self._check(lib().zkaes_msm_g1_device(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n, flags, _ptr(out)))
         return out
+
+    def msm_g1_prepare_bases(self, curve: int, bases_dev, n: int):
+        """rewrite device-resident bases in place into the MSM kernels' internal form (do once per SRS)"""
+        self._check(lib().zkaes_msm_g1_prepare_bases(self._h, curve, _ptr(bases_dev), n))
 
     def msm_g1_windows_bytes(self, curve: int, n_total: int) -> int:
         return lib().zkaes_msm_g1_windows_bytes(self._h, curve, n_total)
 
-    def msm_g1_windows(self, curve: int, bases_dev, scalars_dev, n_local: int, n_total: int, windows_dev, scalars_montgomery: bool = False):
-        self._check(lib().zkaes_msm_g1_windows(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n_local, n_total,
-                                               int(scalars_montgomery), _ptr(windows_dev)))
+    def msm_g1_windows(self, curve: int, bases_dev, scalars_dev, n_local: int, n_total: int, windows_dev, scalars_montgomery: bool = False,
+                       bases_prepared: bool = False):
+        flags = int(scalars_montgomery) | (2 if bases_prepared else 0)
+        self._check(lib().zkaes_msm_g1_windows(self._h, curve, _ptr(bases_dev), _ptr(scalars_dev), n_local, n_total, flags, _ptr(windows_dev)))
 
     def msm_g1_fold(self, curve: int, gathered_dev, n_ranks: int, n_total: int) -> np.ndarray:
         out = np.zeros(12, dtype=np.uint64)

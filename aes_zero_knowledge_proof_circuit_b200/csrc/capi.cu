@@ -15,6 +15,7 @@ namespace zk {
 template <class F> int selftest_field_asm(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class F> int selftest_field_portable(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class C> int selftest_g1(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template <class P29> int selftest_field_r29(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 }
 using namespace zk;
 
@@ -28,7 +29,7 @@ template <class C>
 static int msm_windows_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n_local, size_t n_total, int mont,
                             void* windows_dev) {
     MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits);
-    return msm_window_sums<C>(ctx, bases, scalars, n_local, mont, p, windows_dev);
+    return msm_window_sums<C>(ctx, bases, scalars, n_local, mont & 1, p, windows_dev, (mont >> 1) & 1);
 }
 template <class C>
 static int msm_fold_impl(zkaes_ctx* ctx, const void* gathered, int n_ranks, size_t n_total, void* out96) {
@@ -45,7 +46,7 @@ static int msm_device_impl(zkaes_ctx* ctx, const void* bases, const void* scalar
     MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits);
     DevBuf win;
     ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * p.W, ctx->stream));
-    ZK_TRY(msm_window_sums<C>(ctx, bases, scalars, n, mont, p, win.p));
+    ZK_TRY(msm_window_sums<C>(ctx, bases, scalars, n, mont & 1, p, win.p, (mont >> 1) & 1));
     return msm_fold_impl<C>(ctx, win.p, 1, n, out96);
 }
 template <class C>
@@ -176,6 +177,12 @@ int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases, const v
     return CURVE_DISPATCH(ctx, curve_id, msm_device_impl<G1_377Params>(ctx, bases, scalars, n, mont, out96),
                           msm_device_impl<G1_381Params>(ctx, bases, scalars, n, mont, out96));
 }
+int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, size_t n) {
+    NEED_CTX(ctx);
+    if (n && !bases_dev) return fail(ctx, ZK_ERR_ARG, "prepare_bases: null pointer");
+    return CURVE_DISPATCH(ctx, curve_id, msm_bases_to_internal<G1_377Params>(ctx, bases_dev, bases_dev, n),
+                          msm_bases_to_internal<G1_381Params>(ctx, bases_dev, bases_dev, n));
+}
 size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total) {
     if (!ctx) return 0;
     int bits = curve_id == 377 ? Fr377Params::BITS : Fr381Params::BITS;
@@ -232,6 +239,11 @@ int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int va
     NEED_CTX(ctx);
     if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
     if (curve_id != 377 && curve_id != 381) return fail(ctx, ZK_ERR_ARG, "unknown curve_id");
+    if (variant == 2) {  // Fq through the radix-2^29 internal form
+        if (field != 1) return fail(ctx, ZK_ERR_ARG, "selftest: the radix-2^29 form exists for Fq only");
+        return curve_id == 377 ? selftest_field_r29<Fq377R29Params>(ctx, op, a, b, out, count)
+                               : selftest_field_r29<Fq381R29Params>(ctx, op, a, b, out, count);
+    }
     int sel = (curve_id == 381 ? 4 : 0) | (field ? 2 : 0) | (variant ? 1 : 0);
     switch (sel) {
         case 0: return selftest_field_asm<Fr377>(ctx, op, a, b, out, count);
@@ -271,6 +283,31 @@ int zkaes_selftest_host_field(int curve_id, int field, int op, const void* a, co
         }
         return ZK_OK;
     };
+    // field 2: Fq through the radix-2^29 internal form (fq29.cuh): from_std -> op -> to_std
+    auto run29 = [&](auto tag) {
+        using P29 = decltype(tag);
+        using G = Fq29<P29>;
+        const uint32_t* x = reinterpret_cast<const uint32_t*>(a);
+        const uint32_t* y = reinterpret_cast<const uint32_t*>(b);
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+        for (size_t i = 0; i < count; ++i) {
+            G u = G::from_std(x + 12 * i), v = G::from_std(y + 12 * i), r;
+            switch (op) {
+                case 0: r = u + v; break;
+                case 1: r = u - v; break;
+                case 2: r = u * v; break;
+                case 4: r = u.neg(); break;
+                default: return ZK_ERR_ARG;
+            }
+            r.to_std(o + 12 * i);
+        }
+        return ZK_OK;
+    };
+    if (field == 2) {
+        if (curve_id == 377) return run29(Fq377R29Params());
+        if (curve_id == 381) return run29(Fq381R29Params());
+        return ZK_ERR_ARG;
+    }
     if (curve_id == 377) return field ? run(Fq377()) : run(Fr377());
     if (curve_id == 381) return field ? run(Fq381()) : run(Fr381());
     return ZK_ERR_ARG;

@@ -9,7 +9,10 @@
 // no field inversion and no Z^2/Z^3 recomputation.  Results leave the device as XYZZ window sums and are
 // normalised to affine on the host (host code uses the portable multiplier in ff.cuh).
 #pragma once
+#include <type_traits>
+
 #include "ff.cuh"
+#include "fq29.cuh"
 
 // Point doubling / full addition are off the inner loop (bucket reduction, rare mixed-add corner cases):
 // keeping them out of line cuts both compile time and instruction-cache footprint of the hot kernels.
@@ -21,9 +24,41 @@
 
 namespace zk {
 
+// base-field type of a curve description: Fp<FqP> (arkworks layout) unless the description names its own (C::FqCustom:
+// the radix-2^29 form the MSM kernels compute in)
+template <class C, class = void>
+struct FqOf {
+    using type = Fp<typename C::FqP>;
+};
+template <class C>
+struct FqOf<C, std::void_t<typename C::FqCustom>> {
+    using type = typename C::FqCustom;
+};
+// internal curve descriptions used by msm.cu
+struct G1_377R29 {
+    using FqP = Fq377Params;
+    using FrP = Fr377Params;
+    using FqCustom = Fq29<Fq377R29Params>;
+    static constexpr int CURVE_ID = 377;
+};
+struct G1_381R29 {
+    using FqP = Fq381Params;
+    using FrP = Fr381Params;
+    using FqCustom = Fq29<Fq381R29Params>;
+    static constexpr int CURVE_ID = 381;
+};
+// Which form the MSM kernels compute in.  Default: the arkworks 32-bit-limb form.  -DZK_MSM_R29 selects the radix-2^29
+// form; it is bit-exact (tests run both) but SLOWER on B200: every 32x32->64 IMAD (WIDE or HI, with or without carry)
+// issues at half rate, so 13 x 13 limb products cannot beat 12 x 12 (profiles/ubench_r1.txt).
+template <class C> struct InternalCurve { using type = C; };
+#if defined(ZK_MSM_R29)
+template <> struct InternalCurve<G1_377Params> { using type = G1_377R29; };
+template <> struct InternalCurve<G1_381Params> { using type = G1_381R29; };
+#endif
+
 template <class C>
 struct Affine {
-    using Fq = Fp<typename C::FqP>;
+    using Fq = typename FqOf<C>::type;
     Fq x, y;
     ZK_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
     static ZK_HD Affine inf() {
@@ -58,7 +93,7 @@ struct Affine {
 
 template <class C>
 struct XYZZ {
-    using Fq = Fp<typename C::FqP>;
+    using Fq = typename FqOf<C>::type;
     Fq x, y, zz, zzz;
 
     ZK_HD bool is_inf() const { return zz.is_zero(); }

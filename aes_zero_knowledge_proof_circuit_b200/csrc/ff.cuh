@@ -33,6 +33,8 @@ static __constant__ uint32_t zk_c_mont_inv[4] = {Fr377Params::INV, Fq377Params::
 // products: without it ptxas interleaves their carry chains, runs out of the 7 predicate registers and spills carries
 // through P2R/LOP3/ISETP (about one extra ALU instruction per IMAD.WIDE in the madd inner loop).
 static __constant__ uint32_t zk_c_zero = 0;
+// -p^-1 mod 2^29 for the radix-2^29 base fields (fq29.cuh), opaque to ptxas for the same reason
+static __constant__ uint32_t zk_c_r29_inv[2] = {Fq377R29Params::INV, Fq381R29Params::INV};
 #endif
 
 template <int N>
@@ -204,6 +206,20 @@ struct Fp {
         return a * b;
 #endif
     }
+
+    // wire-format hooks shared with the radix-2^29 form (fq29.cuh): for Fp the arkworks limbs ARE the working form
+    static ZK_HD Fp unpack(const uint32_t* w) {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = w[i];
+        return r;
+    }
+    ZK_HD void pack(uint32_t* w) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = v[i];
+    }
+    static ZK_HD Fp from_std(const uint32_t* w) { return unpack(w); }
+    ZK_HD void to_std(uint32_t* w) const { pack(w); }
 
     // canonical integer -> Montgomery and back
     ZK_HD Fp to_mont() const { return *this * r2(); }

@@ -143,21 +143,56 @@ int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32
 }
 
 // ---- bucket accumulation ---------------------------------------------------------------------------------
-template <class C>
-__device__ __forceinline__ Affine<C> load_affine(const Affine<C>* bases, uint32_t idx) {
-    Affine<C> r;
-    const uint4* p = reinterpret_cast<const uint4*>(bases + idx);
+// Bases are read in the INTERNAL packed form: per coordinate the radix-2^29 Montgomery representative (R' = 2^(29 NL))
+// as a plain little-endian integer in 48 bytes -- the same 96 B per point as the arkworks form, 6 x 128-bit loads.
+template <class CI>
+__device__ __forceinline__ Affine<CI> load_affine(const uint32_t* __restrict__ bases, uint32_t idx) {
+    using Fq = typename Affine<CI>::Fq;
+    uint32_t w[24];
+    const uint4* p = reinterpret_cast<const uint4*>(bases + (size_t)idx * 24);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 6; ++k) {
         uint4 v = __ldg(p + k);
-        r.x.v[4 * k] = v.x; r.x.v[4 * k + 1] = v.y; r.x.v[4 * k + 2] = v.z; r.x.v[4 * k + 3] = v.w;
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        uint4 v = __ldg(p + 3 + k);
-        r.y.v[4 * k] = v.x; r.y.v[4 * k + 1] = v.y; r.y.v[4 * k + 2] = v.z; r.y.v[4 * k + 3] = v.w;
-    }
+    Affine<CI> r;
+    r.x = Fq::unpack(w);
+    r.y = Fq::unpack(w + 12);
     return r;
+}
+// arkworks wire form (Montgomery R = 2^384 limbs) -> internal packed form; in place when dst == src
+template <class C>
+__global__ void __launch_bounds__(128) k_bases_to_internal(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
+    using CI = typename InternalCurve<C>::type;
+    using Fq = typename Affine<CI>::Fq;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[24];
+    const uint4* p = reinterpret_cast<const uint4*>(src + i * 24);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        uint4 v = p[k];
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+    Fq x = Fq::from_std(w), y = Fq::from_std(w + 12);
+    x.pack(w);
+    y.pack(w + 12);
+    uint4* o = reinterpret_cast<uint4*>(dst + i * 24);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+// internal XYZZ window sums -> arkworks-form XYZZ for the host fold
+template <class C>
+__global__ void k_windows_to_std(const XYZZ<typename InternalCurve<C>::type>* __restrict__ in, XYZZ<C>* __restrict__ out, int W) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    XYZZ<typename InternalCurve<C>::type> p = in[w];
+    XYZZ<C> r;
+    p.x.to_std(r.x.v);
+    p.y.to_std(r.y.v);
+    p.zz.to_std(r.zz.v);
+    p.zzz.to_std(r.zzz.v);
+    out[w] = r;
 }
 
 // Work items: bucket b is cut into ceil(count[b] / S) slices of at most S sorted entries, so a heavily loaded bucket
@@ -170,7 +205,7 @@ __global__ void __launch_bounds__(256) k_msm_item_counts(const uint32_t* __restr
 
 // one thread per work item: partial[item] = sum of its slice (XYZZ += affine, 8M+2S each)
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<C>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ counts,
                                                         const uint32_t* __restrict__ item_off, uint32_t nb, uint32_t n_items,
@@ -279,15 +314,16 @@ __global__ void k_msm_window_final(const XYZZ<C>* __restrict__ partials, uint32_
 
 template <class C>
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
-                    void* d_window_sums) {
+                    void* d_window_sums, int bases_internal) {
     using FrP = typename C::FrP;
+    using CI = typename InternalCurve<C>::type;  // all curve arithmetic below runs in the radix-2^29 form
     cudaStream_t st = ctx->stream;
     DevBuf counts, offsets, sorted, buckets, partials, items, item_off, acc_partial;
     ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * p.nb, st));
     ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * p.nb, st));
     ZK_CUDA(ctx, items.alloc(sizeof(uint32_t) * p.nb, st));
     ZK_CUDA(ctx, item_off.alloc(sizeof(uint32_t) * p.nb, st));
-    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
+    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
     size_t chunk_max = n < MSM_CHUNK ? n : MSM_CHUNK;
     ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * chunk_max * p.W, st));
     // slice length: twice the mean bucket load, clamped; #items <= nb + chunk*W/S
@@ -296,8 +332,15 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     if (S < 16) S = 16;
     if (S > 1024) S = 1024;
     size_t max_items = (size_t)p.nb + (chunk_max * p.W) / S + 1;
-    ZK_CUDA(ctx, acc_partial.alloc(sizeof(XYZZ<C>) * max_items, st));
-    const auto* bases = reinterpret_cast<const Affine<C>*>(d_bases);
+    ZK_CUDA(ctx, acc_partial.alloc(sizeof(XYZZ<CI>) * max_items, st));
+    const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
+    DevBuf conv;
+    if (!bases_internal && n) {  // caller's bases are in the arkworks form: one conversion pass into scratch
+        ZK_CUDA(ctx, conv.alloc(96 * n, st));
+        k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, st>>>(bases, conv.as<uint32_t>(), n);
+        ctx->launches++;
+        bases = conv.as<uint32_t>();
+    }
     const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
     if (n == 0) {
         ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * p.W, st));
@@ -331,9 +374,9 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
                 cudaEventCreate(&span.e1);
                 cudaEventRecord(span.e0, st);
             }
-            k_msm_accumulate<C><<<cdiv(n_items, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
+            k_msm_accumulate<CI><<<cdiv(n_items, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
                                                                    counts.as<uint32_t>(), item_off.as<uint32_t>(), p.nb, n_items, S,
-                                                                   acc_partial.as<XYZZ<C>>());
+                                                                   acc_partial.as<XYZZ<CI>>());
             ctx->launches++;
             if (ctx->prof) {
                 cudaEventRecord(span.e1, st);
@@ -342,8 +385,8 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
                 ctx->prof_spans.push_back(span);
             }
         }
-        k_msm_merge<C><<<cdiv(p.nb, 128), 128, 0, st>>>(acc_partial.as<XYZZ<C>>(), item_off.as<uint32_t>(), items.as<uint32_t>(), p.nb,
-                                                       buckets.as<XYZZ<C>>(), base == 0);
+        k_msm_merge<CI><<<cdiv(p.nb, 128), 128, 0, st>>>(acc_partial.as<XYZZ<CI>>(), item_off.as<uint32_t>(), items.as<uint32_t>(), p.nb,
+                                                       buckets.as<XYZZ<CI>>(), base == 0);
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
     }
@@ -352,10 +395,13 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     uint32_t seg = p.nbw / tpw;
     uint32_t bs = tpw < RED_BS ? tpw : RED_BS;
     uint32_t bpw = tpw / bs;
-    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<C>) * (size_t)bpw * p.W, st));
-    k_msm_reduce<C><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<C>>(), p.nbw, seg, partials.as<XYZZ<C>>());
-    k_msm_window_final<C><<<1, p.W, 0, st>>>(partials.as<XYZZ<C>>(), bpw, reinterpret_cast<XYZZ<C>*>(d_window_sums));
-    ctx->launches += 2;
+    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<CI>) * (size_t)bpw * p.W, st));
+    k_msm_reduce<CI><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<CI>>(), p.nbw, seg, partials.as<XYZZ<CI>>());
+    DevBuf win_int;
+    ZK_CUDA(ctx, win_int.alloc(sizeof(XYZZ<CI>) * p.W, st));
+    k_msm_window_final<CI><<<1, p.W, 0, st>>>(partials.as<XYZZ<CI>>(), bpw, win_int.as<XYZZ<CI>>());
+    k_windows_to_std<C><<<cdiv(p.W, 32), 32, 0, st>>>(win_int.as<XYZZ<CI>>(), reinterpret_cast<XYZZ<C>*>(d_window_sums), p.W);
+    ctx->launches += 3;
     ZK_CUDA(ctx, cudaGetLastError());
     return ZK_OK;
 }
@@ -372,22 +418,34 @@ Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& 
 }
 
 template <class C>
-int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out) {
+int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out, int bases_internal) {
     MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits);
     DevBuf win;
     ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * p.W, ctx->stream));
-    ZK_TRY(msm_window_sums<C>(ctx, d_bases, d_scalars, n, scalars_mont, p, win.p));
+    ZK_TRY(msm_window_sums<C>(ctx, d_bases, d_scalars, n, scalars_mont, p, win.p, bases_internal));
     std::vector<XYZZ<C>> h(p.W);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win.p, sizeof(XYZZ<C>) * p.W, cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = msm_fold_windows_host<C>(h.data(), 1, p);
     return ZK_OK;
 }
-template int msm_to_affine<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_377Params>*);
-template int msm_to_affine<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_381Params>*);
+template int msm_to_affine<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_377Params>*, int);
+template int msm_to_affine<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_381Params>*, int);
 
-template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
-template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*);
+// arkworks-form bases -> internal packed form (in place when dst == src): for bases that stay resident (the SRS)
+template <class C>
+int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n) {
+    if (!n) return ZK_OK;
+    k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), n);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+template int msm_bases_to_internal<G1_377Params>(zkaes_ctx*, const void*, void*, size_t);
+template int msm_bases_to_internal<G1_381Params>(zkaes_ctx*, const void*, void*, size_t);
+
+template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int);
+template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int);
 template Affine<G1_377Params> msm_fold_windows_host<G1_377Params>(const XYZZ<G1_377Params>*, int, const MsmPlan&);
 template Affine<G1_381Params> msm_fold_windows_host<G1_381Params>(const XYZZ<G1_381Params>*, int, const MsmPlan&);
 

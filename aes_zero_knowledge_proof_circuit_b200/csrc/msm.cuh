@@ -16,8 +16,11 @@ MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c);
 
 // Device-resident inputs -> W window sums (XYZZ, device).  scalars: n x 8 u32 (canonical, or Montgomery if scalars_mont).
 template <class C>
+// bases_internal != 0: bases are already in the internal packed form (msm_bases_to_internal); otherwise arkworks form.
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
-                    void* d_window_sums);
+                    void* d_window_sums, int bases_internal = 0);
+template <class C>
+int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n);
 
 // Host Horner fold over n_sets sets of W window sums (one set per rank), returns the affine result.
 template <class C>
@@ -28,6 +31,6 @@ int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32
 
 // Whole MSM: device-resident bases / scalars -> affine result on the host (window sums on the device, Horner fold on the host).
 template <class C>
-int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out);
+int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, Affine<C>* out, int bases_internal = 0);
 
 }  // namespace zk

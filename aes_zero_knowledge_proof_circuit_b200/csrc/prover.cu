@@ -231,7 +231,7 @@ struct zkaes_pk_impl {
     size_t n_heavy = 0;
     Fr* elems_h = nullptr;
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
-    Aff* srs = nullptr;     // tau^i G, i <= D
+    Aff* srs = nullptr;     // tau^i G, i <= D, in the MSM kernels' internal packed form (msm_bases_to_internal)
     Aff gamma_g[3];         // gamma tau^i G (host)
     Aff index_comms[12];
     std::vector<uint8_t> vk_bytes;
@@ -260,7 +260,7 @@ int ntt(zkaes_ctx* ctx, Fr* data, int log_n, bool inverse, bool coset) { return 
 // commit(poly) through the device MSM: sum coeffs[i] * srs[offset + i]
 int msm_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, Aff* out) {
     if (offset + n > pk.D + 1) return fail(ctx, ZK_ERR_STATE, "commit: polynomial exceeds the SRS");
-    return msm_to_affine<C>(ctx, pk.srs + offset, coeffs, n, /*scalars_mont=*/1, out);
+    return msm_to_affine<C>(ctx, pk.srs + offset, coeffs, n, /*scalars_mont=*/1, out, /*bases_internal=*/1);
 }
 // KZG10::commit with an optional hiding polynomial of degree hiding_bound + 1 (three draws for hiding_bound = 1)
 int kzg_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, bool hiding, ChaCha20Rng& zk, Aff* out,
@@ -318,6 +318,7 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     // ---- SRS: tau^i G on the device, gamma tau^i G (i < 3) on the host -----------------------------------------------
     ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * (pk.D + 1)));
     ZK_TRY(srs_powers_device<C>(ctx, tau_seed, pk.D + 1, pk.srs));
+    ZK_TRY(msm_bases_to_internal<C>(ctx, pk.srs, pk.srs, pk.D + 1));  // resident bases live in the MSM kernels' internal form
     Fr tau = fr_from_seed(tau_seed), gamma = fr_from_seed(gamma_seed);
     Fr gt = gamma;
     for (int i = 0; i < 3; ++i) {

@@ -69,16 +69,23 @@ int zkaes_dev_download(zkaes_ctx* ctx, void* host, const void* dev, size_t bytes
  */
 /* host buffers in, 96-byte affine result out (host) */
 int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases_host, const void* scalars_host, size_t n, void* out_affine96);
-/* device-resident inputs; scalars_montgomery != 0 means the scalars are Fr elements in Montgomery form (as the
- * prover's coefficient vectors are) and are converted on the fly */
+/* device-resident inputs.  flags: bit 0 (ZKAES_MSM_SCALARS_MONTGOMERY) = the scalars are Fr elements in Montgomery form
+ * (as the prover's coefficient vectors are) and are converted on the fly; bit 1 (ZKAES_MSM_BASES_PREPARED) = the bases
+ * were rewritten in place by zkaes_msm_g1_prepare_bases. */
+#define ZKAES_MSM_SCALARS_MONTGOMERY 1
+#define ZKAES_MSM_BASES_PREPARED 2
 int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n,
-                        int scalars_montgomery, void* out_affine96_host);
+                        int flags, void* out_affine96_host);
+/* Rewrites n device-resident bases IN PLACE from the arkworks form into the kernels' internal form (same 96 bytes per
+ * point: radix-2^29 Montgomery representative, R' = 2^377 / 2^406, packed little-endian).  Bases that are reused across
+ * many MSMs (an SRS) should be prepared once; unprepared bases are converted into scratch on every call. */
+int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, size_t n);
 /* multi-GPU split: (1) per-rank window sums of this rank's point range, written to a device buffer of
  * zkaes_msm_g1_windows_bytes(n_total) bytes; the window plan is derived from n_total so all ranks agree.
  * (2) after an all-gather of those buffers, fold n_ranks sets into the affine result (host). */
 size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total);
 int zkaes_msm_g1_windows(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n_local,
-                         size_t n_total, int scalars_montgomery, void* windows_dev);
+                         size_t n_total, int flags, void* windows_dev);
 int zkaes_msm_g1_fold(zkaes_ctx* ctx, int curve_id, const void* gathered_windows_dev, int n_ranks, size_t n_total,
                       void* out_affine96_host);
 

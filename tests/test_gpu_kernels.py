@@ -40,6 +40,25 @@ def test_device_field_ops(ctx, oracle, curve, field, variant):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_device_fq_radix29_form(ctx, oracle, curve):
+    """Fq through the MSM kernels' internal radix-2^29 form (from_std -> op -> to_std) equals the arkworks-form result"""
+    rng = np.random.default_rng(curve + 29)
+    p = FQ[curve]
+    n = 1 << 14
+    a, b = rand_fq(rng, curve, n), rand_fq(rng, curve, n)
+    edge = ints_to_limbs([0, 1, p - 1, p - 2, (1 << 376) % p, p >> 1], 6)
+    a[: len(edge)] = edge
+    b[: len(edge)] = edge[::-1]
+    a[len(edge): 2 * len(edge)] = edge
+    b[len(edge): 2 * len(edge)] = edge
+    for op in (0, 1, 2):
+        got = ctx.selftest_field(curve, 1, op, 2, a, b)
+        exp = oracle.field_op(curve, 1, op, a, b)
+        bad = np.nonzero((got != exp).any(axis=1))[0]
+        assert bad.size == 0, f"curve {curve} op {op}: {bad.size} mismatches, first at {bad[:4]}"
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_device_g1_formulas(ctx, oracle, curve):
     rng = np.random.default_rng(curve)
     n = 64
