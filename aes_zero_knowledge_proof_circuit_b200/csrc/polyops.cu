@@ -244,6 +244,34 @@ __global__ void k_round3(F* out, R3Args p, const F* f, size_t n) {
     F num = a * p.vv - ab * dc * ld_fr(f + i);
     st_fr(out + i, num * p.vkinv[i & 3]);
 }
+// out[a] = in[a] * lo[a & 1023] * hi[a >> 10]
+__global__ void k_scale_powers(F* out, const F* in, const F* __restrict__ lo, const F* __restrict__ hi, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F a = ld_fr(in + i) * ld_fr(lo + (i & 1023));
+    if (i >> 10) a = a * ld_fr(hi + (i >> 10));
+    st_fr(out + i, a);
+}
+__global__ void k_mul3(F* out, const F* a, const F* b, const F* c, F s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(out + i, ld_fr(a + i) * ld_fr(b + i) * ld_fr(c + i) * s);
+}
+__global__ void k_fma3(F* acc, const F* a, const F* b, const F* c, F s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_fr(acc + i, ld_fr(acc + i) + ld_fr(a + i) * ld_fr(b + i) * ld_fr(c + i) * s);
+}
+// 4-point inverse DFT across the coset blocks, times g^(-k b) / 4
+__global__ void k_coset4_combine(F* v, size_t k, F c0, F c1, F c2, F c3, F i4_inv) {
+    size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= k) return;
+    F u0 = ld_fr(v + a), u1 = ld_fr(v + k + a), u2 = ld_fr(v + 2 * k + a), u3 = ld_fr(v + 3 * k + a);
+    // w = i4^-1 (a primitive 4th root): sum_j w^(j b) u_j
+    F s02 = u0 + u2, d02 = u0 - u2, s13 = u1 + u3, d13 = (u1 - u3) * i4_inv;
+    st_fr(v + a, (s02 + s13) * c0);
+    st_fr(v + k + a, (d02 + d13) * c1);
+    st_fr(v + 2 * k + a, (s02 - s13) * c2);
+    st_fr(v + 3 * k + a, (d02 - d13) * c3);
+}
 // partial[c] = sum_{i < CH} coeffs[c*CH + i] * x^i
 constexpr int EV_CH = 256;
 __global__ void __launch_bounds__(128) k_eval_partial(const F* coeffs, size_t n, F x, F* partial) {
@@ -376,6 +404,27 @@ int po_round3(zkaes_ctx* ctx, F* out, const F* const val[3], const F* const den[
     p.vv = vv;
     for (int i = 0; i < 4; ++i) p.vkinv[i] = vkinv[i];
     LAUNCH(ctx, k_round3, n, TB, out, p, f, n);
+    return ZK_OK;
+}
+int po_scale_powers(zkaes_ctx* ctx, F* out, const F* in, const F& base, size_t n) {
+    cudaStream_t st = ctx->stream;
+    DevBuf lo, hi;
+    size_t nhi = (n >> 10) + 1;
+    ZK_CUDA(ctx, lo.alloc(sizeof(F) * 1024, st));
+    ZK_CUDA(ctx, hi.alloc(sizeof(F) * nhi, st));
+    F b1024 = base;
+    for (int i = 0; i < 10; ++i) b1024 = b1024.sqr();
+    ZK_TRY(po_powers(ctx, lo.as<F>(), 1024, base, F::one()));
+    ZK_TRY(po_powers(ctx, hi.as<F>(), nhi, b1024, F::one()));
+    LAUNCH(ctx, k_scale_powers, n, TB, out, in, lo.as<F>(), hi.as<F>(), n);
+    return ZK_OK;
+}
+int po_mul3(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_mul3, n, TB, out, a, b, c, s, n); return ZK_OK; }
+int po_fma3(zkaes_ctx* ctx, F* acc, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_fma3, n, TB, acc, a, b, c, s, n); return ZK_OK; }
+int po_coset4_combine(zkaes_ctx* ctx, F* v, size_t k, const F& gk_inv, const F& i4_inv) {
+    F quarter = F::from_u64(4).inverse();
+    F c0 = quarter, c1 = c0 * gk_inv, c2 = c1 * gk_inv, c3 = c2 * gk_inv;
+    LAUNCH(ctx, k_coset4_combine, k, TB, v, k, c0, c1, c2, c3, i4_inv);
     return ZK_OK;
 }
 int po_eval(zkaes_ctx* ctx, const F* coeffs, size_t n, const F& x, F* out_host) {

@@ -57,6 +57,15 @@ int po_den_coset(zkaes_ctx* ctx, FrS* row, const FrS* col, const FrS* rc, const 
 // out = (vv * (eta_a val_a den_b den_c + eta_b val_b den_a den_c + eta_c val_c den_a den_b) - den_a den_b den_c * f) * vkinv[i & 3]
 int po_round3(zkaes_ctx* ctx, FrS* out, const FrS* const val[3], const FrS* const den[3], const FrS* f, const FrS eta[3], const FrS& vv,
               const FrS vkinv[4], size_t n);
+// out[a] = in[a] * base^a   (coset shift of a coefficient vector; out may alias in)
+int po_scale_powers(zkaes_ctx* ctx, FrS* out, const FrS* in, const FrS& base, size_t n);
+// out = a * b * c * s
+int po_mul3(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
+// acc += s * a * b * c
+int po_fma3(zkaes_ctx* ctx, FrS* acc, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
+// In place on v (4 blocks of k): block j holds u_j[a] = (coefficient a of the degree-<k interpolant on coset j) * s_j^-a.
+// Afterwards block b holds the coefficients p_{a + k b} of the degree-<4k polynomial: p = (g^-kb / 4) sum_j i4^(-j b) u_j.
+int po_coset4_combine(zkaes_ctx* ctx, FrS* v, size_t k, const FrS& gk_inv, const FrS& i4_inv);
 // polynomial evaluation (Horner), result on the host
 int po_eval(zkaes_ctx* ctx, const FrS* coeffs, size_t n, const FrS& x, FrS* out_host);
 // q = c / (X - z) (synthetic division, remainder dropped): n coefficients in, n - 1 out; q must not alias c

@@ -310,7 +310,7 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     pk.k = next_pow2(nnz_max);
     pk.x = c.num_instance;
     pk.log_h = log2_exact(pk.h); pk.log_k = log2_exact(pk.k); pk.log_x = log2_exact(pk.x);
-    if (pk.log_k + 2 > 30) return fail(ctx, ZK_ERR_UNSUPPORTED, "synthesize_keys: |K| too large for this build (4|K| NTT limit 2^30)");
+    if (pk.log_k > 28) return fail(ctx, ZK_ERR_UNSUPPORTED, "synthesize_keys: |K| too large for this build (limit 2^28)");
     // AHPForR1CS::max_degree with zk_bound = 1
     pk.D = std::max(std::max(2 * pk.h - 1, 3 * pk.h - 1), std::max(pk.h, 3 * pk.k - 3));
     const size_t h = pk.h, k = pk.k, x = pk.x;
@@ -594,45 +594,50 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const Fr* g2 = fpoly.as<Fr>() + 1;  // f = X g_2 + t(beta) / |K|
     const size_t len_g2 = k - 1;
     tr.mark("r3: f");
-    // h_2 = (a - b f) / v_K on the coset g * B, |B| = 4|K|
-    const size_t k4 = 4 * k;
+    // h_2 = (a - b f) / v_K, evaluated on the coset g*B (|B| = 4|K|, where v_K does not vanish) as four cosets
+    // s_j K, s_j = g w_4K^j, of size |K| each: every buffer is |K|-sized (the reference keeps 12 tables of 4|K| in the
+    // index, ahp/indexer.rs evals_on_B -- 206 GB at 4 KiB), and v_K is the constant s_j^K - 1 on each of them.
     const int log4k = pk.log_k + 2;
-    DevBuf dden[3], dval[3], t_col, t_rc, f4;
-    auto to_coset4 = [&](DevBuf& dst, const Fr* src, size_t len) -> int {
-        if (!dst.p) ZK_CUDA(ctx, dst.alloc(sizeof(Fr) * k4, st));
-        ZK_CUDA(ctx, cudaMemsetAsync(dst.as<Fr>() + len, 0, sizeof(Fr) * (k4 - len), st));
-        ZK_CUDA(ctx, cudaMemcpyAsync(dst.p, src, sizeof(Fr) * len, cudaMemcpyDeviceToDevice, st));
-        return ntt(ctx, dst.as<Fr>(), log4k, false, true);
-    };
     const Fr ab = alpha * beta;
-    for (int m = 0; m < 3; ++m) {
-        Fr* const* P = &pk.idx_poly[4 * m];
-        ZK_TRY(to_coset4(dden[m], P[0], k));
-        ZK_TRY(to_coset4(t_col, P[1], k));
-        ZK_TRY(to_coset4(t_rc, P[3], k));
-        ZK_TRY(po_den_coset(ctx, dden[m].as<Fr>(), t_col.as<Fr>(), t_rc.as<Fr>(), alpha, beta, ab, k4));
-        ZK_TRY(to_coset4(dval[m], P[2], k));
-    }
-    t_rc.release();
-    ZK_TRY(to_coset4(f4, fpoly.as<Fr>(), k));
-    Fr vkinv[4];
-    {
-        Fr gk = fr_pow_u64(coset_gen(), k), w4 = fr_pow_u64(domain_gen(log4k), k), cur = gk;
-        for (int i = 0; i < 4; ++i) {
-            vkinv[i] = (cur - Fr::one()).inverse();
-            cur = cur * w4;
+    const Fr g = coset_gen(), w4k = domain_gen(log4k);
+    DevBuf V, dden[3], tA, tB;
+    ZK_CUDA(ctx, V.alloc(sizeof(Fr) * 4 * k, st));
+    for (int m = 0; m < 3; ++m) ZK_CUDA(ctx, dden[m].alloc(sizeof(Fr) * k, st));
+    ZK_CUDA(ctx, tA.alloc(sizeof(Fr) * k, st));
+    ZK_CUDA(ctx, tB.alloc(sizeof(Fr) * k, st));
+    auto to_coset = [&](Fr* dst, const Fr* poly, const Fr& shift) -> int {  // dst[i] = poly(shift * w_K^i)
+        ZK_TRY(po_scale_powers(ctx, dst, poly, shift, k));
+        return ntt(ctx, dst, pk.log_k, false, false);
+    };
+    Fr sj = g;
+    for (int j = 0; j < 4; ++j) {
+        for (int m = 0; m < 3; ++m) {
+            Fr* const* P = &pk.idx_poly[4 * m];
+            ZK_TRY(to_coset(dden[m].as<Fr>(), P[0], sj));
+            ZK_TRY(to_coset(tA.as<Fr>(), P[1], sj));
+            ZK_TRY(to_coset(tB.as<Fr>(), P[3], sj));
+            ZK_TRY(po_den_coset(ctx, dden[m].as<Fr>(), tA.as<Fr>(), tB.as<Fr>(), alpha, beta, ab, k));
         }
+        Fr* Vj = V.as<Fr>() + (size_t)j * k;
+        ZK_TRY(to_coset(tA.as<Fr>(), fpoly.as<Fr>(), sj));
+        ZK_TRY(po_mul3(ctx, Vj, dden[0].as<Fr>(), dden[1].as<Fr>(), dden[2].as<Fr>(), Fr::one().neg(), k));
+        ZK_TRY(po_vec(ctx, 2, Vj, Vj, tA.as<Fr>(), k));  // - b * f
+        for (int m = 0; m < 3; ++m) {
+            ZK_TRY(to_coset(tA.as<Fr>(), pk.idx_poly[4 * m + 2], sj));
+            ZK_TRY(po_fma3(ctx, Vj, tA.as<Fr>(), dden[(m + 1) % 3].as<Fr>(), dden[(m + 2) % 3].as<Fr>(), vv * eta[m], k));  // + a
+        }
+        const Fr vk_inv = (fr_pow_u64(sj, k) - Fr::one()).inverse();
+        ZK_TRY(po_scale(ctx, Vj, Vj, vk_inv, k));
+        // back to the coefficients of the degree-<|K| interpolant on this coset, with the shift undone
+        ZK_TRY(ntt(ctx, Vj, pk.log_k, true, false));
+        ZK_TRY(po_scale_powers(ctx, Vj, Vj, sj.inverse(), k));
+        sj = sj * w4k;
     }
-    const Fr* vals[3] = {dval[0].as<Fr>(), dval[1].as<Fr>(), dval[2].as<Fr>()};
-    const Fr* dens[3] = {dden[0].as<Fr>(), dden[1].as<Fr>(), dden[2].as<Fr>()};
-    Fr* h2 = t_col.as<Fr>();
-    ZK_TRY(po_round3(ctx, h2, vals, dens, f4.as<Fr>(), eta, vv, vkinv, k4));
-    for (int m = 0; m < 3; ++m) {
-        dden[m].release();
-        dval[m].release();
-    }
-    f4.release();
-    ZK_TRY(ntt(ctx, h2, log4k, true, true));
+    for (int m = 0; m < 3; ++m) dden[m].release();
+    tA.release();
+    tB.release();
+    ZK_TRY(po_coset4_combine(ctx, V.as<Fr>(), k, fr_pow_u64(g, k).inverse(), fr_pow_u64(w4k, k).inverse()));
+    Fr* h2 = V.as<Fr>();  // 3|K| - 3 coefficients (block 3 is zero: deg h_2 < 3|K|)
     const size_t len_h2 = 3 * k - 3;
     tr.mark("r3: h_2 on the coset");
     Committed c_g2, c_h2;

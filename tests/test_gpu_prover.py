@@ -76,6 +76,22 @@ def test_verifier_accepts_and_rejects(ctx, msg_len):
         pk.close()
 
 
+def test_full_size_4kib_proof_verifies(ctx):
+    """BASELINE.json's headline configuration: 256 ECB blocks, 37,994,400 constraints, |H| = 2^26, |K| = 2^27 on one GPU"""
+    msg = bytes((i * 131 + 7) & 0xFF for i in range(4096))
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    pk = ctx.synthesize_keys(4096, TAU, GAMMA)
+    try:
+        assert (pk.info["h"], pk.info["k"], pk.info["num_constraints"]) == (1 << 26, 1 << 27, 37994400)
+        ct, proof = ctx.encrypt(pk, msg, key, bytes([5] * 32))
+        assert _verify(pk, ct, proof)
+        wrong = bytearray(ct)
+        wrong[4095] ^= 1
+        assert not _verify(pk, bytes(wrong), proof)
+    finally:
+        pk.close()
+
+
 def test_wrong_length_rejected(ctx, pk16):
     with pytest.raises(zk.ZkAesError):
         ctx.encrypt(pk16, b"\x00" * 32, b"\x00" * 16, bytes(32))
