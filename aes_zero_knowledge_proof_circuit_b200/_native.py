@@ -38,6 +38,9 @@ def _load():
         "zkaes_ctx_launches": (c_uint64, [vp]),
         "zkaes_ctx_sync": (c_int, [vp]),
         "zkaes_ctx_set_msm_window": (c_int, [vp, c_int]),
+        "zkaes_comm_unique_id": (c_int, [vp]),
+        "zkaes_ctx_comm_init": (c_int, [vp, c_int, c_int, vp]),
+        "zkaes_shard_range": (c_int, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
         "zkaes_ctx_profile": (c_int, [vp, c_int]),
         "zkaes_ctx_profile_read": (c_int, [vp, vp]),
         "zkaes_dev_alloc": (c_int, [vp, c_size_t, POINTER(vp)]),
@@ -102,6 +105,22 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+def comm_unique_id() -> bytes:
+    buf = np.zeros(128, dtype=np.uint8)
+    rc = lib().zkaes_comm_unique_id(_ptr(buf))
+    if rc != 0:
+        raise ZkAesError(f"zkaes_comm_unique_id failed with {rc} (is libnccl.so.2 loadable?)")
+    return buf.tobytes()
+
+
+def shard_range(n: int, rank: int, nranks: int):
+    """point range [start, start + count) of `rank` in an n-point MSM sharded over nranks GPUs"""
+    s, c = c_size_t(0), c_size_t(0)
+    if lib().zkaes_shard_range(n, rank, nranks, ctypes.byref(s), ctypes.byref(c)) != 0:
+        raise ZkAesError("zkaes_shard_range: bad arguments")
+    return s.value, c.value
+
+
 class Context:
     """One prover context bound to one CUDA device (one per process / rank)."""
 
@@ -138,6 +157,11 @@ class Context:
 
     def sync(self):
         self._check(lib().zkaes_ctx_sync(self._h))
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        """join the NCCL communicator of the sharded MSM (call before synthesize_keys); unique_id from comm_unique_id() on rank 0"""
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8) if unique_id is not None else None
+        self._check(lib().zkaes_ctx_comm_init(self._h, rank, nranks, _ptr(buf)))
 
     def profile(self, enable: bool):
         self._check(lib().zkaes_ctx_profile(self._h, int(enable)))

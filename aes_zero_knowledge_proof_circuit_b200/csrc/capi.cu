@@ -8,6 +8,7 @@
 #include "circuit.h"
 #include "witness.cuh"
 #include "prover.cuh"
+#include "comm.cuh"
 #include <cstring>
 #include <stdexcept>
 
@@ -91,6 +92,7 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    zk::comm_destroy(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -101,6 +103,21 @@ uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) { return ctx ? ctx->launches :
 int zkaes_ctx_sync(zkaes_ctx* ctx) {
     NEED_CTX(ctx);
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZK_OK;
+}
+int zkaes_comm_unique_id(uint8_t out128[128]) {
+    if (!out128) return ZK_ERR_ARG;
+    std::string err;
+    return zk::comm_unique_id(out128, err);
+}
+int zkaes_ctx_comm_init(zkaes_ctx* ctx, int rank, int nranks, const uint8_t unique_id128[128]) {
+    NEED_CTX(ctx);
+    if (nranks > 1 && !unique_id128) return fail(ctx, ZK_ERR_ARG, "comm_init: null unique id");
+    return zk::comm_init(ctx, rank, nranks, unique_id128);
+}
+int zkaes_shard_range(size_t n, int rank, int nranks, size_t* start, size_t* count) {
+    if (!start || !count || nranks < 1 || rank < 0 || rank >= nranks) return ZK_ERR_ARG;
+    zk::shard_range(n, rank, nranks, start, count);
     return ZK_OK;
 }
 int zkaes_ctx_profile(zkaes_ctx* ctx, int enable) {

@@ -22,6 +22,9 @@ struct zkaes_ctx {
     std::map<uint64_t, void*> tables;
     // tuning knobs (0 = automatic)
     int msm_window_bits = 0;
+    // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
     // optional per-kernel timing of the dominant kernel (bench.py's roofline): CUDA events around every bucket
     // accumulation launch, resolved by zkaes_ctx_profile_read
     bool prof = false;

@@ -47,8 +47,8 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int 
 }
 
 template <class FrP>
-__device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, int mont, uint32_t* s) {
-    const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * i;
+__device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, size_t stride, int mont, uint32_t* s) {
+    const uint4* p = reinterpret_cast<const uint4*>(scalars) + 2 * i * stride;  // one 32-byte sector per scalar at any stride
     uint4 a = __ldg(p), b = __ldg(p + 1);
     s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
     s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
@@ -64,13 +64,13 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, i
 
 // pass 1 (scatter == nullptr): histogram.  pass 2: write sorted indices.
 template <class FrP>
-__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, uint32_t idx_base, int mont,
+__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
                                                     MsmPlan p, uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
-    load_scalar<FrP>(scalars, i, mont, s);
+    load_scalar<FrP>(scalars, i, stride, mont, s);
     const uint32_t half = 1u << (p.c - 1);
     uint32_t carry = 0;
     for (int w = 0; w < p.W; ++w) {
@@ -314,7 +314,7 @@ __global__ void k_msm_window_final(const XYZZ<C>* __restrict__ partials, uint32_
 
 template <class C>
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
-                    void* d_window_sums, int bases_internal) {
+                    void* d_window_sums, int bases_internal, size_t scalar_stride) {
     using FrP = typename C::FrP;
     using CI = typename InternalCurve<C>::type;  // all curve arithmetic below runs in the radix-2^29 form
     cudaStream_t st = ctx->stream;
@@ -335,7 +335,7 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     ZK_CUDA(ctx, acc_partial.alloc(sizeof(XYZZ<CI>) * max_items, st));
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
     DevBuf conv;
-    if (!bases_internal && n) {  // caller's bases are in the arkworks form: one conversion pass into scratch
+    if (!bases_internal && n && !std::is_same<CI, C>::value) {  // arkworks-form bases, kernels in another form: convert into scratch
         ZK_CUDA(ctx, conv.alloc(96 * n, st));
         k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, st>>>(bases, conv.as<uint32_t>(), n);
         ctx->launches++;
@@ -348,14 +348,14 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     }
     for (size_t base = 0; base < n; base += MSM_CHUNK) {
         size_t m = n - base < MSM_CHUNK ? n - base : MSM_CHUNK;
-        const uint32_t* sc = scalars + 8 * base;
+        const uint32_t* sc = scalars + 8 * base * scalar_stride;
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
-        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
+        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
                                                         nullptr);
         ctx->launches++;
         ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb));
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
-        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
+        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
                                                         offsets.as<uint32_t>(), sorted.as<uint32_t>());
         k_msm_item_counts<<<cdiv(p.nb, 256), 256, 0, st>>>(counts.as<uint32_t>(), p.nb, S, items.as<uint32_t>());
         ctx->launches += 2;
@@ -444,8 +444,8 @@ int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n) 
 template int msm_bases_to_internal<G1_377Params>(zkaes_ctx*, const void*, void*, size_t);
 template int msm_bases_to_internal<G1_381Params>(zkaes_ctx*, const void*, void*, size_t);
 
-template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int);
-template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int);
+template int msm_window_sums<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int, size_t);
+template int msm_window_sums<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, const MsmPlan&, void*, int, size_t);
 template Affine<G1_377Params> msm_fold_windows_host<G1_377Params>(const XYZZ<G1_377Params>*, int, const MsmPlan&);
 template Affine<G1_381Params> msm_fold_windows_host<G1_381Params>(const XYZZ<G1_381Params>*, int, const MsmPlan&);
 

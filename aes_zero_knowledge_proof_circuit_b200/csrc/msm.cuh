@@ -16,9 +16,10 @@ MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c);
 
 // Device-resident inputs -> W window sums (XYZZ, device).  scalars: n x 8 u32 (canonical, or Montgomery if scalars_mont).
 template <class C>
+// scalar_stride: distance between consecutive scalars in elements (cyclic sharding reads every N-th coefficient).
 // bases_internal != 0: bases are already in the internal packed form (msm_bases_to_internal); otherwise arkworks form.
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
-                    void* d_window_sums, int bases_internal = 0);
+                    void* d_window_sums, int bases_internal = 0, size_t scalar_stride = 1);
 template <class C>
 int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n);
 

@@ -252,6 +252,13 @@ __global__ void k_scale_powers(F* out, const F* in, const F* __restrict__ lo, co
     if (i >> 10) a = a * ld_fr(hi + (i >> 10));
     st_fr(out + i, a);
 }
+__global__ void k_lincomb_den(F* out, const F* a, const F* b, const F* c, F sa, F sb, F k0, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F v = ld_fr(a + i) * sa + ld_fr(b + i) * sb + ld_fr(c + i);
+    if (i == 0) v = v + k0;
+    st_fr(out + i, v);
+}
 __global__ void k_mul3(F* out, const F* a, const F* b, const F* c, F s, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_fr(out + i, ld_fr(a + i) * ld_fr(b + i) * ld_fr(c + i) * s);
@@ -417,6 +424,10 @@ int po_scale_powers(zkaes_ctx* ctx, F* out, const F* in, const F& base, size_t n
     ZK_TRY(po_powers(ctx, lo.as<F>(), 1024, base, F::one()));
     ZK_TRY(po_powers(ctx, hi.as<F>(), nhi, b1024, F::one()));
     LAUNCH(ctx, k_scale_powers, n, TB, out, in, lo.as<F>(), hi.as<F>(), n);
+    return ZK_OK;
+}
+int po_lincomb_den(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, const F& sa, const F& sb, const F& k0, size_t n) {
+    LAUNCH(ctx, k_lincomb_den, n, TB, out, a, b, c, sa, sb, k0, n);
     return ZK_OK;
 }
 int po_mul3(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_mul3, n, TB, out, a, b, c, s, n); return ZK_OK; }

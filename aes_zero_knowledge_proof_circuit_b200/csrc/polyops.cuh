@@ -59,6 +59,8 @@ int po_round3(zkaes_ctx* ctx, FrS* out, const FrS* const val[3], const FrS* cons
               const FrS vkinv[4], size_t n);
 // out[a] = in[a] * base^a   (coset shift of a coefficient vector; out may alias in)
 int po_scale_powers(zkaes_ctx* ctx, FrS* out, const FrS* in, const FrS& base, size_t n);
+// out = sa * a + sb * b + c, and out[0] += k0   (one denominator polynomial ab - alpha row - beta col + row_col)
+int po_lincomb_den(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const FrS* c, const FrS& sa, const FrS& sb, const FrS& k0, size_t n);
 // out = a * b * c * s
 int po_mul3(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
 // acc += s * a * b * c

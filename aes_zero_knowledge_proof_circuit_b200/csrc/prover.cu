@@ -18,6 +18,7 @@
 #include <stdexcept>
 #include <thread>
 
+#include "comm.cuh"
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "srs.cuh"
@@ -231,7 +232,8 @@ struct zkaes_pk_impl {
     size_t n_heavy = 0;
     Fr* elems_h = nullptr;
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
-    Aff* srs = nullptr;     // tau^i G, i <= D, in the MSM kernels' internal packed form (msm_bases_to_internal)
+    Aff* srs = nullptr;     // this rank's share of tau^i G, i <= D: the points i = rank (mod nranks), in the MSM kernels' internal form
+    size_t srs_count = 0;
     Aff gamma_g[3];         // gamma tau^i G (host)
     Aff index_comms[12];
     std::vector<uint8_t> vk_bytes;
@@ -257,10 +259,34 @@ namespace {
 
 int ntt(zkaes_ctx* ctx, Fr* data, int log_n, bool inverse, bool coset) { return ntt_device<Fr377Params>(ctx, CURVE, data, log_n, inverse, coset); }
 
-// commit(poly) through the device MSM: sum coeffs[i] * srs[offset + i]
+// commit(poly) through the device MSM: sum coeffs[i] * srs[offset + i].
+// Multi-GPU: rank r keeps the SRS points i = r (mod N) (cyclic, so that polynomials of every length and the shifted
+// commitments at the top of the SRS spread evenly), runs the bucket method on the matching every-N-th coefficients, the W
+// window sums per rank are all-gathered (NCCL) and folded on every rank: all ranks obtain the same commitment and their
+// transcripts stay in lock step.  The window plan comes from the GLOBAL n.
 int msm_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, Aff* out) {
     if (offset + n > pk.D + 1) return fail(ctx, ZK_ERR_STATE, "commit: polynomial exceeds the SRS");
-    return msm_to_affine<C>(ctx, pk.srs + offset, coeffs, n, /*scalars_mont=*/1, out, /*bases_internal=*/1);
+    const size_t N = (size_t)ctx->nranks, r = (size_t)ctx->rank;
+    // local point j is global point r + N j: first j with r + N j >= offset
+    const size_t j_lo = offset > r ? (offset - r + N - 1) / N : 0;
+    const size_t i0 = r + N * j_lo;
+    const size_t n_local = i0 < offset + n ? (offset + n - 1 - i0) / N + 1 : 0;
+    if (j_lo + n_local > pk.srs_count) return fail(ctx, ZK_ERR_STATE, "commit: local point range exceeds this rank's SRS share");
+    const Aff* bases = pk.srs + (n_local ? j_lo : 0);
+    const Fr* scalars = coeffs + (n_local ? i0 - offset : 0);
+    MsmPlan p = msm_make_plan(n ? n : 1, Fr377Params::BITS, ctx->msm_window_bits);
+    cudaStream_t st = ctx->stream;
+    DevBuf win, all;
+    const size_t wbytes = sizeof(XY) * p.W;
+    ZK_CUDA(ctx, win.alloc(wbytes, st));
+    ZK_CUDA(ctx, all.alloc(wbytes * N, st));
+    ZK_TRY(msm_window_sums<C>(ctx, bases, scalars, n_local, /*scalars_mont=*/1, p, win.p, /*bases_internal=*/1, /*scalar_stride=*/N));
+    ZK_TRY(comm_all_gather(ctx, win.p, all.p, wbytes));
+    std::vector<XY> h((size_t)p.W * N);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), all.p, wbytes * N, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = msm_fold_windows_host<C>(h.data(), (int)N, p);
+    return ZK_OK;
 }
 // KZG10::commit with an optional hiding polynomial of degree hiding_bound + 1 (three draws for hiding_bound = 1)
 int kzg_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, size_t offset, bool hiding, ChaCha20Rng& zk, Aff* out,
@@ -316,9 +342,13 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     const size_t h = pk.h, k = pk.k, x = pk.x;
 
     // ---- SRS: tau^i G on the device, gamma tau^i G (i < 3) on the host -----------------------------------------------
-    ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * (pk.D + 1)));
-    ZK_TRY(srs_powers_device<C>(ctx, tau_seed, pk.D + 1, pk.srs));
-    ZK_TRY(msm_bases_to_internal<C>(ctx, pk.srs, pk.srs, pk.D + 1));  // resident bases live in the MSM kernels' internal form
+    {
+        const size_t N = (size_t)ctx->nranks, r = (size_t)ctx->rank;
+        pk.srs_count = pk.D + 1 > r ? (pk.D + 1 - r + N - 1) / N : 0;  // points i = r (mod N), i <= D
+        ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * std::max<size_t>(pk.srs_count, 1)));
+        ZK_TRY(srs_powers_device<C>(ctx, tau_seed, pk.srs_count, pk.srs, /*start=*/r, /*stride=*/N));
+    }
+    ZK_TRY(msm_bases_to_internal<C>(ctx, pk.srs, pk.srs, pk.srs_count));  // resident bases live in the MSM kernels' internal form
     Fr tau = fr_from_seed(tau_seed), gamma = fr_from_seed(gamma_seed);
     Fr gt = gamma;
     for (int i = 0; i < 3; ++i) {
@@ -600,23 +630,24 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const int log4k = pk.log_k + 2;
     const Fr ab = alpha * beta;
     const Fr g = coset_gen(), w4k = domain_gen(log4k);
-    DevBuf V, dden[3], tA, tB;
+    DevBuf V, dden[3], tA;
     ZK_CUDA(ctx, V.alloc(sizeof(Fr) * 4 * k, st));
     for (int m = 0; m < 3; ++m) ZK_CUDA(ctx, dden[m].alloc(sizeof(Fr) * k, st));
     ZK_CUDA(ctx, tA.alloc(sizeof(Fr) * k, st));
-    ZK_CUDA(ctx, tB.alloc(sizeof(Fr) * k, st));
     auto to_coset = [&](Fr* dst, const Fr* poly, const Fr& shift) -> int {  // dst[i] = poly(shift * w_K^i)
         ZK_TRY(po_scale_powers(ctx, dst, poly, shift, k));
         return ntt(ctx, dst, pk.log_k, false, false);
     };
+    // Multi-GPU: the four cosets are independent -- rank (j mod N) evaluates coset j and broadcasts its |K| values
+    // (NVLink; 4.3 GB per coset at 4 KiB), instead of every rank repeating all four.
     Fr sj = g;
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 4; ++j, sj = sj * w4k) {
+        if (j % ctx->nranks != ctx->rank) continue;
         for (int m = 0; m < 3; ++m) {
+            // the denominator is linear in (row, col, row_col): combine the coefficient vectors first, one NTT instead of three
             Fr* const* P = &pk.idx_poly[4 * m];
-            ZK_TRY(to_coset(dden[m].as<Fr>(), P[0], sj));
-            ZK_TRY(to_coset(tA.as<Fr>(), P[1], sj));
-            ZK_TRY(to_coset(tB.as<Fr>(), P[3], sj));
-            ZK_TRY(po_den_coset(ctx, dden[m].as<Fr>(), tA.as<Fr>(), tB.as<Fr>(), alpha, beta, ab, k));
+            ZK_TRY(po_lincomb_den(ctx, dden[m].as<Fr>(), P[0], P[1], P[3], alpha.neg(), beta.neg(), ab, k));
+            ZK_TRY(to_coset(dden[m].as<Fr>(), dden[m].as<Fr>(), sj));
         }
         Fr* Vj = V.as<Fr>() + (size_t)j * k;
         ZK_TRY(to_coset(tA.as<Fr>(), fpoly.as<Fr>(), sj));
@@ -631,11 +662,11 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         // back to the coefficients of the degree-<|K| interpolant on this coset, with the shift undone
         ZK_TRY(ntt(ctx, Vj, pk.log_k, true, false));
         ZK_TRY(po_scale_powers(ctx, Vj, Vj, sj.inverse(), k));
-        sj = sj * w4k;
     }
+    if (ctx->nranks > 1)
+        for (int j = 0; j < 4; ++j) ZK_TRY(comm_broadcast(ctx, V.as<Fr>() + (size_t)j * k, sizeof(Fr) * k, j % ctx->nranks));
     for (int m = 0; m < 3; ++m) dden[m].release();
     tA.release();
-    tB.release();
     ZK_TRY(po_coset4_combine(ctx, V.as<Fr>(), k, fr_pow_u64(g, k).inverse(), fr_pow_u64(w4k, k).inverse()));
     Fr* h2 = V.as<Fr>();  // 3|K| - 3 coefficients (block 3 is zero: deg h_2 < 3|K|)
     const size_t len_h2 = 3 * k - 3;

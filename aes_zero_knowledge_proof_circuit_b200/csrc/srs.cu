@@ -38,12 +38,14 @@ __global__ void k_fb_fill(const Affine<C>* __restrict__ rows, Affine<C>* __restr
 // scalar_i = lo[i & 1023] * hi[i >> 10]  (Montgomery), converted to canonical bytes
 template <class C>
 __global__ void __launch_bounds__(128) k_fb_mul(const Affine<C>* __restrict__ table, const Fp<typename C::FrP>* __restrict__ pw_lo,
-                                               const Fp<typename C::FrP>* __restrict__ pw_hi, size_t n, Affine<C>* __restrict__ out) {
+                                               const Fp<typename C::FrP>* __restrict__ pw_hi, size_t start, size_t stride, size_t n,
+                                               Affine<C>* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     using Fr = Fp<typename C::FrP>;
-    Fr s = pw_lo[i & 1023];
-    if (i >> 10) s = s * pw_hi[i >> 10];
+    const size_t e = start + i * stride;  // exponent of tau
+    Fr s = pw_lo[e & 1023];
+    if (e >> 10) s = s * pw_hi[e >> 10];
     s = s.from_mont();
     XYZZ<C> acc = XYZZ<C>::inf();
     for (int w = 0; w < FB_WINDOWS; ++w) {
@@ -68,7 +70,7 @@ __global__ void k_pow_table_srs(F* out, size_t count, F base, int shift) {
 }
 
 template <class C>
-int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out) {
+int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out, size_t start, size_t stride) {
     using Fr = Fp<typename C::FrP>;
     cudaStream_t st = ctx->stream;
     // tau: seed as a 252-bit integer (always < r for both curves), lifted to Montgomery form
@@ -79,21 +81,21 @@ int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* 
     DevBuf rows, table, lo, hi;
     ZK_CUDA(ctx, rows.alloc(sizeof(Affine<C>) * FB_WINDOWS, st));
     ZK_CUDA(ctx, table.alloc(sizeof(Affine<C>) * FB_WINDOWS * FB_ROW, st));
-    size_t hi_cnt = (n >> 10) + 1;
+    size_t hi_cnt = ((start + n * stride) >> 10) + 1;
     ZK_CUDA(ctx, lo.alloc(sizeof(Fr) * 1024, st));
     ZK_CUDA(ctx, hi.alloc(sizeof(Fr) * hi_cnt, st));
     k_fb_rows<C><<<1, FB_WINDOWS, 0, st>>>(rows.as<Affine<C>>());
     k_fb_fill<C><<<cdiv(FB_WINDOWS * FB_ROW, 64), 64, 0, st>>>(rows.as<Affine<C>>(), table.as<Affine<C>>());
     k_pow_table_srs<Fr><<<4, 256, 0, st>>>(lo.as<Fr>(), 1024, tau, 0);
     k_pow_table_srs<Fr><<<cdiv(hi_cnt, 256), 256, 0, st>>>(hi.as<Fr>(), hi_cnt, tau, 10);
-    if (n) k_fb_mul<C><<<cdiv(n, 128), 128, 0, st>>>(table.as<Affine<C>>(), lo.as<Fr>(), hi.as<Fr>(), n,
+    if (n) k_fb_mul<C><<<cdiv(n, 128), 128, 0, st>>>(table.as<Affine<C>>(), lo.as<Fr>(), hi.as<Fr>(), start, stride, n,
                                                      reinterpret_cast<Affine<C>*>(d_out));
     ctx->launches += 5;
     ZK_CUDA(ctx, cudaGetLastError());
     return ZK_OK;
 }
 
-template int srs_powers_device<G1_377Params>(zkaes_ctx*, const uint8_t*, size_t, void*);
-template int srs_powers_device<G1_381Params>(zkaes_ctx*, const uint8_t*, size_t, void*);
+template int srs_powers_device<G1_377Params>(zkaes_ctx*, const uint8_t*, size_t, void*, size_t, size_t);
+template int srs_powers_device<G1_381Params>(zkaes_ctx*, const uint8_t*, size_t, void*, size_t, size_t);
 
 }  // namespace zk

@@ -4,5 +4,6 @@
 #include "ec.cuh"
 namespace zk {
 template <class C>
-int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out);
+// out[i] = tau^(start + i * stride) * G, i < n
+int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out, size_t start = 0, size_t stride = 1);
 }

@@ -49,6 +49,19 @@ void* zkaes_ctx_stream(zkaes_ctx* ctx);
 uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx);
 /* Blocks until all work queued on the context's stream has finished. */
 int zkaes_ctx_sync(zkaes_ctx* ctx);
+/* ---- multi-GPU (one process and one context per GPU) ---------------------------------------------------------------
+ * The prover's MSMs shard by point: rank r keeps the SRS points i = r (mod N) (cyclic, so polynomials of every length
+ * spread evenly), runs the bucket method on them and the per-rank window sums (W x 192 B) are all-gathered over NCCL and
+ * folded on every rank; witness generation and NTTs stay
+ * per GPU (every rank computes them redundantly, so transcripts stay identical).  Rank 0 obtains an id with
+ * zkaes_comm_unique_id and distributes it out of band (bench.py: torch.distributed broadcast); every rank then calls
+ * zkaes_ctx_comm_init BEFORE zkaes_synthesize_keys.  All ranks must issue the same sequence of key / encrypt calls.
+ * zkaes_shard_range is the contiguous point-range rule for callers that shard their own zkaes_msm_g1_windows inputs
+ * (host only). */
+int zkaes_comm_unique_id(uint8_t out128[128]);
+int zkaes_ctx_comm_init(zkaes_ctx* ctx, int rank, int nranks, const uint8_t unique_id128[128]);
+int zkaes_shard_range(size_t n, int rank, int nranks, size_t* start, size_t* count);
+
 /* Per-kernel timing of the dominant kernel (the MSM bucket accumulation) for bench.py's roofline: when enabled, every
  * launch is bracketed by CUDA events on the context's stream.  profile_read synchronises and returns
  * out = {launches, total ms, total MSM terms, total mixed additions (upper bound)} since the last read, then resets. */
