@@ -29,12 +29,12 @@ using namespace zk;
 template <class C>
 static int msm_windows_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n_local, size_t n_total, int mont,
                             void* windows_dev) {
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, 1, ctx->msm_window_max);
     return msm_window_sums<C>(ctx, bases, scalars, n_local, mont & 1, p, windows_dev, (mont >> 1) & 1);
 }
 template <class C>
 static int msm_fold_impl(zkaes_ctx* ctx, const void* gathered, int n_ranks, size_t n_total, void* out96) {
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, 1, ctx->msm_window_max);
     std::vector<XYZZ<C>> h((size_t)n_ranks * p.W);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), gathered, sizeof(XYZZ<C>) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -44,7 +44,7 @@ static int msm_fold_impl(zkaes_ctx* ctx, const void* gathered, int n_ranks, size
 }
 template <class C>
 static int msm_device_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n, int mont, void* out96) {
-    MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits);
+    MsmPlan p = msm_make_plan(n ? n : 1, C::FrP::BITS, ctx->msm_window_bits, 1, ctx->msm_window_max);
     DevBuf win;
     ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * p.W, ctx->stream));
     ZK_TRY(msm_window_sums<C>(ctx, bases, scalars, n, mont & 1, p, win.p, (mont >> 1) & 1));
@@ -203,7 +203,7 @@ int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, si
 size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total) {
     if (!ctx) return 0;
     int bits = curve_id == 377 ? Fr377Params::BITS : Fr381Params::BITS;
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, bits, ctx->msm_window_bits);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, bits, ctx->msm_window_bits, 1, ctx->msm_window_max);
     return (size_t)p.W * 192;
 }
 int zkaes_msm_g1_windows(zkaes_ctx* ctx, int curve_id, const void* bases, const void* scalars, size_t n_local, size_t n_total,

@@ -2,49 +2,27 @@
 //
 // Replaces ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul(&[G1Affine], &[BigInteger256]) -> G1Projective`
 // (reference Cargo.lock:118-120; reached from src/lib.rs:111 via ark-poly-commit's `commit`/`open`).
-// Same inputs (affine bases, canonical 256-bit scalars), same mathematical result; the schedule is GPU-first:
+// Same inputs (affine bases, canonical 256-bit scalars < r), same mathematical result; the schedule is GPU-first
+// (per-thread bodies and their rationale: msm_core.cuh):
 //
-//   1. k_msm_count    : signed c-bit digits per scalar, histogram of (window, |digit|) keys      [HBM: 32 B/term]
-//   2. k_scan_*       : exclusive scan of the histogram -> bucket offsets
-//   3. k_msm_scatter  : counting-sort of point indices (sign in bit 31) by bucket key
-//   4. k_msm_accumulate: one thread per bucket, XYZZ += affine (8M+2S), 128-bit coalesced base loads [ALU bound]
-//   5. k_msm_reduce   : per-window sum_k k*B_k by segmented running sums + shared-memory tree
-//   6. k_msm_window_final: fold the per-block partials -> W window sums (XYZZ) on device
+//   1. k_msm_digits    : s -> min(s, r-s), signed c-bit digits, histogram of (window, |digit|) keys   [HBM: 32 B/term]
+//   2. k_scan_*        : exclusive scan of the histogram -> bucket offsets (nb + 1 entries)
+//   3. k_msm_digits    : counting-sort scatter of point indices (sign in bit 31) by bucket key
+//   4. k_msm_accumulate: equal-length slices of the sorted entries, one thread each, XYZZ += affine (8M+2S)  [ALU bound]
+//   5. k_msm_merge     : buckets cut by slice boundaries = tail + heads
+//   6. k_msm_reduce / k_msm_window_final: per-window sum_k k*B_k -> W window sums (XYZZ) on device
 // The c*W doublings of the final Horner fold and the affine normalisation are O(W*c) work and run on the
 // host (portable arithmetic in ff.cuh) because the result is consumed by the host-side transcript anyway.
 // Multi-GPU: each rank runs 1-6 on its point range; window sums are all-gathered and folded (see capi.cu).
 //
 // Large inputs are processed in chunks of at most MSM_CHUNK points so that the sort scratch stays bounded;
-// buckets persist across chunks.
+// buckets persist across chunks.  No host synchronisation inside an MSM: grids are sized from upper bounds and the
+// kernels read the actual entry count from offsets[nb].
 #include "msm.cuh"
 
 namespace zk {
 
-static constexpr size_t MSM_CHUNK = (size_t)1 << 24;
-
-__host__ MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c) {
-    MsmPlan p;
-    int lg = 0;
-    while (((size_t)2 << lg) <= n) ++lg;  // floor(log2 n), n >= 1
-    int c = forced_c > 0 ? forced_c : lg - 3;
-    if (forced_c <= 0) {
-        if (c > 16) c = 16;
-        if (c < 3) c = 3;
-    }
-    p.c = c;
-    p.W = (fr_bits + 1 + c - 1) / c;
-    p.nbw = 1u << (c - 1);
-    p.nb = p.nbw * (uint32_t)p.W;
-    return p;
-}
-
-__device__ __forceinline__ uint32_t scalar_bits(const uint32_t* s, int pos, int c) {
-    int limb = pos >> 5, off = pos & 31;
-    if (limb >= 8) return 0;
-    uint64_t v = s[limb];
-    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
-    return (uint32_t)(v >> off) & ((1u << c) - 1);
-}
+static constexpr size_t MSM_CHUNK = (size_t)1 << 26;  // sort scratch: 4 B x W per point (3.2 GB at W = 12)
 
 template <class FrP>
 __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, size_t stride, int mont, uint32_t* s) {
@@ -62,7 +40,7 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, s
     }
 }
 
-// pass 1 (scatter == nullptr): histogram.  pass 2: write sorted indices.
+// pass 1 (sorted == nullptr): histogram.  pass 2: write sorted indices.
 template <class FrP>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
                                                     MsmPlan p, uint32_t* __restrict__ counts,
@@ -71,24 +49,12 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
     if (i >= n) return;
     uint32_t s[8];
     load_scalar<FrP>(scalars, i, stride, mont, s);
-    const uint32_t half = 1u << (p.c - 1);
-    uint32_t carry = 0;
-    for (int w = 0; w < p.W; ++w) {
-        uint32_t d = scalar_bits(s, w * p.c, p.c) + carry;
-        uint32_t neg = 0;
-        if (d > half) {
-            d = (1u << p.c) - d;
-            carry = 1;
-            neg = 1;
-        } else {
-            carry = 0;
-        }
-        if (d) {
-            uint32_t key = (uint32_t)w * p.nbw + d - 1;
-            uint32_t pos = atomicAdd(&counts[key], 1u);
-            if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
-        }
-    }
+    const uint32_t flip = msm_fold_scalar<FrP>(s);
+    const uint32_t idx = idx_base + (uint32_t)i;
+    msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t neg) {
+        uint32_t pos = atomicAdd(&counts[key], 1u);
+        if (sorted) sorted[offsets[key] + pos] = idx | (neg << 31);
+    });
 }
 
 // ---- exclusive scan over <= 2^22 counters: per-block scan, scan of block sums, add-back -----------------
@@ -143,23 +109,8 @@ int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32
 }
 
 // ---- bucket accumulation ---------------------------------------------------------------------------------
-// Bases are read in the INTERNAL packed form: per coordinate the radix-2^29 Montgomery representative (R' = 2^(29 NL))
-// as a plain little-endian integer in 48 bytes -- the same 96 B per point as the arkworks form, 6 x 128-bit loads.
-template <class CI>
-__device__ __forceinline__ Affine<CI> load_affine(const uint32_t* __restrict__ bases, uint32_t idx) {
-    using Fq = typename Affine<CI>::Fq;
-    uint32_t w[24];
-    const uint4* p = reinterpret_cast<const uint4*>(bases + (size_t)idx * 24);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        uint4 v = __ldg(p + k);
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-    }
-    Affine<CI> r;
-    r.x = Fq::unpack(w);
-    r.y = Fq::unpack(w + 12);
-    return r;
-}
+// Bases are read in the INTERNAL packed form (for the default build this IS the arkworks form: 12 x u32 Montgomery limbs
+// per coordinate, 96 B per point, 6 x 128-bit loads; -DZK_MSM_R29 selects the radix-2^29 representative in the same 96 B).
 // arkworks wire form (Montgomery R = 2^384 limbs) -> internal packed form; in place when dst == src
 template <class C>
 __global__ void __launch_bounds__(128) k_bases_to_internal(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
@@ -195,79 +146,21 @@ __global__ void k_windows_to_std(const XYZZ<typename InternalCurve<C>::type>* __
     out[w] = r;
 }
 
-// Work items: bucket b is cut into ceil(count[b] / S) slices of at most S sorted entries, so a heavily loaded bucket
-// (the partially filled top window, repeated scalars, ...) is shared by several threads instead of serialising on one.
-__global__ void __launch_bounds__(256) k_msm_item_counts(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t S,
-                                                         uint32_t* __restrict__ items) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) items[b] = (counts[b] + S - 1) / S;
-}
-
-// one thread per work item: partial[item] = sum of its slice (XYZZ += affine, 8M+2S each)
 template <class C>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ counts,
-                                                        const uint32_t* __restrict__ item_off, uint32_t nb, uint32_t n_items,
-                                                        uint32_t S, XYZZ<C>* __restrict__ partial) {
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n_items) return;
-    // bucket = last b with item_off[b] <= it   (item_off is the exclusive scan of items per bucket)
-    uint32_t lo = 0, hi = nb;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(item_off + mid) <= it) lo = mid; else hi = mid;
-    }
-    const uint32_t b = lo;
-    const uint32_t k0 = (it - __ldg(item_off + b)) * S;
-    uint32_t cnt = __ldg(counts + b) - k0;
-    if (cnt > S) cnt = S;
-    const uint32_t* lst = sorted + __ldg(offsets + b) + k0;
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t k = 0; k < cnt; ++k) {
-        uint32_t e = __ldg(lst + k);
-        Affine<C> pt = load_affine<C>(bases, e & 0x7fffffffu);
-        if (e >> 31) pt.y = pt.y.neg();
-        acc.madd(pt);
-    }
-    partial[it] = acc;
+                                                        const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t L,
+                                                        XYZZ<C>* __restrict__ buckets, XYZZ<C>* __restrict__ head, XYZZ<C>* __restrict__ tail) {
+    msm_slice_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, L, offsets, nb, sorted, bases, buckets, head, tail);
 }
 
-// one thread per bucket: bucket (+)= its partials
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_merge(const XYZZ<C>* __restrict__ partial, const uint32_t* __restrict__ item_off,
-                                                   const uint32_t* __restrict__ items, uint32_t nb, XYZZ<C>* __restrict__ buckets,
-                                                   int first) {
+__global__ void __launch_bounds__(128) k_msm_merge(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t L, XYZZ<C>* __restrict__ buckets,
+                                                   const XYZZ<C>* __restrict__ head, const XYZZ<C>* __restrict__ tail) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nb) return;
-    uint32_t m = items[b];
-    if (m == 0) {
-        if (first) buckets[b] = XYZZ<C>::inf();
-        return;
-    }
-    const XYZZ<C>* p = partial + item_off[b];
-    XYZZ<C> acc;
-    if (first) {
-        acc = p[0];
-        for (uint32_t k = 1; k < m; ++k) acc.add(p[k]);
-    } else {
-        acc = buckets[b];
-        for (uint32_t k = 0; k < m; ++k) acc.add(p[k]);
-    }
-    buckets[b] = acc;
+    if (b < nb) msm_merge_bucket<C>(b, L, offsets, buckets, head, tail);
 }
 
 // ---- bucket reduction: S_w = sum_{j<nbw} (j+1) * B[w][j] ---------------------------------------------------
-template <class C>
-__device__ XYZZ<C> mul_small(const XYZZ<C>& p, uint32_t k) {
-    XYZZ<C> r = XYZZ<C>::inf();
-    for (int b = 31 - __clz(k | 1); b >= 0; --b) {
-        r = r.dbl();
-        if ((k >> b) & 1) r.add(p);
-    }
-    return k ? r : XYZZ<C>::inf();
-}
-
 static constexpr int RED_BS = 128;
 // grid: (blocks_per_window, W).  Each thread owns `seg` consecutive buckets of its window.
 template <class C>
@@ -276,21 +169,7 @@ __global__ void __launch_bounds__(RED_BS) k_msm_reduce(const XYZZ<C>* __restrict
     __shared__ XYZZ<C> sh[RED_BS];
     uint32_t w = blockIdx.y;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // segment id within window
-    uint32_t lo = t * seg;
-    XYZZ<C> contrib = XYZZ<C>::inf();
-    if (lo < nbw) {
-        uint32_t hi = lo + seg < nbw ? lo + seg : nbw;
-        const XYZZ<C>* B = buckets + (size_t)w * nbw;
-        XYZZ<C> running = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
-        for (uint32_t j = hi; j-- > lo;) {
-            running.add(B[j]);
-            acc.add(running);
-        }
-        // sum (j+1) B_j = acc + lo * running      (acc = sum (j-lo+1) B_j)
-        contrib = mul_small<C>(running, lo);
-        contrib.add(acc);
-    }
-    sh[threadIdx.x] = contrib;
+    sh[threadIdx.x] = msm_reduce_segment<C>(buckets + (size_t)w * nbw, nbw, seg, t);
     __syncthreads();
     for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
@@ -303,95 +182,107 @@ __global__ void __launch_bounds__(RED_BS) k_msm_reduce(const XYZZ<C>* __restrict
     if (threadIdx.x == 0) partials[(size_t)w * gridDim.x + blockIdx.x] = sh[0];
 }
 
+// one warp per window: lane-strided partial sums, then a shuffle-free fold through shared memory
 template <class C>
-__global__ void k_msm_window_final(const XYZZ<C>* __restrict__ partials, uint32_t per_window, XYZZ<C>* __restrict__ out) {
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= gridDim.x * blockDim.x) return;
+__global__ void __launch_bounds__(32) k_msm_window_final(const XYZZ<C>* __restrict__ partials, uint32_t per_window, XYZZ<C>* __restrict__ out) {
+    __shared__ XYZZ<C> sh[32];
+    const uint32_t w = blockIdx.x;
     XYZZ<C> a = XYZZ<C>::inf();
-    for (uint32_t k = 0; k < per_window; ++k) a.add(partials[(size_t)w * per_window + k]);
-    out[w] = a;
+    for (uint32_t k = threadIdx.x; k < per_window; k += 32) a.add(partials[(size_t)w * per_window + k]);
+    sh[threadIdx.x] = a;
+    __syncwarp();
+    for (int s = 16; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            XYZZ<C> x = sh[threadIdx.x];
+            x.add(sh[threadIdx.x + s]);
+            sh[threadIdx.x] = x;
+        }
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) out[w] = sh[0];
+}
+
+// slice length of the accumulation: long enough to amortise the per-slice bookkeeping and keep the partial arrays
+// small, short enough for >= ~16 waves of threads on 148 SMs x 384 resident threads
+static uint32_t msm_slice_len(uint64_t max_entries) {
+    uint64_t L = max_entries / (148ull * 384 * 16);
+    if (L < 32) L = 32;
+    if (L > 512) L = 512;
+    return (uint32_t)L;
 }
 
 template <class C>
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
                     void* d_window_sums, int bases_internal, size_t scalar_stride) {
     using FrP = typename C::FrP;
-    using CI = typename InternalCurve<C>::type;  // all curve arithmetic below runs in the radix-2^29 form
+    using CI = typename InternalCurve<C>::type;  // the form the curve arithmetic below runs in
     cudaStream_t st = ctx->stream;
-    DevBuf counts, offsets, sorted, buckets, partials, items, item_off, acc_partial;
-    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * p.nb, st));
-    ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * p.nb, st));
-    ZK_CUDA(ctx, items.alloc(sizeof(uint32_t) * p.nb, st));
-    ZK_CUDA(ctx, item_off.alloc(sizeof(uint32_t) * p.nb, st));
+    if (n == 0) {
+        ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * p.W, st));
+        return ZK_OK;
+    }
+    // entries per chunk stay below 2^31 (u32 offsets, sign bit in the sorted indices)
+    size_t chunk_max = MSM_CHUNK;
+    while (chunk_max * (size_t)p.W >= ((size_t)1 << 31)) chunk_max >>= 1;
+    chunk_max = (n + (n + chunk_max - 1) / chunk_max - 1) / ((n + chunk_max - 1) / chunk_max);  // equal chunks (n = 2^k + 1 must not leave a 1-point chunk)
+    if (n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_UNSUPPORTED, "msm: more than 2^31 points");
+    const uint64_t max_entries = (uint64_t)chunk_max * p.W;
+    const uint32_t L = msm_slice_len(max_entries);
+    const size_t max_slices = (size_t)((max_entries + L - 1) / L);
+    DevBuf counts, offsets, sorted, buckets, partials, head, tail;
+    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+    ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
-    size_t chunk_max = n < MSM_CHUNK ? n : MSM_CHUNK;
-    ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * chunk_max * p.W, st));
-    // slice length: twice the mean bucket load, clamped; #items <= nb + chunk*W/S
-    uint64_t mean = ((uint64_t)chunk_max * p.W + p.nb - 1) / p.nb;
-    uint32_t S = (uint32_t)(2 * mean);
-    if (S < 16) S = 16;
-    if (S > 1024) S = 1024;
-    size_t max_items = (size_t)p.nb + (chunk_max * p.W) / S + 1;
-    ZK_CUDA(ctx, acc_partial.alloc(sizeof(XYZZ<CI>) * max_items, st));
+    ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
+    ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+    ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<CI>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
     DevBuf conv;
-    if (!bases_internal && n && !std::is_same<CI, C>::value) {  // arkworks-form bases, kernels in another form: convert into scratch
+    if (!bases_internal && !std::is_same<CI, C>::value) {  // arkworks-form bases, kernels in another form: convert into scratch
         ZK_CUDA(ctx, conv.alloc(96 * n, st));
         k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, st>>>(bases, conv.as<uint32_t>(), n);
         ctx->launches++;
         bases = conv.as<uint32_t>();
     }
     const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
-    if (n == 0) {
-        ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * p.W, st));
-        return ZK_OK;
-    }
-    for (size_t base = 0; base < n; base += MSM_CHUNK) {
-        size_t m = n - base < MSM_CHUNK ? n - base : MSM_CHUNK;
+    for (size_t base = 0; base < n; base += chunk_max) {
+        size_t m = n - base < chunk_max ? n - base : chunk_max;
         const uint32_t* sc = scalars + 8 * base * scalar_stride;
-        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
+        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nb + 1), st));
         k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
                                                         nullptr);
         ctx->launches++;
-        ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb));
-        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * p.nb, st));
+        // scanning nb + 1 counters (the last one is zero) leaves the total entry count in offsets[nb]
+        ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb + 1));
+        ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
         k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
                                                         offsets.as<uint32_t>(), sorted.as<uint32_t>());
-        k_msm_item_counts<<<cdiv(p.nb, 256), 256, 0, st>>>(counts.as<uint32_t>(), p.nb, S, items.as<uint32_t>());
-        ctx->launches += 2;
-        ZK_TRY(exclusive_scan_u32(ctx, items.as<uint32_t>(), item_off.as<uint32_t>(), p.nb));
-        // total item count = last offset + last count (tiny D2H; the launch below needs it for its grid)
-        uint32_t tail[2];
-        ZK_CUDA(ctx, cudaMemcpyAsync(&tail[0], item_off.as<uint32_t>() + (p.nb - 1), 4, cudaMemcpyDeviceToHost, st));
-        ZK_CUDA(ctx, cudaMemcpyAsync(&tail[1], items.as<uint32_t>() + (p.nb - 1), 4, cudaMemcpyDeviceToHost, st));
-        ZK_CUDA(ctx, cudaStreamSynchronize(st));
-        uint32_t n_items = tail[0] + tail[1];
-        if (n_items > max_items) return fail(ctx, ZK_ERR_STATE, "msm: work-item count exceeds its bound");
-        if (n_items) {
-            zkaes_ctx::ProfSpan span{};
-            if (ctx->prof) {
-                cudaEventCreate(&span.e0);
-                cudaEventCreate(&span.e1);
-                cudaEventRecord(span.e0, st);
-            }
-            k_msm_accumulate<CI><<<cdiv(n_items, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(),
-                                                                   counts.as<uint32_t>(), item_off.as<uint32_t>(), p.nb, n_items, S,
-                                                                   acc_partial.as<XYZZ<CI>>());
-            ctx->launches++;
-            if (ctx->prof) {
-                cudaEventRecord(span.e1, st);
-                span.terms = m;
-                span.madds = (uint64_t)m * p.W;  // upper bound: zero digits are skipped
-                ctx->prof_spans.push_back(span);
-            }
+        ctx->launches++;
+        const size_t slices = (size_t)(((uint64_t)m * p.W + L - 1) / L);  // upper bound: zero digits produce no entry
+        zkaes_ctx::ProfSpan span{};
+        if (ctx->prof) {
+            cudaEventCreate(&span.e0);
+            cudaEventCreate(&span.e1);
+            cudaEventRecord(span.e0, st);
         }
-        k_msm_merge<CI><<<cdiv(p.nb, 128), 128, 0, st>>>(acc_partial.as<XYZZ<CI>>(), item_off.as<uint32_t>(), items.as<uint32_t>(), p.nb,
-                                                       buckets.as<XYZZ<CI>>(), base == 0);
+        k_msm_accumulate<CI><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, L,
+                                                                buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>());
+        ctx->launches++;
+        if (ctx->prof) {
+            cudaEventRecord(span.e1, st);
+            span.terms = m;
+            span.madds = (uint64_t)m * p.W;  // upper bound: zero digits are skipped
+            ctx->prof_spans.push_back(span);
+        }
+        k_msm_merge<CI><<<cdiv(p.nb, 128), 128, 0, st>>>(offsets.as<uint32_t>(), p.nb, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
+                                                         tail.as<XYZZ<CI>>());
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
     }
-    // reduction
+    // reduction: segments of <= 64 buckets (the per-segment lo * running product costs ~2 log2(nbw) group operations)
     uint32_t tpw = p.nbw < 2048 ? p.nbw : 2048;  // threads (segments) per window
+    if (p.nbw / 64 > tpw) tpw = p.nbw / 64;
     uint32_t seg = p.nbw / tpw;
     uint32_t bs = tpw < RED_BS ? tpw : RED_BS;
     uint32_t bpw = tpw / bs;
@@ -399,7 +290,7 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     k_msm_reduce<CI><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<CI>>(), p.nbw, seg, partials.as<XYZZ<CI>>());
     DevBuf win_int;
     ZK_CUDA(ctx, win_int.alloc(sizeof(XYZZ<CI>) * p.W, st));
-    k_msm_window_final<CI><<<1, p.W, 0, st>>>(partials.as<XYZZ<CI>>(), bpw, win_int.as<XYZZ<CI>>());
+    k_msm_window_final<CI><<<p.W, 32, 0, st>>>(partials.as<XYZZ<CI>>(), bpw, win_int.as<XYZZ<CI>>());
     k_windows_to_std<C><<<cdiv(p.W, 32), 32, 0, st>>>(win_int.as<XYZZ<CI>>(), reinterpret_cast<XYZZ<C>*>(d_window_sums), p.W);
     ctx->launches += 3;
     ZK_CUDA(ctx, cudaGetLastError());

@@ -2,17 +2,9 @@
 #pragma once
 #include "common.cuh"
 #include "ec.cuh"
+#include "msm_core.cuh"  // MsmPlan, msm_make_plan, the per-thread kernel bodies
 
 namespace zk {
-
-struct MsmPlan {
-    int c;         // window bits (signed digits in [-2^(c-1), 2^(c-1)])
-    int W;         // number of windows = ceil((Fr bits + 1) / c)
-    uint32_t nbw;  // buckets per window = 2^(c-1)
-    uint32_t nb;   // total buckets
-};
-
-MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c);
 
 // Device-resident inputs -> W window sums (XYZZ, device).  scalars: n x 8 u32 (canonical, or Montgomery if scalars_mont).
 template <class C>

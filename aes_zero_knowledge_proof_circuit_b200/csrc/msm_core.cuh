@@ -1,0 +1,250 @@
+// Per-thread bodies of the MSM kernels (msm.cu), written as host/device functions of the thread index so that the
+// same code runs inside the CUDA kernels and, sequentially, inside the CPU emulation that tests/ uses to check the index
+// bookkeeping without a GPU (msm_emul.cpp).  Nothing here is a CPU fallback: the product only ever launches the kernels.
+//
+// Pipeline (per chunk of at most `chunk` points; buckets persist across chunks):
+//   digits     s -> min(s, r - s) (sign folded into the point), then signed c-bit digits; key = window * 2^(c-1) + |d| - 1
+//   sort       counting sort of point indices by key (histogram, exclusive scan, scatter)
+//   accumulate the sorted entry array is cut into SLICES OF EQUAL LENGTH L, one thread each, regardless of bucket
+//              boundaries: every thread performs exactly L mixed additions, so a warp never waits for its most loaded
+//              bucket (the thread-per-bucket form ran at 26.4 / 32 active lanes, profiles/r1_ncu_full_msm_accumulate_c16.txt).
+//              A bucket that lies inside one slice is updated in place; a bucket cut by slice boundaries leaves one
+//              partial per slice (`tail` for the slice it starts in, `head` for the slices it continues into).
+//   merge      bucket = tail + sum of heads, for the buckets that were cut
+//   reduce     S_w = sum_j (j + 1) B[w][j]
+#pragma once
+#include "ec.cuh"
+
+namespace zk {
+
+struct MsmPlan {
+    int c;         // window bits (signed digits in [-2^(c-1), 2^(c-1)])
+    int W;         // number of windows = ceil(Fr bits / c): scalars are folded to s <= (r-1)/2 first
+    uint32_t nbw;  // buckets per window = 2^(c-1)
+    uint32_t nb;   // total buckets
+};
+
+// ---- digits --------------------------------------------------------------------------------------------------------
+// s (canonical, < r) -> min(s, r - s); returns 1 when r - s was taken (the term becomes (r - s) * (-P)).
+template <class FrP>
+ZK_HD uint32_t msm_fold_scalar(uint32_t* s) {
+    uint32_t m[8], t[8], d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = FrP::MOD(i);
+    sub_n<8>(t, m, s);                  // r - s  (s = 0 gives r, which is not < s)
+    uint32_t lt = sub_n<8>(d, t, s);    // borrow <=> r - s < s
+    if (lt) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = t[i];
+    }
+    return lt;
+}
+
+ZK_HD uint32_t msm_scalar_bits(const uint32_t* s, int pos, int c) {
+    int limb = pos >> 5, off = pos & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+// Calls emit(key, neg) for every non-zero digit of the (folded) scalar.
+template <class Emit>
+ZK_HD void msm_for_each_digit(const uint32_t* s, uint32_t flip, const MsmPlan& p, Emit&& emit) {
+    const uint32_t half = 1u << (p.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < p.W; ++w) {
+        uint32_t d = msm_scalar_bits(s, w * p.c, p.c) + carry;
+        uint32_t neg = 0;
+        if (d > half) {
+            d = (1u << p.c) - d;
+            carry = 1;
+            neg = 1;
+        } else {
+            carry = 0;
+        }
+        if (d) emit((uint32_t)w * p.nbw + d - 1, neg ^ flip);
+    }
+}
+
+// ---- 128-bit moves of points -----------------------------------------------------------------------------------------
+template <class C>
+ZK_HD Affine<C> msm_load_affine(const uint32_t* bases, uint32_t idx) {
+    using Fq = typename Affine<C>::Fq;
+    uint32_t w[24];
+#if defined(__CUDA_ARCH__)
+    const uint4* p = reinterpret_cast<const uint4*>(bases + (size_t)idx * 24);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        uint4 v = __ldg(p + k);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+#else
+    for (int k = 0; k < 24; ++k) w[k] = bases[(size_t)idx * 24 + k];
+#endif
+    Affine<C> r;
+    r.x = Fq::unpack(w);
+    r.y = Fq::unpack(w + 12);
+    return r;
+}
+template <class C>
+ZK_HD XYZZ<C> msm_load_xyzz(const XYZZ<C>* p) {
+#if defined(__CUDA_ARCH__)
+    static_assert(sizeof(XYZZ<C>) % 16 == 0, "XYZZ must be a whole number of 128-bit words");
+    constexpr int Q = sizeof(XYZZ<C>) / 16;
+    union { XYZZ<C> v; uint4 q[Q]; } u;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) u.q[k] = s[k];
+    return u.v;
+#else
+    return *p;
+#endif
+}
+template <class C>
+ZK_HD void msm_store_xyzz(XYZZ<C>* p, const XYZZ<C>& v) {
+#if defined(__CUDA_ARCH__)
+    constexpr int Q = sizeof(XYZZ<C>) / 16;
+    union { XYZZ<C> v; uint4 q[Q]; } u;
+    u.v = v;
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) d[k] = u.q[k];
+#else
+    *p = v;
+#endif
+}
+
+// ---- accumulate: thread t owns sorted[t L, min((t+1) L, E)) ------------------------------------------------------------
+// offsets has nb + 1 entries (offsets[nb] = E = number of sorted entries).  buckets must hold valid points (zeroed =
+// infinity before the first chunk).  head / tail have one slot per slice.
+template <class C>
+ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t L, const uint32_t* offsets, uint32_t nb, const uint32_t* sorted,
+                                const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail) {
+    const uint32_t E = offsets[nb];
+    const uint64_t lo64 = (uint64_t)t * L;
+    if (lo64 >= E) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (E - lo > L) ? lo + L : E;
+    // bucket of entry lo: the largest b with offsets[b] <= lo (then offsets[b + 1] > lo)
+    uint32_t a = 0, z = nb;
+    while (z - a > 1) {
+        uint32_t mid = (a + z) >> 1;
+        if (offsets[mid] <= lo) a = mid; else z = mid;
+    }
+    uint32_t b = a;
+    uint32_t seg_end = offsets[b + 1];
+    bool open_head = offsets[b] < lo;  // the bucket began in an earlier slice
+    XYZZ<C> acc = open_head ? XYZZ<C>::inf() : msm_load_xyzz<C>(buckets + b);
+    for (uint32_t pos = lo; pos < hi; ++pos) {
+        if (pos == seg_end) {  // bucket b is complete: flush, move to the next non-empty bucket
+            if (open_head) {
+                msm_store_xyzz<C>(head + t, acc);
+                open_head = false;
+            } else {
+                msm_store_xyzz<C>(buckets + b, acc);
+            }
+            // next non-empty bucket: probe a few, then binary search (a sparse chunk can leave millions of empty buckets
+            // between two entries).  Terminates inside the array because offsets[nb] = E > pos.
+            ++b;
+            seg_end = offsets[b + 1];
+            for (int probe = 0; probe < 4 && seg_end == pos; ++probe) {
+                ++b;
+                seg_end = offsets[b + 1];
+            }
+            if (seg_end == pos) {
+                uint32_t a2 = b, z2 = nb;  // offsets[a2] <= pos < offsets[z2]
+                while (z2 - a2 > 1) {
+                    uint32_t mid = (a2 + z2) >> 1;
+                    if (offsets[mid] <= pos) a2 = mid; else z2 = mid;
+                }
+                b = a2;
+                seg_end = offsets[b + 1];
+            }
+            acc = msm_load_xyzz<C>(buckets + b);
+        }
+        const uint32_t e = sorted[pos];
+        Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
+        if (e >> 31) pt.y = pt.y.neg();
+        acc.madd(pt);
+    }
+    if (open_head)
+        msm_store_xyzz<C>(head + t, acc);       // the whole slice lies inside a bucket that began earlier
+    else if (seg_end == hi)
+        msm_store_xyzz<C>(buckets + b, acc);    // began here (or at lo) and ends exactly at the slice end
+    else
+        msm_store_xyzz<C>(tail + t, acc);       // began here, continues in the next slice (includes the old bucket value)
+}
+
+// ---- merge: one thread per bucket ------------------------------------------------------------------------------------------
+template <class C>
+ZK_HD void msm_merge_bucket(uint32_t b, uint32_t L, const uint32_t* offsets, XYZZ<C>* buckets, const XYZZ<C>* head, const XYZZ<C>* tail) {
+    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+    if (o1 == o0) return;
+    const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
+    if (t0 == t1) return;  // inside one slice: already updated in place
+    XYZZ<C> acc = msm_load_xyzz<C>(tail + t0);
+    for (uint32_t t = t0 + 1; t <= t1; ++t) acc.add(msm_load_xyzz<C>(head + t));
+    msm_store_xyzz<C>(buckets + b, acc);
+}
+
+// ---- reduce: segment `seg_id` of window w covers buckets [seg_id * seg, ...) ------------------------------------------------
+template <class C>
+ZK_HD_COLD XYZZ<C> msm_mul_small(const XYZZ<C>& p, uint32_t k) {
+    XYZZ<C> r = XYZZ<C>::inf();
+    if (!k) return r;
+    int top = 31;
+    while (!((k >> top) & 1)) --top;
+    for (int b = top; b >= 0; --b) {
+        r = r.dbl();
+        if ((k >> b) & 1) r.add(p);
+    }
+    return r;
+}
+// sum_{j in segment} (j + 1) B_j
+template <class C>
+ZK_HD XYZZ<C> msm_reduce_segment(const XYZZ<C>* B, uint32_t nbw, uint32_t seg, uint32_t seg_id) {
+    const uint64_t lo64 = (uint64_t)seg_id * seg;
+    XYZZ<C> contrib = XYZZ<C>::inf();
+    if (lo64 >= nbw) return contrib;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = nbw - lo > seg ? lo + seg : nbw;
+    XYZZ<C> running = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+    for (uint32_t j = hi; j-- > lo;) {
+        running.add(msm_load_xyzz<C>(B + j));
+        acc.add(running);
+    }
+    // sum (j + 1) B_j = acc + lo * running      (acc = sum (j - lo + 1) B_j)
+    contrib = msm_mul_small<C>(running, lo);
+    contrib.add(acc);
+    return contrib;
+}
+
+// ---- plan ---------------------------------------------------------------------------------------------------------------
+// Window size: minimise  W * (n_local + 3 * 2^(c-1))  -- n_local mixed additions per window in the accumulation and two
+// full additions (~1.5 mixed additions each) per bucket in the reduction -- over c <= c_max.  c_max bounds the bucket
+// array (2^(c-1) W XYZZ points: 4.8 GB at c = 22).  n_local = points per rank (the plan is a function of the global
+// (n, nranks) so that every rank derives the same windows).
+inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1, int c_max = 22) {
+    MsmPlan p;
+    int c = forced_c;
+    if (c <= 0) {
+        const double n_local = (double)((n + (size_t)nranks - 1) / (size_t)nranks);
+        double best = 0;
+        for (int cc = 3; cc <= c_max; ++cc) {
+            const int W = (fr_bits + cc - 1) / cc;
+            const double cost = W * (n_local + 3.0 * (double)((size_t)1 << (cc - 1)));
+            if (c <= 0 || cost < best) {
+                best = cost;
+                c = cc;
+            }
+        }
+    }
+    p.c = c;
+    p.W = (fr_bits + c - 1) / c;
+    p.nbw = 1u << (c - 1);
+    p.nb = p.nbw * (uint32_t)p.W;
+    return p;
+}
+
+}  // namespace zk

@@ -274,7 +274,7 @@ int msm_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t
     if (j_lo + n_local > pk.srs_count) return fail(ctx, ZK_ERR_STATE, "commit: local point range exceeds this rank's SRS share");
     const Aff* bases = pk.srs + (n_local ? j_lo : 0);
     const Fr* scalars = coeffs + (n_local ? i0 - offset : 0);
-    MsmPlan p = msm_make_plan(n ? n : 1, Fr377Params::BITS, ctx->msm_window_bits);
+    MsmPlan p = msm_make_plan(n ? n : 1, Fr377Params::BITS, ctx->msm_window_bits, ctx->nranks, ctx->msm_window_max);
     cudaStream_t st = ctx->stream;
     DevBuf win, all;
     const size_t wbytes = sizeof(XY) * p.W;
@@ -719,8 +719,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         const Fr c_za_lc = r_ab_beta * (eta[0] + eta[2] * ev_zb);
         const Fr c_w_lc = (ev_t * vx_beta).neg();
         const Fr c_h1_lc = vh_beta.neg();
-        DevBuf P;
-        ZK_CUDA(ctx, P.alloc(sizeof(Fr) * len_mask, st));
+        DevBuf& P = mask;  // the mask polynomial is not needed after this point: build the combination in place
         ZK_TRY(po_scale(ctx, P.as<Fr>(), mask.as<Fr>(), chp[2], len_mask));                 // ch^2 * mask
         ZK_TRY(po_axpy(ctx, P.as<Fr>(), za.as<Fr>(), chp[2] * c_za_lc, h + 1));
         ZK_TRY(po_axpy(ctx, P.as<Fr>(), w_poly.as<Fr>(), chp[2] * c_w_lc, len_w));
@@ -750,13 +749,14 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         w_beta = g1_add(w_beta, g1_mul(sw, chp[1]));
         rv_beta = rv_beta + chp[1] * c_g1.shifted_rand.eval(beta);
     }
+    // nothing below needs the round-1 / round-2 polynomials: return ~23 GB (at 4 KiB) to the pool before the 3|K|-sized opening
+    mask.release(); za.release(); zb.release(); w_poly.release(); tpoly.release(); h1.release(); xg1.release();
     tr.mark("opening at beta");
     // gamma: a_denom [ch^0], b_denom [ch^1], c_denom [ch^2], g_2 [ch^3, shifted ch^4], inner_sumcheck [ch^5]; nothing is hiding
     {
         const Fr vk_gamma = vanishing(gamma, k);
         const size_t len_p = len_h2;
-        DevBuf P;
-        ZK_CUDA(ctx, P.alloc(sizeof(Fr) * len_p, st));
+        DevBuf& P = V;  // h_2 is consumed here: build the combination in place (V holds 4|K| >= len_p elements)
         ZK_TRY(po_scale(ctx, P.as<Fr>(), h2, (chp[5] * vk_gamma).neg(), len_p));
         const Fr inner_c[3] = {eta[0] * ev_den[1] * ev_den[2] * vv, eta[1] * ev_den[0] * ev_den[2] * vv, eta[2] * ev_den[1] * ev_den[0] * vv};
         for (int m = 0; m < 3; ++m) {

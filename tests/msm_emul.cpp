@@ -1,0 +1,73 @@
+// CPU emulation of the MSM kernel pipeline (test infrastructure, built on demand by tests/test_msm_emul.py).
+// It runs the SAME per-thread bodies the CUDA kernels run (aes_zero_knowledge_proof_circuit_b200/csrc/msm_core.cuh),
+// one "thread" after another, so that the slice / head / tail / merge / reduce index bookkeeping is checked against the
+// oracle in the CPU-only test tier.  It is not part of the product and is never used as a fallback.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../aes_zero_knowledge_proof_circuit_b200/csrc/msm_core.cuh"
+
+using namespace zk;
+
+template <class C>
+static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t seg, uint32_t* out96) {
+    using FrP = typename C::FrP;
+    MsmPlan p = msm_make_plan(n ? n : 1, FrP::BITS, forced_c);
+    std::vector<XYZZ<C>> buckets(p.nb, XYZZ<C>::inf());
+    std::vector<uint32_t> counts(p.nb + 1), offsets(p.nb + 1);
+    for (size_t base = 0; base < n; base += chunk) {
+        size_t m = n - base < chunk ? n - base : chunk;
+        std::fill(counts.begin(), counts.end(), 0u);
+        for (size_t i = 0; i < m; ++i) {
+            uint32_t s[8];
+            memcpy(s, scalars + 8 * (base + i), 32);
+            uint32_t flip = msm_fold_scalar<FrP>(s);
+            msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t) { counts[key]++; });
+        }
+        uint32_t run = 0;
+        for (size_t k = 0; k <= p.nb; ++k) {
+            offsets[k] = run;
+            run += counts[k];
+        }
+        std::vector<uint32_t> sorted(run ? run : 1);
+        std::fill(counts.begin(), counts.end(), 0u);
+        for (size_t i = 0; i < m; ++i) {
+            uint32_t s[8];
+            memcpy(s, scalars + 8 * (base + i), 32);
+            uint32_t flip = msm_fold_scalar<FrP>(s);
+            msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t neg) {
+                sorted[offsets[key] + counts[key]++] = (uint32_t)(base + i) | (neg << 31);
+            });
+        }
+        size_t slices = (m * (size_t)p.W + L - 1) / L;  // the same upper bound the host code launches
+        std::vector<XYZZ<C>> head(slices + 1), tail(slices + 1);
+        // poison the partial arrays: a slot that is read without having been written shows up as a wrong result
+        memset((void*)head.data(), 0x5a, sizeof(XYZZ<C>) * head.size());
+        memset((void*)tail.data(), 0x5a, sizeof(XYZZ<C>) * tail.size());
+        for (size_t t = 0; t < slices; ++t)
+            msm_slice_accumulate<C>((uint32_t)t, L, offsets.data(), p.nb, sorted.data(), bases, buckets.data(), head.data(), tail.data());
+        for (uint32_t b = 0; b < p.nb; ++b) msm_merge_bucket<C>(b, L, offsets.data(), buckets.data(), head.data(), tail.data());
+    }
+    XYZZ<C> total = XYZZ<C>::inf();
+    for (int w = p.W - 1; w >= 0; --w) {
+        for (int k = 0; k < p.c; ++k) total = total.dbl();
+        uint32_t nseg = (p.nbw + seg - 1) / seg + 1;  // one segment past the end: must contribute nothing
+        for (uint32_t sid = 0; sid < nseg; ++sid) total.add(msm_reduce_segment<C>(buckets.data() + (size_t)w * p.nbw, p.nbw, seg, sid));
+    }
+    Affine<C> r = total.to_affine();
+    memcpy(out96, r.x.v, 48);
+    memcpy(out96 + 12, r.y.v, 48);
+    return p.c;
+}
+
+extern "C" int msm_emul(int curve, const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t seg,
+                        uint32_t* out96) {
+    if (curve == 377) return emul<G1_377Params>(bases, scalars, n, forced_c, L, chunk, seg, out96);
+    if (curve == 381) return emul<G1_381Params>(bases, scalars, n, forced_c, L, chunk, seg, out96);
+    return -1;
+}
+extern "C" void msm_plan(size_t n, int fr_bits, int forced_c, int nranks, int c_max, int* out) {
+    MsmPlan p = msm_make_plan(n, fr_bits, forced_c, nranks, c_max);
+    out[0] = p.c; out[1] = p.W; out[2] = (int)p.nbw;
+}

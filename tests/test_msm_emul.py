@@ -1,0 +1,96 @@
+"""CPU tier: the MSM kernels' per-thread bodies (csrc/msm_core.cuh), run sequentially by tests/msm_emul.cpp, against the
+oracle's MSM.  Covers what the GPU tier cannot enumerate cheaply: every combination of slice length, chunk size, window
+size and reduction segment on inputs that force buckets to straddle slices and chunks."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.oracle_lib import FR, ints_to_limbs, rand_fr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "msm_emul.cpp")
+    out = os.path.join(ROOT, "tests", "_msm_emul.so")
+    hdr = os.path.join(ROOT, "aes_zero_knowledge_proof_circuit_b200", "csrc", "msm_core.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    lib = ctypes.CDLL(out)
+    lib.msm_emul.restype = ctypes.c_int
+    lib.msm_emul.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t,
+                             ctypes.c_uint32, ctypes.c_void_p]
+    lib.msm_plan.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+
+    def run(curve, bases, scalars, c=0, L=32, chunk=1 << 27, seg=64):
+        bases = np.ascontiguousarray(bases, dtype=np.uint64)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+        out = np.zeros(12, dtype=np.uint64)
+        rc = lib.msm_emul(curve, bases.ctypes.data, scalars.ctypes.data, len(scalars), c, L, chunk, seg, out.ctypes.data)
+        assert rc > 0
+        return out
+
+    run.lib = lib
+    return run
+
+
+def _inputs(oracle, curve, n, seed):
+    rng = np.random.default_rng(seed)
+    bases = oracle.g1_walk(curve, 1000 + seed, 3, n)
+    sc = rand_fr(rng, curve, n)
+    if n > 16:
+        sc[1] = 0
+        sc[2] = ints_to_limbs([1], 4)[0]
+        sc[3] = ints_to_limbs([FR[curve] - 1], 4)[0]
+        sc[4] = ints_to_limbs([(FR[curve] - 1) // 2], 4)[0]        # largest scalar that is not folded
+        sc[5] = ints_to_limbs([(FR[curve] - 1) // 2 + 1], 4)[0]    # smallest scalar that is
+        sc[6] = sc[7]
+        bases[8] = bases[9]          # equal points with equal scalars: a doubling inside a bucket
+        sc[8] = sc[9]
+        bases[10] = 0                # point at infinity
+        sc[11:16] = sc[16]           # a heavier bucket
+    return bases, sc
+
+
+@pytest.mark.parametrize("curve", [377, 381])
+@pytest.mark.parametrize("c,L,chunk,seg", [(4, 1, 1000, 1), (4, 3, 37, 2), (5, 7, 64, 3), (7, 32, 50, 64), (3, 64, 1000, 4), (9, 5, 200, 16),
+                                           (11, 33, 128, 64), (2, 4, 16, 1)])
+def test_emulated_pipeline_matches_oracle(emul, oracle, curve, c, L, chunk, seg):
+    n = 150
+    bases, sc = _inputs(oracle, curve, n, c * 100 + L)
+    exp = oracle.g1_msm(curve, bases, sc).reshape(-1)
+    assert (emul(curve, bases, sc, c=c, L=L, chunk=chunk, seg=seg) == exp).all()
+
+
+def test_emulated_heavy_buckets_and_small_inputs(emul, oracle):
+    curve = 377
+    bases = oracle.g1_walk(curve, 5, 2, 64)
+    same = np.tile(ints_to_limbs([FR[curve] - 12345], 4), (64, 1))   # every term in the same bucket of every window
+    for L in (1, 5, 64, 100):
+        assert (emul(curve, bases, same, c=6, L=L, chunk=40, seg=8) == oracle.g1_msm(curve, bases, same).reshape(-1)).all()
+    zero = np.zeros((64, 4), dtype=np.uint64)
+    assert (emul(curve, bases, zero, c=6, L=8) == 0).all()
+    one = zero.copy()
+    one[:, 0] = 1
+    assert (emul(curve, bases, one, c=6, L=8) == oracle.g1_msm(curve, bases, one, algo=1).reshape(-1)).all()
+    assert (emul(curve, bases[:1], one[:1], c=0, L=32) == bases[0].reshape(-1)).all()
+    assert (emul(curve, bases[:0], one[:0], c=0, L=32) == 0).all()
+
+
+def test_automatic_plan(emul):
+    def plan(n, bits=253, forced=0, nranks=1, cmax=22):
+        out = (ctypes.c_int * 3)()
+        emul.lib.msm_plan(n, bits, forced, nranks, cmax, out)
+        return tuple(out)
+
+    for n in (1, 100, 1 << 16, 1 << 22, 1 << 27, 3 << 27):
+        c, W, nbw = plan(n)
+        assert 3 <= c <= 22 and W == -(-253 // c) and nbw == 1 << (c - 1)
+    assert plan(1 << 27)[0] == 22 and plan(1 << 27)[1] == 12
+    assert plan(1 << 27, nranks=8) == plan(1 << 24)          # the plan follows the per-rank share
+    assert plan(1 << 27, cmax=23)[:2] == (23, 11)
+    assert plan(1 << 20, bits=255, forced=16)[:2] == (16, 16)
