@@ -38,6 +38,7 @@ def _load():
         "zkaes_ctx_launches": (c_uint64, [vp]),
         "zkaes_ctx_sync": (c_int, [vp]),
         "zkaes_ctx_set_msm_window": (c_int, [vp, c_int]),
+        "zkaes_ctx_set_tuning": (c_int, [vp, ctypes.c_char_p, c_int]),
         "zkaes_comm_unique_id": (c_int, [vp]),
         "zkaes_ctx_comm_init": (c_int, [vp, c_int, c_int, vp]),
         "zkaes_shard_range": (c_int, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
@@ -174,6 +175,9 @@ class Context:
 
     def set_msm_window(self, bits: int):
         self._check(lib().zkaes_ctx_set_msm_window(self._h, bits))
+
+    def set_tuning(self, key: str, value: int):
+        self._check(lib().zkaes_ctx_set_tuning(self._h, key.encode(), value))
 
     # ---- device memory ----
     def alloc(self, nbytes: int) -> int:

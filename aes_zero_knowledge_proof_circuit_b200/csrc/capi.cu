@@ -146,9 +146,24 @@ int zkaes_ctx_profile_read(zkaes_ctx* ctx, double out[4]) {
     ctx->prof_spans.clear();
     return ZK_OK;
 }
+int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
+    NEED_CTX(ctx);
+    if (!key) return fail(ctx, ZK_ERR_ARG, "tuning: null key");
+    const std::string k(key);
+    if (k == "msm_window_max") {
+        if (value < 3 || value > 24) return fail(ctx, ZK_ERR_ARG, "msm_window_max must be in 3..24");
+        ctx->msm_window_max = value;
+    } else if (k == "msm_acc_blocks") {
+        if (value != 3 && value != 4) return fail(ctx, ZK_ERR_ARG, "msm_acc_blocks must be 3 or 4");
+        ctx->msm_acc_blocks = value;
+    } else {
+        return fail(ctx, ZK_ERR_ARG, "tuning: unknown key " + k);
+    }
+    return ZK_OK;
+}
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits) {
     NEED_CTX(ctx);
-    if (window_bits < 0 || window_bits > 22 || window_bits == 1 || window_bits == 2) return fail(ctx, ZK_ERR_ARG, "window bits must be 0 or 3..22");
+    if (window_bits < 0 || window_bits > 24 || window_bits == 1 || window_bits == 2) return fail(ctx, ZK_ERR_ARG, "window bits must be 0 or 3..24");
     ctx->msm_window_bits = window_bits;
     return ZK_OK;
 }

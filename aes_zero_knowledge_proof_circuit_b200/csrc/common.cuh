@@ -22,6 +22,7 @@ struct zkaes_ctx {
     std::map<uint64_t, void*> tables;
     // tuning knobs (0 = automatic)
     int msm_window_bits = 0;
+    int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
     int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
     // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)
     int rank = 0, nranks = 1;

@@ -9,7 +9,7 @@
 //   2. k_scan_*        : exclusive scan of the histogram -> bucket offsets (nb + 1 entries)
 //   3. k_msm_digits    : counting-sort scatter of point indices (sign in bit 31) by bucket key
 //   4. k_msm_accumulate: equal-length slices of the sorted entries, one thread each, XYZZ += affine (8M+2S)  [ALU bound]
-//   5. k_msm_merge     : buckets cut by slice boundaries = tail + heads
+//   5. k_msm_merge     : buckets cut by slice boundaries = tail + heads (one thread per slice)
 //   6. k_msm_reduce / k_msm_window_final: per-window sum_k k*B_k -> W window sums (XYZZ) on device
 // The c*W doublings of the final Horner fold and the affine normalisation are O(W*c) work and run on the
 // host (portable arithmetic in ff.cuh) because the result is consumed by the host-side transcript anyway.
@@ -40,7 +40,10 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, s
     }
 }
 
-// pass 1 (sorted == nullptr): histogram.  pass 2: write sorted indices.
+// pass 1 (sorted == nullptr): histogram.  pass 2: write sorted indices.  grid = (scalars / 256, W): blockIdx.y is the
+// window, so the blocks of one window run together and its 2^(c-1) counters (8 MB at c = 22) stay L2-resident under the
+// atomics; every (scalar, window) thread re-reads its 32-byte scalar (W x 32 B per term of L2/HBM traffic instead of
+// DRAM-missing atomics over all W 2^(c-1) counters).
 template <class FrP>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
                                                     MsmPlan p, uint32_t* __restrict__ counts,
@@ -50,11 +53,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__
     uint32_t s[8];
     load_scalar<FrP>(scalars, i, stride, mont, s);
     const uint32_t flip = msm_fold_scalar<FrP>(s);
-    const uint32_t idx = idx_base + (uint32_t)i;
-    msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t neg) {
-        uint32_t pos = atomicAdd(&counts[key], 1u);
-        if (sorted) sorted[offsets[key] + pos] = idx | (neg << 31);
-    });
+    const int w = blockIdx.y;
+    uint32_t neg;
+    const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
+    if (!d) return;
+    const uint32_t key = (uint32_t)w * p.nbw + d - 1;
+    const uint32_t pos = atomicAdd(&counts[key], 1u);
+    if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
 }
 
 // ---- exclusive scan over <= 2^22 counters: per-block scan, scan of block sums, add-back -----------------
@@ -146,18 +151,21 @@ __global__ void k_windows_to_std(const XYZZ<typename InternalCurve<C>::type>* __
     out[w] = r;
 }
 
-template <class C>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                        const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t L,
-                                                        XYZZ<C>* __restrict__ buckets, XYZZ<C>* __restrict__ head, XYZZ<C>* __restrict__ tail) {
-    msm_slice_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, L, offsets, nb, sorted, bases, buckets, head, tail);
+// BLOCKS = resident blocks per SM the register allocation is held to: 3 (166 registers, no spills) or 4 (128 registers,
+// 92 bytes of spills, 16 instead of 12 warps per SM to cover the IMAD dependency waits).
+template <class C, int BLOCKS>
+__global__ void __launch_bounds__(128, BLOCKS) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                                const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t n_slices, uint32_t L,
+                                                                XYZZ<C>* __restrict__ buckets, XYZZ<C>* __restrict__ head,
+                                                                XYZZ<C>* __restrict__ tail, uint32_t* __restrict__ tail_bucket) {
+    msm_slice_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, nb, sorted, bases, buckets, head, tail, tail_bucket);
 }
 
 template <class C>
-__global__ void __launch_bounds__(128) k_msm_merge(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t L, XYZZ<C>* __restrict__ buckets,
-                                                   const XYZZ<C>* __restrict__ head, const XYZZ<C>* __restrict__ tail) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < nb) msm_merge_bucket<C>(b, L, offsets, buckets, head, tail);
+__global__ void __launch_bounds__(128) k_msm_merge(const uint32_t* __restrict__ offsets, uint32_t n_slices, uint32_t L, XYZZ<C>* __restrict__ buckets,
+                                                   const XYZZ<C>* __restrict__ head, const XYZZ<C>* __restrict__ tail,
+                                                   const uint32_t* __restrict__ tail_bucket) {
+    msm_merge_slice<C>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, buckets, head, tail, tail_bucket);
 }
 
 // ---- bucket reduction: S_w = sum_{j<nbw} (j+1) * B[w][j] ---------------------------------------------------
@@ -229,13 +237,14 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     const uint64_t max_entries = (uint64_t)chunk_max * p.W;
     const uint32_t L = msm_slice_len(max_entries);
     const size_t max_slices = (size_t)((max_entries + L - 1) / L);
-    DevBuf counts, offsets, sorted, buckets, partials, head, tail;
+    DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket;
     ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
     ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
     ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
     ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<CI>) * max_slices, st));
     ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+    ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
     ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<CI>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
     DevBuf conv;
@@ -250,14 +259,14 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         size_t m = n - base < chunk_max ? n - base : chunk_max;
         const uint32_t* sc = scalars + 8 * base * scalar_stride;
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nb + 1), st));
-        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(), nullptr,
-                                                        nullptr);
+        k_msm_digits<FrP><<<dim3(cdiv(m, 256), p.W), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
+                                                                   nullptr, nullptr);
         ctx->launches++;
         // scanning nb + 1 counters (the last one is zero) leaves the total entry count in offsets[nb]
         ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb + 1));
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
-        k_msm_digits<FrP><<<cdiv(m, 256), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
-                                                        offsets.as<uint32_t>(), sorted.as<uint32_t>());
+        k_msm_digits<FrP><<<dim3(cdiv(m, 256), p.W), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
+                                                                   offsets.as<uint32_t>(), sorted.as<uint32_t>());
         ctx->launches++;
         const size_t slices = (size_t)(((uint64_t)m * p.W + L - 1) / L);  // upper bound: zero digits produce no entry
         zkaes_ctx::ProfSpan span{};
@@ -266,8 +275,14 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
             cudaEventCreate(&span.e1);
             cudaEventRecord(span.e0, st);
         }
-        k_msm_accumulate<CI><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, L,
-                                                                buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>());
+        if (ctx->msm_acc_blocks == 4)
+            k_msm_accumulate<CI, 4><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, (uint32_t)slices, L,
+                                                                       buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>(),
+                                                                       tail_bucket.as<uint32_t>());
+        else
+            k_msm_accumulate<CI, 3><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, (uint32_t)slices, L,
+                                                                       buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>(),
+                                                                       tail_bucket.as<uint32_t>());
         ctx->launches++;
         if (ctx->prof) {
             cudaEventRecord(span.e1, st);
@@ -275,8 +290,8 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
             span.madds = (uint64_t)m * p.W;  // upper bound: zero digits are skipped
             ctx->prof_spans.push_back(span);
         }
-        k_msm_merge<CI><<<cdiv(p.nb, 128), 128, 0, st>>>(offsets.as<uint32_t>(), p.nb, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
-                                                         tail.as<XYZZ<CI>>());
+        k_msm_merge<CI><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
+                                                           tail.as<XYZZ<CI>>(), tail_bucket.as<uint32_t>());
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
     }

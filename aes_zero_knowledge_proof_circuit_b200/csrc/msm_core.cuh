@@ -48,14 +48,14 @@ ZK_HD uint32_t msm_scalar_bits(const uint32_t* s, int pos, int c) {
     return (uint32_t)(v >> off) & ((1u << c) - 1);
 }
 
-// Calls emit(key, neg) for every non-zero digit of the (folded) scalar.
-template <class Emit>
-ZK_HD void msm_for_each_digit(const uint32_t* s, uint32_t flip, const MsmPlan& p, Emit&& emit) {
+// The signed digit of window w alone (0 = no entry): the per-window sort passes call this once per (scalar, window) so
+// that the histogram counters and the scatter targets of one window stay L2-resident.
+ZK_HD uint32_t msm_digit_of_window(const uint32_t* s, uint32_t flip, const MsmPlan& p, int w, uint32_t* neg_out) {
     const uint32_t half = 1u << (p.c - 1);
-    uint32_t carry = 0;
-    for (int w = 0; w < p.W; ++w) {
-        uint32_t d = msm_scalar_bits(s, w * p.c, p.c) + carry;
-        uint32_t neg = 0;
+    uint32_t carry = 0, d = 0, neg = 0;
+    for (int i = 0; i <= w; ++i) {
+        d = msm_scalar_bits(s, i * p.c, p.c) + carry;
+        neg = 0;
         if (d > half) {
             d = (1u << p.c) - d;
             carry = 1;
@@ -63,8 +63,9 @@ ZK_HD void msm_for_each_digit(const uint32_t* s, uint32_t flip, const MsmPlan& p
         } else {
             carry = 0;
         }
-        if (d) emit((uint32_t)w * p.nbw + d - 1, neg ^ flip);
     }
+    *neg_out = neg ^ flip;
+    return d;
 }
 
 // ---- 128-bit moves of points -----------------------------------------------------------------------------------------
@@ -117,12 +118,16 @@ ZK_HD void msm_store_xyzz(XYZZ<C>* p, const XYZZ<C>& v) {
 
 // ---- accumulate: thread t owns sorted[t L, min((t+1) L, E)) ------------------------------------------------------------
 // offsets has nb + 1 entries (offsets[nb] = E = number of sorted entries).  buckets must hold valid points (zeroed =
-// infinity before the first chunk).  head / tail have one slot per slice.
+// infinity before the first chunk).  head / tail / tail_bucket have one slot per slice; tail_bucket[t] names the bucket
+// whose partial sits in tail[t] (MSM_NO_BUCKET if none), which is all the merge pass needs.
+static constexpr uint32_t MSM_NO_BUCKET = 0xffffffffu;
 template <class C>
-ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t L, const uint32_t* offsets, uint32_t nb, const uint32_t* sorted,
-                                const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail) {
+ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const uint32_t* offsets, uint32_t nb, const uint32_t* sorted,
+                                const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket) {
+    if (t >= n_slices) return;
     const uint32_t E = offsets[nb];
     const uint64_t lo64 = (uint64_t)t * L;
+    tail_bucket[t] = MSM_NO_BUCKET;
     if (lo64 >= E) return;
     const uint32_t lo = (uint32_t)lo64;
     const uint32_t hi = (E - lo > L) ? lo + L : E;
@@ -172,19 +177,23 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t L, const uint32_t* offsets,
         msm_store_xyzz<C>(head + t, acc);       // the whole slice lies inside a bucket that began earlier
     else if (seg_end == hi)
         msm_store_xyzz<C>(buckets + b, acc);    // began here (or at lo) and ends exactly at the slice end
-    else
+    else {
         msm_store_xyzz<C>(tail + t, acc);       // began here, continues in the next slice (includes the old bucket value)
+        tail_bucket[t] = b;
+    }
 }
 
-// ---- merge: one thread per bucket ------------------------------------------------------------------------------------------
+// ---- merge: one thread per slice -- the bucket that began in slice t and ran past its end = tail[t] + the heads of the
+// slices it continues into (one thread per BUCKET left 30 of 32 lanes idle: ~1 bucket in 16 is cut at L = 512) -------------
 template <class C>
-ZK_HD void msm_merge_bucket(uint32_t b, uint32_t L, const uint32_t* offsets, XYZZ<C>* buckets, const XYZZ<C>* head, const XYZZ<C>* tail) {
-    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
-    if (o1 == o0) return;
-    const uint32_t t0 = o0 / L, t1 = (o1 - 1) / L;
-    if (t0 == t1) return;  // inside one slice: already updated in place
-    XYZZ<C> acc = msm_load_xyzz<C>(tail + t0);
-    for (uint32_t t = t0 + 1; t <= t1; ++t) acc.add(msm_load_xyzz<C>(head + t));
+ZK_HD void msm_merge_slice(uint32_t t, uint32_t n_slices, uint32_t L, const uint32_t* offsets, XYZZ<C>* buckets, const XYZZ<C>* head,
+                           const XYZZ<C>* tail, const uint32_t* tail_bucket) {
+    if (t >= n_slices) return;
+    const uint32_t b = tail_bucket[t];
+    if (b == MSM_NO_BUCKET) return;
+    const uint32_t t1 = (offsets[b + 1] - 1) / L;  // last slice the bucket reaches (> t)
+    XYZZ<C> acc = msm_load_xyzz<C>(tail + t);
+    for (uint32_t u = t + 1; u <= t1; ++u) acc.add(msm_load_xyzz<C>(head + u));
     msm_store_xyzz<C>(buckets + b, acc);
 }
 
@@ -221,8 +230,9 @@ ZK_HD XYZZ<C> msm_reduce_segment(const XYZZ<C>* B, uint32_t nbw, uint32_t seg, u
 }
 
 // ---- plan ---------------------------------------------------------------------------------------------------------------
-// Window size: minimise  W * (n_local + 3 * 2^(c-1))  -- n_local mixed additions per window in the accumulation and two
-// full additions (~1.5 mixed additions each) per bucket in the reduction -- over c <= c_max.  c_max bounds the bucket
+// Window size: minimise  W * (1.15 n_local + 4 * 2^(c-1))  -- per window n_local mixed additions in the accumulation plus
+// the sort passes (~0.15 of a mixed addition per entry), and two full additions per bucket in the reduction (measured
+// ~4 mixed-addition times per bucket, profiles/r1_launches_msm_2p26_slices.txt) -- over c <= c_max.  c_max bounds the bucket
 // array (2^(c-1) W XYZZ points: 4.8 GB at c = 22).  n_local = points per rank (the plan is a function of the global
 // (n, nranks) so that every rank derives the same windows).
 inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1, int c_max = 22) {
@@ -233,7 +243,7 @@ inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1
         double best = 0;
         for (int cc = 3; cc <= c_max; ++cc) {
             const int W = (fr_bits + cc - 1) / cc;
-            const double cost = W * (n_local + 3.0 * (double)((size_t)1 << (cc - 1)));
+            const double cost = W * (1.15 * n_local + 4.0 * (double)((size_t)1 << (cc - 1)));
             if (c <= 0 || cost < best) {
                 best = cost;
                 c = cc;

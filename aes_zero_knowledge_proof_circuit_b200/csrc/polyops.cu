@@ -267,17 +267,15 @@ __global__ void k_fma3(F* acc, const F* a, const F* b, const F* c, F s, size_t n
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_fr(acc + i, ld_fr(acc + i) + ld_fr(a + i) * ld_fr(b + i) * ld_fr(c + i) * s);
 }
-// 4-point inverse DFT across the coset blocks, times g^(-k b) / 4
-__global__ void k_coset4_combine(F* v, size_t k, F c0, F c1, F c2, F c3, F i4_inv) {
+// three coset interpolants p_j = c_0 + u_j c_1 + u_j^2 c_2 (block 3 of the quotient is zero) -> c_b = sum_j m[3 b + j] p_j, in place
+struct Mat3 { F m[9]; };
+__global__ void k_coset3_combine(F* v, size_t k, Mat3 M) {
     size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= k) return;
-    F u0 = ld_fr(v + a), u1 = ld_fr(v + k + a), u2 = ld_fr(v + 2 * k + a), u3 = ld_fr(v + 3 * k + a);
-    // w = i4^-1 (a primitive 4th root): sum_j w^(j b) u_j
-    F s02 = u0 + u2, d02 = u0 - u2, s13 = u1 + u3, d13 = (u1 - u3) * i4_inv;
-    st_fr(v + a, (s02 + s13) * c0);
-    st_fr(v + k + a, (d02 + d13) * c1);
-    st_fr(v + 2 * k + a, (s02 - s13) * c2);
-    st_fr(v + 3 * k + a, (d02 - d13) * c3);
+    F p0 = ld_fr(v + a), p1 = ld_fr(v + k + a), p2 = ld_fr(v + 2 * k + a);
+    st_fr(v + a, p0 * M.m[0] + p1 * M.m[1] + p2 * M.m[2]);
+    st_fr(v + k + a, p0 * M.m[3] + p1 * M.m[4] + p2 * M.m[5]);
+    st_fr(v + 2 * k + a, p0 * M.m[6] + p1 * M.m[7] + p2 * M.m[8]);
 }
 // partial[c] = sum_{i < CH} coeffs[c*CH + i] * x^i
 constexpr int EV_CH = 256;
@@ -432,10 +430,18 @@ int po_lincomb_den(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, c
 }
 int po_mul3(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_mul3, n, TB, out, a, b, c, s, n); return ZK_OK; }
 int po_fma3(zkaes_ctx* ctx, F* acc, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_fma3, n, TB, acc, a, b, c, s, n); return ZK_OK; }
-int po_coset4_combine(zkaes_ctx* ctx, F* v, size_t k, const F& gk_inv, const F& i4_inv) {
-    F quarter = F::from_u64(4).inverse();
-    F c0 = quarter, c1 = c0 * gk_inv, c2 = c1 * gk_inv, c3 = c2 * gk_inv;
-    LAUNCH(ctx, k_coset4_combine, k, TB, v, k, c0, c1, c2, c3, i4_inv);
+int po_coset3_combine(zkaes_ctx* ctx, F* v, size_t k, const F u[3]) {
+    // inverse Vandermonde through the Lagrange basis on the nodes u_j: l_j(y) = (y - u_a)(y - u_b) / ((u_j - u_a)(u_j - u_b))
+    Mat3 M;
+    for (int j = 0; j < 3; ++j) {
+        const F& ua = u[(j + 1) % 3];
+        const F& ub = u[(j + 2) % 3];
+        F d = ((u[j] - ua) * (u[j] - ub)).inverse();
+        M.m[0 + j] = ua * ub * d;
+        M.m[3 + j] = (ua + ub).neg() * d;
+        M.m[6 + j] = d;
+    }
+    LAUNCH(ctx, k_coset3_combine, k, TB, v, k, M);
     return ZK_OK;
 }
 int po_eval(zkaes_ctx* ctx, const F* coeffs, size_t n, const F& x, F* out_host) {

@@ -65,9 +65,9 @@ int po_lincomb_den(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const F
 int po_mul3(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
 // acc += s * a * b * c
 int po_fma3(zkaes_ctx* ctx, FrS* acc, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
-// In place on v (4 blocks of k): block j holds u_j[a] = (coefficient a of the degree-<k interpolant on coset j) * s_j^-a.
-// Afterwards block b holds the coefficients p_{a + k b} of the degree-<4k polynomial: p = (g^-kb / 4) sum_j i4^(-j b) u_j.
-int po_coset4_combine(zkaes_ctx* ctx, FrS* v, size_t k, const FrS& gk_inv, const FrS& i4_inv);
+// v = three |K|-blocks holding the interpolants of a polynomial of degree < 3|K| on the cosets with u_j = s_j^|K|
+// (each with its shift undone); replaces them by the polynomial's three coefficient blocks
+int po_coset3_combine(zkaes_ctx* ctx, FrS* v, size_t k, const FrS u[3]);
 // polynomial evaluation (Horner), result on the host
 int po_eval(zkaes_ctx* ctx, const FrS* coeffs, size_t n, const FrS& x, FrS* out_host);
 // q = c / (X - z) (synthetic division, remainder dropped): n coefficients in, n - 1 out; q must not alias c

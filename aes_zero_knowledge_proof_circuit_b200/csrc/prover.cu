@@ -201,7 +201,10 @@ struct PhaseTrace {
         if (!on) return;
         cudaStreamSynchronize(st);
         auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[zkaes] %-28s %9.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        size_t mfree = 0, mtotal = 0;
+        cudaMemGetInfo(&mfree, &mtotal);  // device memory in use at the phase boundary (the pool keeps what the phase peaked at)
+        fprintf(stderr, "[zkaes] %-28s %9.2f ms   %6.1f GB in use\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                (double)(mtotal - mfree) / 1e9);
         t0 = t1;
     }
 };
@@ -624,24 +627,27 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const Fr* g2 = fpoly.as<Fr>() + 1;  // f = X g_2 + t(beta) / |K|
     const size_t len_g2 = k - 1;
     tr.mark("r3: f");
-    // h_2 = (a - b f) / v_K, evaluated on the coset g*B (|B| = 4|K|, where v_K does not vanish) as four cosets
-    // s_j K, s_j = g w_4K^j, of size |K| each: every buffer is |K|-sized (the reference keeps 12 tables of 4|K| in the
-    // index, ahp/indexer.rs evals_on_B -- 206 GB at 4 KiB), and v_K is the constant s_j^K - 1 on each of them.
+    // h_2 = (a - b f) / v_K has degree < 3|K|: it is evaluated on THREE cosets s_j K, s_j = g w_4K^j, of size |K| each
+    // (the reference evaluates on the coset g*B, |B| = 4|K|, and keeps 12 tables of 4|K| in the index, ahp/indexer.rs
+    // evals_on_B -- 206 GB at 4 KiB).  Every buffer is |K|-sized, v_K is the constant s_j^K - 1 on each coset, and the
+    // three interpolants h_2 mod (X^K - s_j^K) = c_0 + s_j^K c_1 + s_j^2K c_2 give the coefficient blocks c_b by a 3x3 solve.
     const int log4k = pk.log_k + 2;
     const Fr ab = alpha * beta;
     const Fr g = coset_gen(), w4k = domain_gen(log4k);
     DevBuf V, dden[3], tA;
-    ZK_CUDA(ctx, V.alloc(sizeof(Fr) * 4 * k, st));
+    ZK_CUDA(ctx, V.alloc(sizeof(Fr) * 3 * k, st));
     for (int m = 0; m < 3; ++m) ZK_CUDA(ctx, dden[m].alloc(sizeof(Fr) * k, st));
     ZK_CUDA(ctx, tA.alloc(sizeof(Fr) * k, st));
     auto to_coset = [&](Fr* dst, const Fr* poly, const Fr& shift) -> int {  // dst[i] = poly(shift * w_K^i)
         ZK_TRY(po_scale_powers(ctx, dst, poly, shift, k));
         return ntt(ctx, dst, pk.log_k, false, false);
     };
-    // Multi-GPU: the four cosets are independent -- rank (j mod N) evaluates coset j and broadcasts its |K| values
-    // (NVLink; 4.3 GB per coset at 4 KiB), instead of every rank repeating all four.
-    Fr sj = g;
-    for (int j = 0; j < 4; ++j, sj = sj * w4k) {
+    // Multi-GPU: the cosets are independent -- rank (j mod N) evaluates coset j and broadcasts its |K| values
+    // (NVLink; 4.3 GB per coset at 4 KiB), instead of every rank repeating all of them.
+    constexpr int NCOSET = 3;
+    Fr sj = g, uj[NCOSET];
+    for (int j = 0; j < NCOSET; ++j, sj = sj * w4k) {
+        uj[j] = fr_pow_u64(sj, k);
         if (j % ctx->nranks != ctx->rank) continue;
         for (int m = 0; m < 3; ++m) {
             // the denominator is linear in (row, col, row_col): combine the coefficient vectors first, one NTT instead of three
@@ -657,18 +663,18 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             ZK_TRY(to_coset(tA.as<Fr>(), pk.idx_poly[4 * m + 2], sj));
             ZK_TRY(po_fma3(ctx, Vj, tA.as<Fr>(), dden[(m + 1) % 3].as<Fr>(), dden[(m + 2) % 3].as<Fr>(), vv * eta[m], k));  // + a
         }
-        const Fr vk_inv = (fr_pow_u64(sj, k) - Fr::one()).inverse();
+        const Fr vk_inv = (uj[j] - Fr::one()).inverse();
         ZK_TRY(po_scale(ctx, Vj, Vj, vk_inv, k));
         // back to the coefficients of the degree-<|K| interpolant on this coset, with the shift undone
         ZK_TRY(ntt(ctx, Vj, pk.log_k, true, false));
         ZK_TRY(po_scale_powers(ctx, Vj, Vj, sj.inverse(), k));
     }
     if (ctx->nranks > 1)
-        for (int j = 0; j < 4; ++j) ZK_TRY(comm_broadcast(ctx, V.as<Fr>() + (size_t)j * k, sizeof(Fr) * k, j % ctx->nranks));
+        for (int j = 0; j < NCOSET; ++j) ZK_TRY(comm_broadcast(ctx, V.as<Fr>() + (size_t)j * k, sizeof(Fr) * k, j % ctx->nranks));
     for (int m = 0; m < 3; ++m) dden[m].release();
     tA.release();
-    ZK_TRY(po_coset4_combine(ctx, V.as<Fr>(), k, fr_pow_u64(g, k).inverse(), fr_pow_u64(w4k, k).inverse()));
-    Fr* h2 = V.as<Fr>();  // 3|K| - 3 coefficients (block 3 is zero: deg h_2 < 3|K|)
+    ZK_TRY(po_coset3_combine(ctx, V.as<Fr>(), k, uj));
+    Fr* h2 = V.as<Fr>();  // 3|K| - 3 coefficients
     const size_t len_h2 = 3 * k - 3;
     tr.mark("r3: h_2 on the coset");
     Committed c_g2, c_h2;
@@ -756,7 +762,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     {
         const Fr vk_gamma = vanishing(gamma, k);
         const size_t len_p = len_h2;
-        DevBuf& P = V;  // h_2 is consumed here: build the combination in place (V holds 4|K| >= len_p elements)
+        DevBuf& P = V;  // h_2 is consumed here: build the combination in place (V holds 3|K| >= len_p elements)
         ZK_TRY(po_scale(ctx, P.as<Fr>(), h2, (chp[5] * vk_gamma).neg(), len_p));
         const Fr inner_c[3] = {eta[0] * ev_den[1] * ev_den[2] * vv, eta[1] * ev_den[0] * ev_den[2] * vv, eta[2] * ev_den[1] * ev_den[0] * vv};
         for (int m = 0; m < 3; ++m) {

@@ -23,7 +23,10 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
             uint32_t s[8];
             memcpy(s, scalars + 8 * (base + i), 32);
             uint32_t flip = msm_fold_scalar<FrP>(s);
-            msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t) { counts[key]++; });
+            for (int w = 0; w < p.W; ++w) {
+                uint32_t neg, d = msm_digit_of_window(s, flip, p, w, &neg);
+                if (d) counts[(uint32_t)w * p.nbw + d - 1]++;
+            }
         }
         uint32_t run = 0;
         for (size_t k = 0; k <= p.nb; ++k) {
@@ -36,18 +39,24 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
             uint32_t s[8];
             memcpy(s, scalars + 8 * (base + i), 32);
             uint32_t flip = msm_fold_scalar<FrP>(s);
-            msm_for_each_digit(s, flip, p, [&](uint32_t key, uint32_t neg) {
+            for (int w = 0; w < p.W; ++w) {
+                uint32_t neg, d = msm_digit_of_window(s, flip, p, w, &neg);
+                if (!d) continue;
+                uint32_t key = (uint32_t)w * p.nbw + d - 1;
                 sorted[offsets[key] + counts[key]++] = (uint32_t)(base + i) | (neg << 31);
-            });
+            }
         }
         size_t slices = (m * (size_t)p.W + L - 1) / L;  // the same upper bound the host code launches
         std::vector<XYZZ<C>> head(slices + 1), tail(slices + 1);
+        std::vector<uint32_t> tail_bucket(slices + 1, 0x12345678u);
         // poison the partial arrays: a slot that is read without having been written shows up as a wrong result
         memset((void*)head.data(), 0x5a, sizeof(XYZZ<C>) * head.size());
         memset((void*)tail.data(), 0x5a, sizeof(XYZZ<C>) * tail.size());
         for (size_t t = 0; t < slices; ++t)
-            msm_slice_accumulate<C>((uint32_t)t, L, offsets.data(), p.nb, sorted.data(), bases, buckets.data(), head.data(), tail.data());
-        for (uint32_t b = 0; b < p.nb; ++b) msm_merge_bucket<C>(b, L, offsets.data(), buckets.data(), head.data(), tail.data());
+            msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), p.nb, sorted.data(), bases, buckets.data(), head.data(), tail.data(),
+                                    tail_bucket.data());
+        for (size_t t = 0; t < slices + 1; ++t)  // one thread past the end, as a partly filled last block launches
+            msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), buckets.data(), head.data(), tail.data(), tail_bucket.data());
     }
     XYZZ<C> total = XYZZ<C>::inf();
     for (int w = p.W - 1; w >= 0; --w) {

@@ -8,6 +8,8 @@ import aes_zero_knowledge_proof_circuit_b200 as zk
 def main():
     logs = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["16", "20", "22"])]
     windows = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
+    # optional third argument: tuning sets separated by '/', each "key=value,key=value" (zkaes_ctx_set_tuning)
+    tunings = sys.argv[3].split("/") if len(sys.argv) > 3 else [""]
     ctx = zk.Context(0)
     curve = 377
     stream = torch.cuda.ExternalStream(ctx.stream)
@@ -20,13 +22,16 @@ def main():
         sc = torch.randint(0, 2**62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
         sc[:, 3] &= (1 << 59) - 1   # < r
         torch.cuda.synchronize()
-        for w in windows:
+        for tune in tunings:
+          for kv in filter(None, tune.split(",")):
+            ctx.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
+          for w in windows:
             ctx.set_msm_window(w)
             for it in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream); out = ctx.msm_g1_device(curve, bases, sc, n); e1.record(stream); e1.synchronize()
                 ms = e0.elapsed_time(e1)
-            print(f"msm 2^{lg} c={w}: {ms:.3f} ms  ({n/ms/1e3:.2f} Mpts/s, {128*n/ms/1e6:.1f} GB/s algorithmic)", flush=True)
+            print(f"msm 2^{lg} c={w} [{tune}]: {ms:.3f} ms  ({n/ms/1e3:.2f} Mpts/s, {128*n/ms/1e6:.1f} GB/s algorithmic)", flush=True)
         ctx.set_msm_window(0)
         data = sc.clone()
         for it in range(3):
