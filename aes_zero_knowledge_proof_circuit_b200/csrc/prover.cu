@@ -612,6 +612,19 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const Fr vh_beta = vanishing(beta, h);
     const Fr vv = vh_alpha * vh_beta;
     const Fr hinv = Fr::from_u64(h).inverse();
+    // The hiding part of the opening at beta, S = mask + c_za z_a + c_w w + c_h1 h_1, only needs beta, t(beta) and z_b(beta):
+    // form it now (in place in the mask buffer) so that z_a, w and h_1 (10.7 GB at 4 KiB) are not carried through round 3,
+    // the prover's memory peak.  Field arithmetic is exact, so ch^2 * S later equals the term-by-term combination.
+    Fr ev_t, ev_zb;
+    ZK_TRY(po_eval(ctx, tpoly.as<Fr>(), h, beta, &ev_t));
+    ZK_TRY(po_eval(ctx, zb.as<Fr>(), h + 1, beta, &ev_zb));
+    const Fr c_za_lc = bivariate_u(alpha, beta, h) * (eta[0] + eta[2] * ev_zb);
+    const Fr c_w_lc = (ev_t * vanishing(beta, x)).neg();
+    const Fr c_h1_lc = vh_beta.neg();
+    ZK_TRY(po_axpy(ctx, mask.as<Fr>(), za.as<Fr>(), c_za_lc, h + 1));
+    ZK_TRY(po_axpy(ctx, mask.as<Fr>(), w_poly.as<Fr>(), c_w_lc, len_w));
+    ZK_TRY(po_axpy(ctx, mask.as<Fr>(), h1.as<Fr>(), c_h1_lc, len_h1));
+    za.release(); w_poly.release(); h1.release();
     DevBuf fpoly, den, inv;
     ZK_CUDA(ctx, fpoly.alloc(sizeof(Fr) * k, st));
     ZK_CUDA(ctx, den.alloc(sizeof(Fr) * k, st));
@@ -689,11 +702,9 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     Fr gamma = fr_rand(fs.rng);
 
     // ---- evaluations (sorted by label: a_denom b_denom c_denom g_1 g_2 t z_b) ---------------------------------------------
-    Fr ev_g1, ev_g2, ev_t, ev_zb, ev_den[3];
+    Fr ev_g1, ev_g2, ev_den[3];
     ZK_TRY(po_eval(ctx, g1, len_g1, beta, &ev_g1));
     ZK_TRY(po_eval(ctx, g2, len_g2, gamma, &ev_g2));
-    ZK_TRY(po_eval(ctx, tpoly.as<Fr>(), h, beta, &ev_t));
-    ZK_TRY(po_eval(ctx, zb.as<Fr>(), h + 1, beta, &ev_zb));
     for (int m = 0; m < 3; ++m) {
         Fr er, ec, erc;
         ZK_TRY(po_eval(ctx, pk.idx_poly[4 * m + 0], k, gamma, &er));
@@ -720,16 +731,8 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     Fr rv_beta;
     {
         // x(beta) for the constant term is not part of the opened polynomial (constants are dropped by open_combinations)
-        const Fr r_ab_beta = bivariate_u(alpha, beta, h);
-        const Fr vx_beta = vanishing(beta, x);
-        const Fr c_za_lc = r_ab_beta * (eta[0] + eta[2] * ev_zb);
-        const Fr c_w_lc = (ev_t * vx_beta).neg();
-        const Fr c_h1_lc = vh_beta.neg();
-        DevBuf& P = mask;  // the mask polynomial is not needed after this point: build the combination in place
-        ZK_TRY(po_scale(ctx, P.as<Fr>(), mask.as<Fr>(), chp[2], len_mask));                 // ch^2 * mask
-        ZK_TRY(po_axpy(ctx, P.as<Fr>(), za.as<Fr>(), chp[2] * c_za_lc, h + 1));
-        ZK_TRY(po_axpy(ctx, P.as<Fr>(), w_poly.as<Fr>(), chp[2] * c_w_lc, len_w));
-        ZK_TRY(po_axpy(ctx, P.as<Fr>(), h1.as<Fr>(), chp[2] * c_h1_lc, len_h1));
+        DevBuf& P = mask;  // holds S = mask + c_za z_a + c_w w + c_h1 h_1 since the start of round 3
+        ZK_TRY(po_scale(ctx, P.as<Fr>(), P.as<Fr>(), chp[2], len_mask));                   // ch^2 * S
         ZK_TRY(po_axpy(ctx, P.as<Fr>(), g1, chp[0], len_g1));
         ZK_TRY(po_axpy(ctx, P.as<Fr>(), tpoly.as<Fr>(), chp[3], h));
         ZK_TRY(po_axpy(ctx, P.as<Fr>(), zb.as<Fr>(), chp[4], h + 1));
@@ -755,8 +758,8 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
         w_beta = g1_add(w_beta, g1_mul(sw, chp[1]));
         rv_beta = rv_beta + chp[1] * c_g1.shifted_rand.eval(beta);
     }
-    // nothing below needs the round-1 / round-2 polynomials: return ~23 GB (at 4 KiB) to the pool before the 3|K|-sized opening
-    mask.release(); za.release(); zb.release(); w_poly.release(); tpoly.release(); h1.release(); xg1.release();
+    // nothing below needs the round-1 / round-2 polynomials: return them to the pool before the 3|K|-sized opening
+    mask.release(); zb.release(); tpoly.release(); xg1.release();
     tr.mark("opening at beta");
     // gamma: a_denom [ch^0], b_denom [ch^1], c_denom [ch^2], g_2 [ch^3, shifted ch^4], inner_sumcheck [ch^5]; nothing is hiding
     {

@@ -37,6 +37,9 @@ FR_BITS = 253
 SEED_TAU, SEED_GAMMA, SEED_ZK = bytes(range(32)), bytes(range(1, 33)), bytes([7] * 32)
 AES_KEY = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")  # FIPS-197 (SURVEY.md 8(d) synthetic inputs)
 MADD_PEAK_PER_S = 2.48e9  # XYZZ += affine on one B200, tools/ubench.cu (profiles/ubench_r1.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_msm_accumulate launch over 2^26 terms at c = 22 / 12 windows, from the
+# `ncu --set full` capture summarised in profiles/r1_ncu_full_msm_accumulate_slices_2p26.txt (167.0 GB + 4.2 GB)
+NCU_TRAFFIC_BYTES_PER_TERM = 171.2e9 / 2**26
 
 
 def synth_message(n):
@@ -243,8 +246,11 @@ def bench_prove(args, rank, world, local_rank):
                    "cache": "per-step working set (index polynomials + SRS + round buffers) exceeds the 126 MB L2; no flush needed",
                    "key_setup_s": setup_s, "proof_bytes": len(proof)},
         "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate (MSM bucket accumulation, XYZZ += affine)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "launches_per_step": prof["launches"] / args.steps, "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_TERM * prof["terms"] / max(prof["launches"], 1),
+                     "traffic_note": "bytes per launch = ncu-measured DRAM bytes per MSM term (profiles/r1_ncu_full_msm_accumulate_slices_2p26.txt) x terms per launch; "
+                                     "the bucket method gathers every point once per window (DESIGN.md 4.6)",
+                     "peak_source": peak_src, "launches_per_step": prof["launches"] / args.steps, "avg_launch_ms": acc_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "share_of_step": prof["ms"] / dev_ms if dev_ms else None,
                      "alu": {"madds_per_s": prof["madds"] / (prof["ms"] * 1e-3) if prof["ms"] else 0.0, "madd_peak_per_s": MADD_PEAK_PER_S,
                              "frac": (prof["madds"] / (prof["ms"] * 1e-3) / MADD_PEAK_PER_S) if prof["ms"] else 0.0,
