@@ -2,4 +2,4 @@
 
 Host-side mirror of the reference's public surface (src/lib.rs) over the C ABI in include/zkaes_b200.h.
 """
-from ._native import CURVE_BLS12_377, CURVE_BLS12_381, Circuit, Context, ProvingKey, ZkAesError, comm_unique_id, lib, shard_range  # noqa: F401
+from ._native import CURVE_BLS12_377, CURVE_BLS12_381, Circuit, Context, ProvingKey, ZkAesError, comm_unique_id, lib, pairing_selftest, shard_range, verify_encryption  # noqa: F401

@@ -71,6 +71,9 @@ def _load():
         "zkaes_pk_info": (c_int, [vp, vp]),
         "zkaes_pk_vk_bytes": (c_int, [vp, vp, POINTER(c_size_t)]),
         "zkaes_encrypt": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp, vp, POINTER(c_size_t)]),
+        "zkaes_pk_verifying_key": (c_int, [vp, vp, POINTER(c_size_t)]),
+        "zkaes_verify_encryption": (c_int, [vp, c_size_t, vp, c_size_t, vp, c_size_t, POINTER(c_int)]),
+        "zkaes_selftest_pairing": (c_int, [vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
@@ -327,6 +330,14 @@ class ProvingKey:
         assert lib().zkaes_pk_vk_bytes(self._h, _ptr(buf), ctypes.byref(n)) == 0
         return buf.tobytes()
 
+    def verifying_key(self) -> bytes:
+        """The VerifyingKey half of synthesize_keys' result (src/lib.rs:138): what verify_encryption takes."""
+        n = c_size_t(0)
+        assert lib().zkaes_pk_verifying_key(self._h, None, ctypes.byref(n)) == 0
+        buf = np.zeros(n.value, dtype=np.uint8)
+        assert lib().zkaes_pk_verifying_key(self._h, _ptr(buf), ctypes.byref(n)) == 0
+        return buf.tobytes()
+
     def close(self):
         if self._h:
             lib().zkaes_pk_free(self._h)
@@ -361,6 +372,29 @@ def _encrypt(self, pk: ProvingKey, message: bytes, secret_key: bytes, zk_seed: b
     proof = np.zeros(n.value, dtype=np.uint8)
     self._check(lib().zkaes_encrypt(self._h, pk._h, _ptr(m), len(message), _ptr(k), _ptr(_seed(zk_seed)), _ptr(ct), _ptr(proof), ctypes.byref(n)))
     return ct[: len(message)].tobytes(), proof[: n.value].tobytes()
+
+
+def verify_encryption(verifying_key: bytes, proof: bytes, ciphertext: bytes) -> bool:
+    """`verify_encryption(verifying_key, proof, ciphertext) -> Result<bool>` (reference src/lib.rs:116-136).  Host only: no
+    Context / GPU needed.  Raises ZkAesError when the key or the proof cannot be parsed (the reference's Err)."""
+    vk = np.frombuffer(bytes(verifying_key), dtype=np.uint8)
+    pf = np.frombuffer(bytes(proof), dtype=np.uint8)
+    ct = np.frombuffer(bytes(ciphertext) or b"\0", dtype=np.uint8)
+    ok = c_int(0)
+    rc = lib().zkaes_verify_encryption(_ptr(vk), len(verifying_key), _ptr(pf), len(proof), _ptr(ct), len(ciphertext), ctypes.byref(ok))
+    if rc != 0:
+        msg = lib().zkaes_last_error(None)
+        raise ZkAesError(f"libzkaes_b200 error {rc}: {msg.decode() if msg else ''}")
+    return bool(ok.value)
+
+
+def pairing_selftest(a: int, b: int) -> bytes:
+    """e(a G1, b G2) as 576 canonical bytes (test hook, compared with oracle/pairing_ref.py)."""
+    out = np.zeros(576, dtype=np.uint8)
+    ab = np.frombuffer(int(a).to_bytes(32, "little"), dtype=np.uint8)
+    bb = np.frombuffer(int(b).to_bytes(32, "little"), dtype=np.uint8)
+    assert lib().zkaes_selftest_pairing(_ptr(ab), _ptr(bb), _ptr(out)) == 0
+    return out.tobytes()
 
 
 Context.synthesize_keys = _synthesize_keys

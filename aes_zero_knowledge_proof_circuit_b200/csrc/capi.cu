@@ -9,6 +9,7 @@
 #include "witness.cuh"
 #include "prover.cuh"
 #include "comm.cuh"
+#include "verifier.h"
 #include <cstring>
 #include <stdexcept>
 
@@ -97,7 +98,9 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
-const char* zkaes_last_error(const zkaes_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+// context-free entry points (the host verifier) report through a per-thread string, read with zkaes_last_error(NULL)
+static thread_local std::string g_host_err;
+const char* zkaes_last_error(const zkaes_ctx* ctx) { return ctx ? ctx->err.c_str() : g_host_err.empty() ? "null context" : g_host_err.c_str(); }
 void* zkaes_ctx_stream(zkaes_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int zkaes_ctx_sync(zkaes_ctx* ctx) {
@@ -471,6 +474,31 @@ int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len) {
         memcpy(out, v.data(), v.size());
     }
     *len = v.size();
+    return ZK_OK;
+}
+int zkaes_pk_verifying_key(const zkaes_pk* pk, uint8_t* out, size_t* len) {
+    if (!pk || !len) return ZK_ERR_ARG;
+    const std::vector<uint8_t>& v = zk::pk_verifying_key(reinterpret_cast<const zk::zkaes_pk_impl*>(pk));
+    if (out) {
+        if (*len < v.size()) return ZK_ERR_ARG;
+        memcpy(out, v.data(), v.size());
+    }
+    *len = v.size();
+    return ZK_OK;
+}
+int zkaes_verify_encryption(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* ciphertext, size_t ct_len,
+                            int* accepted) {
+    if (!vk || !proof || (!ciphertext && ct_len) || !accepted) {
+        g_host_err = "verify_encryption: null pointer";
+        return ZK_ERR_ARG;
+    }
+    g_host_err.clear();
+    int rc = zk::verify_encryption_host(vk, vk_len, proof, proof_len, ciphertext, ct_len, accepted, &g_host_err);
+    return rc == 0 ? ZK_OK : ZK_ERR_ARG;
+}
+int zkaes_selftest_pairing(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]) {
+    if (!a32 || !b32 || !out576) return ZK_ERR_ARG;
+    zk::pairing_selftest(a32, b32, out576);
     return ZK_OK;
 }
 int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed32[32],

@@ -23,6 +23,7 @@
 #include "ntt.cuh"
 #include "srs.cuh"
 #include "transcript.h"
+#include "verifier.h"
 
 namespace zk {
 
@@ -239,7 +240,8 @@ struct zkaes_pk_impl {
     size_t srs_count = 0;
     Aff gamma_g[3];         // gamma tau^i G (host)
     Aff index_comms[12];
-    std::vector<uint8_t> vk_bytes;
+    std::vector<uint8_t> vk_bytes;   // IndexVerifierKey ToBytes (enters the Fiat-Shamir seed)
+    std::vector<uint8_t> vk_full;    // the verifying key verify_encryption takes (verifier.h)
     WitnessDev wit;
     ~zkaes_pk_impl() {
         for (int m = 0; m < 3; ++m) {
@@ -442,6 +444,8 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         cm.comm = pk.index_comms[i];
         comm_to_bytes(cm, pk.vk_bytes);
     }
+    // the VerifyingKey half of synthesize_keys' result (src/lib.rs:138): index vk + KZG verifier key + the two shift powers
+    pk.vk_full = build_verifying_key(pk.vk_bytes, x, pk.D, tau, gamma, {h - 2, k - 2});
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     *out = pkp.release();
     return ZK_OK;
@@ -449,6 +453,7 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
 
 void pk_free(zkaes_pk_impl* pk) { delete pk; }
 const std::vector<uint8_t>& pk_vk_bytes(const zkaes_pk_impl* pk) { return pk->vk_bytes; }
+const std::vector<uint8_t>& pk_verifying_key(const zkaes_pk_impl* pk) { return pk->vk_full; }
 void pk_info(const zkaes_pk_impl* pk, uint64_t info[ZK_PK_INFO_WORDS]) {
     const AesCircuit& c = pk->circ;
     uint64_t v[ZK_PK_INFO_WORDS] = {c.msg_len, c.num_constraints, (uint64_t)c.num_instance + c.num_witness, pk->nnz[0], pk->nnz[1], pk->nnz[2],

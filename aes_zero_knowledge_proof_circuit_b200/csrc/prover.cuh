@@ -16,6 +16,7 @@ constexpr int ZK_PK_INFO_WORDS = 11;
 int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], const uint8_t gamma_seed[32], zkaes_pk_impl** out);
 void pk_free(zkaes_pk_impl* pk);
 const std::vector<uint8_t>& pk_vk_bytes(const zkaes_pk_impl* pk);
+const std::vector<uint8_t>& pk_verifying_key(const zkaes_pk_impl* pk);
 // 0 msg_len, 1 num_constraints, 2 num_variables, 3-5 nnz(A,B,C), 6 |H|, 7 |K|, 8 |X|, 9 SRS max degree, 10 instance variables used
 void pk_info(const zkaes_pk_impl* pk, uint64_t info[ZK_PK_INFO_WORDS]);
 int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pk, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed[32],

@@ -1,0 +1,491 @@
+// verify_encryption on the host: the Marlin verifier for the AES-128-ECB circuit.
+//
+// Stands in for `verify_encryption(verifying_key, proof, ciphertext)` (reference src/lib.rs:116-136), which formats the
+// ciphertext as 8 public-input bits per byte (src/helpers/mod.rs:84-93) and calls simpleworks::marlin::verify_proof ->
+// ark-marlin 0.3.0 Marlin::verify: Fiat-Shamir replay of the three AHP rounds, ahp/mod.rs construct_linear_combinations,
+// ark-poly-commit 0.3.0 marlin_pc::check_combinations (degree-bound adjustment with the shift powers) and one KZG
+// pairing equation per query point.  The verifier is CPU code in the reference and CPU code here;
+// no device is needed.  Deviation: the two query points are checked one after the other instead of through ark's
+// randomised batch (which draws from the caller's rng); accept/reject is the same up to the batch's soundness error.
+#include "verifier.h"
+
+#include <cstring>
+#include <stdexcept>
+
+#include "pairing.h"
+#include "transcript.h"
+
+namespace zk {
+namespace {
+using Fr = Fp<Fr377Params>;
+using Fq = Fp<Fq377Params>;
+using Aff = Affine<G1_377Params>;
+using XY = XYZZ<G1_377Params>;
+using pairing::Fq2;
+using pairing::G2A;
+
+constexpr char VK_MAGIC[8] = {'Z', 'K', 'A', 'E', 'S', 'V', 'K', '1'};
+
+struct Reader {
+    const uint8_t* p;
+    size_t n, pos = 0;
+    Reader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
+    const uint8_t* take(size_t k) {
+        if (k > n - pos) throw std::runtime_error("truncated input");
+        const uint8_t* r = p + pos;
+        pos += k;
+        return r;
+    }
+    uint64_t u64() {
+        const uint8_t* b = take(8);
+        uint64_t v = 0;
+        for (int i = 0; i < 8; ++i) v |= (uint64_t)b[i] << (8 * i);
+        return v;
+    }
+    uint8_t u8() { return *take(1); }
+    bool done() const { return pos == n; }
+};
+void put_u64(std::vector<uint8_t>& out, uint64_t v) {
+    for (int i = 0; i < 8; ++i) out.push_back((uint8_t)(v >> (8 * i)));
+}
+
+// ---- field helpers ---------------------------------------------------------------------------------------------------
+Fr fr_pow_u64(Fr b, uint64_t e) {
+    Fr r = Fr::one();
+    while (e) {
+        if (e & 1) r = r * b;
+        b = b.sqr();
+        e >>= 1;
+    }
+    return r;
+}
+Fr fr_from_canonical(const uint8_t b[32], bool* ok) {
+    Fr t;
+    memcpy(t.v, b, 32);
+    Fr m;
+    for (int i = 0; i < 8; ++i) m.v[i] = Fr377Params::MOD(i);
+    if (!m.canonical_gt(t)) *ok = false;  // must be < r
+    return t.to_mont();
+}
+Fr fr_rand(ChaCha20Rng& rng) {
+    uint64_t w[4];
+    fr_rand_raw<Fr377Params>(rng, w);
+    Fr r;
+    memcpy(r.v, w, 32);
+    return r;
+}
+Fr domain_gen(int log_n) {
+    Fr g;
+    for (int i = 0; i < 8; ++i) g.v[i] = Fr377Params::ROOT(i);
+    for (int i = log_n; i < Fr377Params::TWO_ADICITY; ++i) g = g.sqr();
+    return g;
+}
+Fr vanishing(const Fr& x, uint64_t n) { return fr_pow_u64(x, n) - Fr::one(); }
+uint64_t next_pow2(uint64_t v) {
+    uint64_t n = 1;
+    while (n < v) n <<= 1;
+    return n;
+}
+int log2_exact(uint64_t n) {
+    int l = 0;
+    while (((uint64_t)1 << l) < n) ++l;
+    return l;
+}
+
+// Tonelli-Shanks in Fq (q - 1 = 2^46 t)
+bool fq_sqrt(const Fq& a, Fq* out) {
+    if (a.is_zero()) {
+        *out = a;
+        return true;
+    }
+    uint32_t qm1[12], t[12], e[12];
+    for (int i = 0; i < 12; ++i) qm1[i] = Fq377Params::MOD(i);
+    qm1[0] -= 1;  // q is odd
+    auto shr = [](uint32_t* w, int s) {  // s < 32
+        for (int i = 0; i < 12; ++i) w[i] = (w[i] >> s) | (i + 1 < 12 ? w[i + 1] << (32 - s) : 0);
+    };
+    memcpy(e, qm1, sizeof(e));
+    shr(e, 1);  // (q - 1) / 2
+    if (!(a.pow(e, 12) == Fq::one())) return false;
+    int s = 0;
+    memcpy(t, qm1, sizeof(t));
+    while (!(t[0] & 1)) {
+        shr(t, 1);
+        ++s;
+    }
+    Fq z = Fq::from_u64(2);
+    while (z.pow(e, 12) == Fq::one()) z = z + Fq::one();  // a non-residue
+    uint32_t t1[12];  // (t + 1) / 2
+    memcpy(t1, t, sizeof(t1));
+    t1[0] += 1;  // t is odd: no carry past limb 0 unless t[0] = 0xffffffff
+    if (t1[0] == 0)
+        for (int i = 1; i < 12 && ++t1[i] == 0; ++i) {}
+    shr(t1, 1);
+    int m = s;
+    Fq c = z.pow(t, 12), tt = a.pow(t, 12), r = a.pow(t1, 12);
+    while (!(tt == Fq::one())) {
+        int i = 0;
+        Fq t2 = tt;
+        while (!(t2 == Fq::one())) {
+            t2 = t2.sqr();
+            ++i;
+        }
+        Fq b = c;
+        for (int k = 0; k < m - i - 1; ++k) b = b.sqr();
+        m = i;
+        c = b.sqr();
+        tt = tt * c;
+        r = r * b;
+    }
+    *out = r;
+    return true;
+}
+
+// ---- G1 helpers --------------------------------------------------------------------------------------------------------
+Aff g1_scale(const Aff& p, const Fr& s_mont) {
+    Fr s = s_mont.from_mont();
+    XY acc = XY::inf();
+    for (int i = 255; i >= 0; --i) {
+        acc = acc.dbl();
+        if ((s.v[i >> 5] >> (i & 31)) & 1) acc.madd(p);
+    }
+    return acc.to_affine();
+}
+bool fq_from_canonical(const uint8_t b[48], Fq* out) {
+    Fq t, m;
+    memcpy(t.v, b, 48);
+    for (int i = 0; i < 12; ++i) m.v[i] = Fq377Params::MOD(i);
+    if (!m.canonical_gt(t)) return false;
+    *out = t.to_mont();
+    return true;
+}
+// ark-ff ToBytes / FromBytes of GroupAffine: x || y canonical LE || infinity flag (97 bytes)
+void g1_to_bytes(const Aff& p, std::vector<uint8_t>& out) {
+    uint8_t b[97];
+    if (p.is_inf()) {
+        memset(b, 0, 97);
+        b[48] = 1;
+        b[96] = 1;
+    } else {
+        Fq x = p.x.from_mont(), y = p.y.from_mont();
+        memcpy(b, x.v, 48);
+        memcpy(b + 48, y.v, 48);
+        b[96] = 0;
+    }
+    out.insert(out.end(), b, b + 97);
+}
+Aff g1_from_bytes(const uint8_t b[97]) {
+    if (b[96]) return Aff::inf();
+    Aff p;
+    if (!fq_from_canonical(b, &p.x) || !fq_from_canonical(b + 48, &p.y)) throw std::runtime_error("G1 coordinate out of range");
+    if (!p.on_curve()) throw std::runtime_error("G1 point not on the curve");
+    return p;
+}
+// ark-serialize 0.3.0 compressed GroupAffine (48 bytes): bit 7 of the last byte = "y > -y", bit 6 = infinity
+Aff g1_deserialize(const uint8_t b[48]) {
+    uint8_t c[48];
+    memcpy(c, b, 48);
+    const int flags = c[47] >> 6;
+    c[47] &= 0x3f;
+    if (flags & 1) return Aff::inf();
+    Aff p;
+    if (!fq_from_canonical(c, &p.x)) throw std::runtime_error("G1 x out of range");
+    Fq y;
+    if (!fq_sqrt(p.x.sqr() * p.x + Fq::one(), &y)) throw std::runtime_error("G1 x not on the curve");  // y^2 = x^3 + 1
+    Fq ny = y.neg();
+    const bool greater = y.from_mont().canonical_gt(ny.from_mont());
+    p.y = (greater == (bool)(flags & 2)) ? y : ny;
+    return p;
+}
+void g2_to_bytes(const G2A& p, std::vector<uint8_t>& out) {
+    const Fq* c[4] = {&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1};
+    for (const Fq* f : c) {
+        Fq t = f->from_mont();
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(t.v);
+        out.insert(out.end(), b, b + 48);
+    }
+}
+G2A g2_from_bytes(const uint8_t* b) {
+    G2A p;
+    Fq* c[4] = {&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1};
+    for (int i = 0; i < 4; ++i)
+        if (!fq_from_canonical(b + 48 * i, c[i])) throw std::runtime_error("G2 coordinate out of range");
+    if (!p.on_curve()) throw std::runtime_error("G2 point not on the twist");
+    return p;
+}
+
+struct Commitment {
+    Aff comm;
+    bool has_shifted = false;
+    Aff shifted;
+};
+void comm_to_bytes(const Commitment& c, std::vector<uint8_t>& out) {  // ToBytes of marlin_pc::Commitment (195 bytes)
+    g1_to_bytes(c.comm, out);
+    out.push_back(c.has_shifted ? 1 : 0);
+    g1_to_bytes(c.has_shifted ? c.shifted : Aff::inf(), out);
+}
+
+struct Term {
+    Fr coeff;
+    int poly;  // index into the commitment table, -1 = the constant polynomial 1
+};
+enum PolyId { A_ROW, A_COL, A_VAL, A_ROW_COL, B_ROW, B_COL, B_VAL, B_ROW_COL, C_ROW, C_COL, C_VAL, C_ROW_COL,
+              P_W, P_ZA, P_ZB, P_MASK, P_T, P_G1, P_H1, P_G2, P_H2, N_POLYS };
+
+}  // namespace
+
+std::vector<uint8_t> build_verifying_key(const std::vector<uint8_t>& index_vk, uint64_t x_padded, uint64_t max_degree, const Fp<Fr377Params>& tau,
+                                         const Fp<Fr377Params>& gamma, const std::vector<uint64_t>& degree_bounds) {
+    std::vector<uint8_t> out(VK_MAGIC, VK_MAGIC + 8);
+    put_u64(out, x_padded);
+    put_u64(out, max_degree);
+    put_u64(out, index_vk.size());
+    out.insert(out.end(), index_vk.begin(), index_vk.end());
+    const Aff g = Aff::generator();
+    g1_to_bytes(g, out);
+    g1_to_bytes(g1_scale(g, gamma), out);
+    const G2A h = G2A::generator();
+    g2_to_bytes(h, out);
+    Fr tc = tau.from_mont();
+    g2_to_bytes(pairing::g2_mul(h, tc.v, 8), out);
+    put_u64(out, degree_bounds.size());
+    for (uint64_t b : degree_bounds) {  // ark-poly-commit VerifierKey::degree_bounds_and_shift_powers: tau^(D - bound) G
+        put_u64(out, b);
+        g1_to_bytes(g1_scale(g, fr_pow_u64(tau, max_degree - b)), out);
+    }
+    return out;
+}
+
+int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t* proof_bytes, size_t proof_len, const uint8_t* ct, size_t ct_len,
+                           int* accepted, std::string* err) {
+    *accepted = 0;
+    try {
+        // ---- verifying key ------------------------------------------------------------------------------------------------
+        Reader vk(vk_bytes, vk_len);
+        if (memcmp(vk.take(8), VK_MAGIC, 8) != 0) throw std::runtime_error("not a zkaes verifying key");
+        const uint64_t x = vk.u64(), D = vk.u64(), ivk_len = vk.u64();
+        const uint8_t* ivk = vk.take(ivk_len);
+        if (ivk_len != 24 + 12 * 195) throw std::runtime_error("index verifying key has the wrong size");
+        Reader ir(ivk, ivk_len);
+        ir.u64();  // number of variables
+        const uint64_t ncons = ir.u64(), nnz = ir.u64();
+        Aff comm[N_POLYS], shifted[N_POLYS];
+        long bound[N_POLYS];
+        for (int i = 0; i < N_POLYS; ++i) bound[i] = -1;
+        for (int i = 0; i < 12; ++i) {
+            comm[i] = g1_from_bytes(ir.take(97));
+            ir.take(98);
+        }
+        const Aff G = g1_from_bytes(vk.take(97)), gamma_G = g1_from_bytes(vk.take(97));
+        const G2A H = g2_from_bytes(vk.take(192)), beta_H = g2_from_bytes(vk.take(192));
+        const uint64_t nb = vk.u64();
+        std::vector<std::pair<uint64_t, Aff>> shift_powers;
+        for (uint64_t i = 0; i < nb; ++i) {
+            uint64_t b = vk.u64();
+            shift_powers.emplace_back(b, g1_from_bytes(vk.take(97)));
+        }
+        if (!vk.done()) throw std::runtime_error("trailing bytes in the verifying key");
+        const uint64_t h = next_pow2(ncons), k = next_pow2(nnz);
+        if (x < 2 || (x & (x - 1)) || x > h) throw std::runtime_error("bad public-input domain");
+        auto shift_power = [&](uint64_t b) -> const Aff& {
+            for (auto& sp : shift_powers)
+                if (sp.first == b) return sp.second;
+            throw std::runtime_error("verifying key lacks a shift power");
+        };
+
+        // ---- proof (ark-serialize 0.3.0 CanonicalDeserialize of ark_marlin::Proof) -------------------------------------------
+        Reader pr(proof_bytes, proof_len);
+        static const int round_sizes[3] = {4, 3, 2};
+        static const int round_poly[3][4] = {{P_W, P_ZA, P_ZB, P_MASK}, {P_T, P_G1, P_H1, -1}, {P_G2, P_H2, -1, -1}};
+        bound[P_G1] = (long)(h - 2);
+        bound[P_G2] = (long)(k - 2);
+        std::vector<uint8_t> round_bytes[3];
+        if (pr.u64() != 3) return 0;
+        for (int r = 0; r < 3; ++r) {
+            if (pr.u64() != (uint64_t)round_sizes[r]) return 0;
+            for (int i = 0; i < round_sizes[r]; ++i) {
+                Commitment c;
+                c.comm = g1_deserialize(pr.take(48));
+                c.has_shifted = pr.u8() != 0;
+                if (c.has_shifted) c.shifted = g1_deserialize(pr.take(48));
+                const int id = round_poly[r][i];
+                if (c.has_shifted != (bound[id] >= 0)) return 0;  // degree bounds exactly where the protocol puts them
+                comm[id] = c.comm;
+                shifted[id] = c.shifted;
+                comm_to_bytes(c, round_bytes[r]);
+            }
+        }
+        bool ok = true;
+        if (pr.u64() != 7) return 0;
+        Fr ev[7];  // a_denom b_denom c_denom g_1 g_2 t z_b
+        const uint8_t* evp = pr.take(7 * 32);
+        const std::vector<uint8_t> ev_bytes(evp, evp + 7 * 32);
+        for (int i = 0; i < 7; ++i) ev[i] = fr_from_canonical(evp + 32 * i, &ok);
+        const uint64_t nmsg = pr.u64();
+        for (uint64_t i = 0; i < nmsg; ++i)
+            if (pr.u8()) {
+                uint64_t cnt = pr.u64();
+                pr.take(32 * cnt);
+            }
+        if (pr.u64() != 2) return 0;
+        Aff W[2];
+        bool has_rv[2];
+        Fr rv[2];
+        for (int i = 0; i < 2; ++i) {
+            W[i] = g1_deserialize(pr.take(48));
+            has_rv[i] = pr.u8() != 0;
+            rv[i] = has_rv[i] ? fr_from_canonical(pr.take(32), &ok) : Fr::zero();
+        }
+        if (pr.u8() != 0 || !pr.done() || !ok) return 0;
+
+        // ---- public input: 8 bits per ciphertext byte, LSB first (src/helpers/mod.rs:84-93), zero-padded to |X| - 1 ----------
+        if (8 * (uint64_t)ct_len > x - 1) return 0;
+        std::vector<uint8_t> seed;
+        seed.insert(seed.end(), {'M', 'A', 'R', 'L', 'I', 'N', '-', '2', '0', '1', '9'});
+        seed.insert(seed.end(), ivk, ivk + ivk_len);
+        const size_t in_off = seed.size();
+        seed.resize(in_off + 32 * (x - 1), 0);
+        for (size_t i = 0; i < 8 * ct_len; ++i) seed[in_off + 32 * i] = (ct[i >> 3] >> (i & 7)) & 1;
+
+        // ---- Fiat-Shamir replay ------------------------------------------------------------------------------------------------
+        FiatShamirRng fs(seed);
+        auto outside = [&](uint64_t n) {
+            for (;;) {
+                Fr t = fr_rand(fs.rng);
+                if (!vanishing(t, n).is_zero()) return t;
+            }
+        };
+        fs.absorb(round_bytes[0]);
+        const Fr alpha = outside(h);
+        const Fr eta_a = fr_rand(fs.rng), eta_b = fr_rand(fs.rng), eta_c = fr_rand(fs.rng);
+        fs.absorb(round_bytes[1]);
+        const Fr beta = outside(h);
+        fs.absorb(round_bytes[2]);
+        const Fr gamma = fr_rand(fs.rng);
+        fs.absorb(ev_bytes);
+        Fr ch = Fr::zero();
+        {
+            uint64_t lo = fs.rng.next_u64(), hi = fs.rng.next_u64();
+            ch.v[0] = (uint32_t)lo; ch.v[1] = (uint32_t)(lo >> 32); ch.v[2] = (uint32_t)hi; ch.v[3] = (uint32_t)(hi >> 32);
+            ch = ch.to_mont();
+        }
+
+        // ---- x(beta): barycentric evaluation of the interpolant of (1, inputs) over the domain X ---------------------------------
+        Fr x_at_beta;
+        {
+            const Fr wx = domain_gen(log2_exact(x));
+            std::vector<Fr> num, den;  // omega^i and beta - omega^i for the non-zero values (all equal to one)
+            Fr wi = Fr::one();
+            for (uint64_t i = 0; i < x; ++i, wi = wi * wx) {
+                const bool set = i == 0 || (i - 1 < 8 * ct_len && ((ct[(i - 1) >> 3] >> ((i - 1) & 7)) & 1));
+                if (!set) continue;
+                num.push_back(wi);
+                den.push_back(beta - wi);
+            }
+            // batch inversion
+            std::vector<Fr> pre(den.size());
+            Fr acc = Fr::one();
+            for (size_t i = 0; i < den.size(); ++i) {
+                pre[i] = acc;
+                acc = acc * den[i];
+            }
+            Fr inv = acc.inverse(), sum = Fr::zero();
+            for (size_t i = den.size(); i-- > 0;) {
+                sum = sum + num[i] * inv * pre[i];
+                inv = inv * den[i];
+            }
+            x_at_beta = sum * vanishing(beta, x) * Fr::from_u64(x).inverse();
+        }
+
+        // ---- ahp/mod.rs construct_linear_combinations ----------------------------------------------------------------------------
+        const Fr ev_den[3] = {ev[0], ev[1], ev[2]}, g1_b = ev[3], g2_g = ev[4], t_b = ev[5], zb_b = ev[6];
+        const Fr vh_alpha = vanishing(alpha, h), vh_beta = vanishing(beta, h), vx_beta = vanishing(beta, x);
+        const Fr r_alpha_at_beta = (vh_alpha - vh_beta) * (alpha - beta).inverse();
+        const Fr ab = alpha * beta, vv = vh_alpha * vh_beta;
+        const Fr one = Fr::one();
+        struct LC {
+            std::vector<Term> terms;
+            Fr value;  // claimed evaluation at the query point
+        };
+        auto denom = [&](int m) {
+            LC lc;
+            lc.terms = {{ab, -1}, {alpha.neg(), 4 * m + 0}, {beta.neg(), 4 * m + 1}, {one, 4 * m + 3}};
+            lc.value = ev_den[m];
+            return lc;
+        };
+        LC lc_g1{{{one, P_G1}}, g1_b}, lc_t{{{one, P_T}}, t_b}, lc_zb{{{one, P_ZB}}, zb_b}, lc_g2{{{one, P_G2}}, g2_g};
+        LC outer{{{one, P_MASK}, {r_alpha_at_beta * (eta_a + eta_c * zb_b), P_ZA}, {r_alpha_at_beta * eta_b * zb_b, -1}, {(t_b * vx_beta).neg(), P_W},
+                  {(t_b * x_at_beta).neg(), -1}, {vh_beta.neg(), P_H1}, {(beta * g1_b).neg(), -1}},
+                 Fr::zero()};
+        const Fr b_at_gamma = ev_den[0] * ev_den[1] * ev_den[2];
+        const Fr b_expr = b_at_gamma * (gamma * g2_g + t_b * Fr::from_u64(k).inverse());
+        LC inner{{{eta_a * ev_den[1] * ev_den[2] * vv, A_VAL}, {eta_b * ev_den[0] * ev_den[2] * vv, B_VAL}, {eta_c * ev_den[1] * ev_den[0] * vv, C_VAL},
+                  {b_expr.neg(), -1}, {vanishing(gamma, k).neg(), P_H2}},
+                 Fr::zero()};
+        const std::vector<LC> at_beta = {lc_g1, outer, lc_t, lc_zb};                           // labels in BTreeSet order
+        const std::vector<LC> at_gamma = {denom(0), denom(1), denom(2), lc_g2, inner};
+
+        // ---- marlin_pc check_combinations + KZG10 check per query point -------------------------------------------------------------
+        const std::vector<LC>* groups[2] = {&at_beta, &at_gamma};
+        const Fr points[2] = {beta, gamma};
+        for (int g = 0; g < 2; ++g) {
+            XY comb = XY::inf();
+            Fr comb_v = Fr::zero(), cj = Fr::one();
+            for (const LC& lc : *groups[g]) {
+                Fr value = lc.value;
+                XY c_lc = XY::inf();
+                long bd = -1;
+                int bd_poly = -1;
+                for (const Term& t : lc.terms) {
+                    if (t.poly < 0) {
+                        value = value - t.coeff;
+                        continue;
+                    }
+                    if (bound[t.poly] >= 0) {
+                        if (lc.terms.size() != 1 || !(t.coeff == one)) return 0;
+                        bd = bound[t.poly];
+                        bd_poly = t.poly;
+                    }
+                    c_lc.madd(g1_scale(comm[t.poly], t.coeff));
+                }
+                comb.madd(g1_scale(c_lc.to_affine(), cj));
+                comb_v = comb_v + cj * value;
+                cj = cj * ch;
+                if (bd >= 0) {
+                    // shifted commitment minus value * tau^(D - bound) G, with the next challenge power
+                    XY adj = XY::from_affine(shifted[bd_poly]);
+                    adj.madd(g1_scale(shift_power((uint64_t)bd), value).neg());
+                    comb.madd(g1_scale(adj.to_affine(), cj));
+                    cj = cj * ch;
+                }
+            }
+            comb.madd(g1_scale(G, comb_v).neg());
+            if (has_rv[g]) comb.madd(g1_scale(gamma_G, rv[g]).neg());
+            // C - v G - rv gamma G = (tau - z) W   <=>   e(C - v G - rv gamma G + z W, H) * e(-W, tau H) = 1
+            comb.madd(g1_scale(W[g], points[g]));
+            if (!pairing::pairing_product_is_one(comb.to_affine(), H, W[g].neg(), beta_H)) return 0;
+        }
+        (void)D;
+        *accepted = 1;
+        return 0;
+    } catch (const std::exception& e) {
+        if (err) *err = e.what();
+        return -1;
+    }
+}
+
+void pairing_selftest(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]) {
+    Fr a, b;
+    memcpy(a.v, a32, 32);
+    memcpy(b.v, b32, 32);
+    const Aff p = g1_scale(Aff::generator(), a.to_mont());
+    const G2A q = pairing::g2_mul(G2A::generator(), b.v, 8);
+    const pairing::Fq12 e = pairing::pairing(p, q);
+    for (int i = 0; i < 6; ++i) {
+        Fq c0 = e.c[i].c0.from_mont(), c1 = e.c[i].c1.from_mont();
+        memcpy(out576 + 96 * i, c0.v, 48);
+        memcpy(out576 + 96 * i + 48, c1.v, 48);
+    }
+}
+
+}  // namespace zk

@@ -180,6 +180,22 @@ int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len);
 int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t msg_len, const uint8_t key[16], const uint8_t zk_seed32[32],
                   uint8_t* ct_out, uint8_t* proof_out, size_t* proof_len);
 
+/* ---- S1 seam: verify_encryption ------------------------------------------------------------------------------------
+ * zkaes_pk_verifying_key exports the VerifyingKey half of `synthesize_keys`' result (src/lib.rs:138,173): ark-marlin's
+ * IndexVerifierKey (index info, 12 index commitments) with ark-poly-commit's marlin_pc::VerifierKey (g, gamma_g, h,
+ * beta_h and the shift powers of the two degree bounds) as one self-describing byte string (layout: csrc/verifier.h).
+ * out may be NULL to query the size.
+ * zkaes_verify_encryption stands in for `verify_encryption(verifying_key, proof, ciphertext)` (src/lib.rs:116-136): the
+ * ciphertext becomes 8 public-input bits per byte (src/helpers/mod.rs:84-93), the Marlin verifier replays the
+ * transcript and checks the two KZG openings with a BLS12-377 pairing.  HOST ONLY -- no context, no device (the
+ * reference verifies on the CPU too).  Returns 0 with *accepted = 1 / 0 (Ok(true) / Ok(false)); a key or proof that
+ * cannot be parsed returns ZK_ERR_ARG (Err(..)) and leaves the reason in zkaes_last_error(NULL). */
+int zkaes_pk_verifying_key(const zkaes_pk* pk, uint8_t* out, size_t* len);
+int zkaes_verify_encryption(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* ciphertext, size_t ct_len,
+                            int* accepted);
+/* Test hook: e(a G1, b G2) for canonical 32-byte LE scalars, as 12 x 48 canonical LE bytes (oracle/pairing_ref.py layout). */
+int zkaes_selftest_pairing(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -916,6 +916,24 @@ def index_from_vk_bytes(vk: bytes, num_instance_padded: int) -> Index:
     return idx
 
 
+def verifying_key_bytes(index_vk: bytes, x_padded: int, max_degree: int, h: int, k: int, tau_seed: bytes, gamma_seed: bytes) -> bytes:
+    """The verifying key `verify_encryption` takes, in the product's self-describing layout (csrc/verifier.h): index vk,
+    KZG verifier key (g, gamma_g in G1; h, beta_h = tau h in G2) and the shift powers tau^(D - bound) G of the two degree
+    bounds.  Built independently of the product (oracle G1 arithmetic, big-integer G2 from oracle/pairing_ref.py)."""
+    from . import pairing_ref as pr
+
+    tau, gamma = seed_to_scalar(tau_seed), seed_to_scalar(gamma_seed)
+    g1 = lambda s: g1_to_bytes_uncompressed(orc().g1_mul_gen(CURVE, ints_to_limbs([s % P], 4))[0])
+    g2 = lambda pt: b"".join(c.to_bytes(48, "little") for c in (pt[0][0], pt[0][1], pt[1][0], pt[1][1]))
+    out = b"ZKAESVK1" + struct.pack("<QQQ", x_padded, max_degree, len(index_vk)) + index_vk
+    out += g1(1) + g1(gamma) + g2(pr.G2) + g2(pr.e2mul(pr.G2, tau))
+    bounds = [h - 2, k - 2]
+    out += struct.pack("<Q", len(bounds))
+    for b in bounds:
+        out += struct.pack("<Q", b) + g1(pow(tau, max_degree - b, P))
+    return out
+
+
 class SparseSRS:
     """The handful of SRS elements the verifier touches, derived from the trapdoor (test SRS)."""
 

@@ -37,6 +37,11 @@ def test_key_matches_oracle_golden(pk16, golden):
     assert hashlib.sha256(vk).hexdigest() == golden["vk_sha256"]
 
 
+def test_verifying_key_matches_oracle_golden(pk16, golden):
+    """the VerifyingKey half of synthesize_keys: product bytes == the blob the oracle builds independently"""
+    assert pk16.verifying_key().hex() == golden["verifying_key"]
+
+
 def test_proof_bytes_match_oracle_golden(ctx, pk16, golden):
     ct, proof = ctx.encrypt(pk16, bytes.fromhex(golden["message"]), bytes.fromhex(golden["key"]), bytes.fromhex(golden["zk_seed"]))
     assert ct.hex() == golden["ciphertext"]
@@ -47,10 +52,20 @@ def test_proof_bytes_match_oracle_golden(ctx, pk16, golden):
 
 
 def _verify(pk, ct, proof_bytes):
+    """Both verifiers must agree: the oracle's (trapdoor check in G1) and the product's verify_encryption (pairing check)."""
+    try:
+        product = zk.verify_encryption(pk.verifying_key(), proof_bytes, ct)
+    except zk.ZkAesError:
+        product = None  # unparseable proof
     idx = mo.index_from_vk_bytes(pk.vk_bytes(), pk.info["x"])
     srs = mo.SparseSRS(pk.info["max_degree"], TAU, GAMMA)
     bits = [(b >> i) & 1 for b in ct for i in range(8)]  # src/helpers/mod.rs:84-93
-    return mo.verify(idx, srs, bits, mo.deserialize_proof(proof_bytes))
+    try:
+        oracle = mo.verify(idx, srs, bits, mo.deserialize_proof(proof_bytes))
+    except (ValueError, AssertionError):
+        oracle = None
+    assert product == oracle, (product, oracle)
+    return bool(oracle)
 
 
 @pytest.mark.parametrize("msg_len", [16, 64, 256])
@@ -67,11 +82,7 @@ def test_verifier_accepts_and_rejects(ctx, msg_len):
         assert not _verify(pk, bytes(wrong), proof)
         tampered = bytearray(proof)
         tampered[-60] ^= 1  # inside the last opening proof
-        try:
-            ok = _verify(pk, ct, bytes(tampered))
-        except (ValueError, AssertionError):
-            ok = False
-        assert not ok
+        assert not _verify(pk, ct, bytes(tampered))
     finally:
         pk.close()
 
