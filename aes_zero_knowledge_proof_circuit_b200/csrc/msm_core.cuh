@@ -168,7 +168,7 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
             }
             acc = msm_load_xyzz<C>(buckets + b);
         }
-        const uint32_t e = sorted[pos];
+        const uint32_t e = sorted ? sorted[pos] : pos;  // no index array: the points themselves are in bucket order (pair round output)
         Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
         if (e >> 31) pt.y = pt.y.neg();
         acc.madd(pt);
@@ -180,6 +180,129 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
     else {
         msm_store_xyzz<C>(tail + t, acc);       // began here, continues in the next slice (includes the old bucket value)
         tail_bucket[t] = b;
+    }
+}
+
+// ---- pair round (batched-affine first level of the bucket sums) ---------------------------------------------------------
+// Before the XYZZ accumulation the entries of every bucket are added in PAIRS as affine points: with the inverse of
+// x1 - x0 in hand an affine addition is 3 field products (lambda, lambda^2, y) instead of the 10 of a mixed XYZZ addition,
+// and Montgomery's trick shares one inversion over a whole launch (3 more products per pair): 6 + 10 = 16 products per two
+// entries instead of 20.  The sort places every bucket at an EVEN offset (odd buckets are padded with MSM_NONE), so pair j
+// is simply entries (2j, 2j+1) and its sum lands at slot j of a dense array whose bucket offsets are the sorted offsets / 2.
+//   A  msm_pair_products: thread t walks pairs [tG, tG+G): den_j (x1-x0, or 2y for a doubling, or 1 when nothing is to be
+//      inverted), prefix[j] = product of the earlier den in the group, tprod[t] = product of the whole group
+//   B  msm_pair_invert  : thread u inverts G2 consecutive group products with one Fermat inversion (every lane busy)
+//   C  msm_pair_add     : thread t walks its group backwards: 1/den_j = (running inverse) * prefix[j], then the addition
+static constexpr uint32_t MSM_NONE = 0xffffffffu;
+enum MsmPairKind { MSM_PAIR_COPY0 = 0, MSM_PAIR_COPY1 = 1, MSM_PAIR_ADD = 2, MSM_PAIR_DBL = 3, MSM_PAIR_INF = 4 };
+
+template <class C>
+ZK_HD Affine<C> msm_load_entry(const uint32_t* bases, uint32_t e) {
+    Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
+    if (e >> 31) pt.y = pt.y.neg();
+    return pt;
+}
+// what is to be inverted for the pair (p0, p1); p1 is absent for the padding slot of an odd bucket
+template <class C>
+ZK_HD int msm_pair_den(const Affine<C>& p0, bool has1, const Affine<C>& p1, typename Affine<C>::Fq* den) {
+    using Fq = typename Affine<C>::Fq;
+    *den = Fq::one();
+    if (!has1 || p1.is_inf()) return MSM_PAIR_COPY0;
+    if (p0.is_inf()) return MSM_PAIR_COPY1;
+    Fq dx = p1.x - p0.x;
+    if (!dx.is_zero()) {
+        *den = dx;
+        return MSM_PAIR_ADD;
+    }
+    if (p0.y == p1.y && !p0.y.is_zero()) {
+        *den = p0.y.dbl();
+        return MSM_PAIR_DBL;
+    }
+    return MSM_PAIR_INF;  // P + (-P), or a point of order two doubled
+}
+template <class C>
+ZK_HD void msm_pair_products(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* sorted2, const uint32_t* bases,
+                             typename Affine<C>::Fq* prefix, typename Affine<C>::Fq* tprod) {
+    using Fq = typename Affine<C>::Fq;
+    const uint64_t lo = (uint64_t)t * G;
+    if (lo >= n_pairs) return;
+    const uint32_t hi = n_pairs - lo > G ? (uint32_t)lo + G : n_pairs;
+    Fq run = Fq::one();
+    for (uint32_t j = (uint32_t)lo; j < hi; ++j) {
+        const uint32_t e0 = sorted2[2 * (size_t)j], e1 = sorted2[2 * (size_t)j + 1];
+        const Affine<C> p0 = msm_load_entry<C>(bases, e0);
+        const bool has1 = e1 != MSM_NONE;
+        const Affine<C> p1 = has1 ? msm_load_entry<C>(bases, e1) : Affine<C>::inf();
+        Fq den;
+        msm_pair_den<C>(p0, has1, p1, &den);
+        prefix[j] = run;
+        run = run * den;
+    }
+    tprod[t] = run;
+}
+// in place: vals[i] -> 1 / vals[i] for this thread's G2 values; scratch holds the running prefixes
+template <class Fq>
+ZK_HD void msm_pair_invert(uint32_t u, uint32_t G2, uint32_t count, Fq* vals, Fq* scratch) {
+    const uint64_t lo = (uint64_t)u * G2;
+    if (lo >= count) return;
+    const uint32_t hi = count - lo > G2 ? (uint32_t)lo + G2 : count;
+    Fq run = Fq::one();
+    for (uint32_t i = (uint32_t)lo; i < hi; ++i) {
+        scratch[i] = run;
+        run = run * vals[i];
+    }
+    Fq inv = run.inverse();
+    for (uint32_t i = hi; i-- > (uint32_t)lo;) {
+        const Fq v = vals[i];
+        vals[i] = inv * scratch[i];
+        inv = inv * v;
+    }
+}
+template <class C>
+ZK_HD void msm_pair_add(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* sorted2, const uint32_t* bases,
+                        const typename Affine<C>::Fq* prefix, const typename Affine<C>::Fq* tinv, uint32_t* out /* n_pairs x 24 words */) {
+    using Fq = typename Affine<C>::Fq;
+    const uint64_t lo = (uint64_t)t * G;
+    if (lo >= n_pairs) return;
+    const uint32_t hi = n_pairs - lo > G ? (uint32_t)lo + G : n_pairs;
+    Fq inv = tinv[t];  // 1 / (product of the group's den)
+    for (uint32_t j = hi; j-- > (uint32_t)lo;) {
+        const uint32_t e0 = sorted2[2 * (size_t)j], e1 = sorted2[2 * (size_t)j + 1];
+        const Affine<C> p0 = msm_load_entry<C>(bases, e0);
+        const bool has1 = e1 != MSM_NONE;
+        const Affine<C> p1 = has1 ? msm_load_entry<C>(bases, e1) : Affine<C>::inf();
+        Fq den;
+        const int kind = msm_pair_den<C>(p0, has1, p1, &den);
+        const Fq dinv = inv * prefix[j];  // 1 / den_j
+        inv = inv * den;
+        Affine<C> r;
+        if (kind == MSM_PAIR_ADD || kind == MSM_PAIR_DBL) {
+            Fq lam;
+            if (kind == MSM_PAIR_ADD) {
+                lam = (p1.y - p0.y) * dinv;
+            } else {
+                Fq x2 = p0.x.sqr();
+                lam = (x2.dbl() + x2) * dinv;
+            }
+            r.x = lam.sqr() - p0.x - p1.x;
+            r.y = lam * (p0.x - r.x) - p0.y;
+        } else if (kind == MSM_PAIR_COPY0) {
+            r = p0;
+        } else if (kind == MSM_PAIR_COPY1) {
+            r = p1;
+        } else {
+            r = Affine<C>::inf();
+        }
+        uint32_t w[24];
+        r.x.pack(w);
+        r.y.pack(w + 12);
+#if defined(__CUDA_ARCH__)
+        uint4* o = reinterpret_cast<uint4*>(out + (size_t)j * 24);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+#else
+        for (int k = 0; k < 24; ++k) out[(size_t)j * 24 + k] = w[k];
+#endif
     }
 }
 

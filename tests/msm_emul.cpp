@@ -70,6 +70,78 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
     return p.c;
 }
 
+// The pair-round pipeline (per window: even-aligned sort, pair products / inversion / affine additions, then the slice
+// accumulation over the pair sums), as msm.cu's msm_window_sums_paired sequences it.
+template <class C>
+static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t G, uint32_t G2,
+                       uint32_t* out96) {
+    using FrP = typename C::FrP;
+    using Fq = typename Affine<C>::Fq;
+    MsmPlan p = msm_make_plan(n ? n : 1, FrP::BITS, forced_c);
+    std::vector<XYZZ<C>> buckets(p.nb, XYZZ<C>::inf());
+    for (size_t base = 0; base < n; base += chunk) {
+        size_t m = n - base < chunk ? n - base : chunk;
+        for (int w = 0; w < p.W; ++w) {
+            std::vector<uint32_t> counts(p.nbw + 1, 0), off2(p.nbw + 1), poff(p.nbw + 1);
+            auto digit = [&](size_t i, uint32_t* neg) {
+                uint32_t s[8];
+                memcpy(s, scalars + 8 * (base + i), 32);
+                uint32_t flip = msm_fold_scalar<FrP>(s);
+                return msm_digit_of_window(s, flip, p, w, neg);
+            };
+            for (size_t i = 0; i < m; ++i) {
+                uint32_t neg, d = digit(i, &neg);
+                if (d) counts[d - 1]++;
+            }
+            uint32_t run = 0;
+            for (size_t k = 0; k <= p.nbw; ++k) {
+                off2[k] = run;
+                run += (counts[k] + 1) & ~1u;
+                poff[k] = off2[k] / 2;
+            }
+            const uint32_t n_pairs = off2[p.nbw] / 2;
+            std::vector<uint32_t> sorted2((size_t)2 * n_pairs + 2, MSM_NONE);
+            std::fill(counts.begin(), counts.end(), 0u);
+            for (size_t i = 0; i < m; ++i) {
+                uint32_t neg, d = digit(i, &neg);
+                if (d) sorted2[off2[d - 1] + counts[d - 1]++] = (uint32_t)(base + i) | (neg << 31);
+            }
+            const uint32_t T = (n_pairs + G - 1) / G;
+            std::vector<Fq> prefix(n_pairs + 1), tprod(T + 1), scratch(T + 1);
+            memset((void*)prefix.data(), 0x5a, sizeof(Fq) * prefix.size());
+            std::vector<uint32_t> t1((size_t)24 * (n_pairs + 1), 0x5a5a5a5au);
+            for (uint32_t t = 0; t < T + 1; ++t) msm_pair_products<C>(t, G, n_pairs, sorted2.data(), bases, prefix.data(), tprod.data());
+            for (uint32_t u = 0; u < (T + G2 - 1) / G2 + 1; ++u) msm_pair_invert<Fq>(u, G2, T, tprod.data(), scratch.data());
+            for (uint32_t t = 0; t < T + 1; ++t) msm_pair_add<C>(t, G, n_pairs, sorted2.data(), bases, prefix.data(), tprod.data(), t1.data());
+            size_t slices = ((size_t)n_pairs + L - 1) / L + 1;
+            std::vector<XYZZ<C>> head(slices + 1), tail(slices + 1);
+            std::vector<uint32_t> tail_bucket(slices + 1, 0x12345678u);
+            memset((void*)head.data(), 0x5a, sizeof(XYZZ<C>) * head.size());
+            memset((void*)tail.data(), 0x5a, sizeof(XYZZ<C>) * tail.size());
+            XYZZ<C>* B = buckets.data() + (size_t)w * p.nbw;
+            for (size_t t = 0; t < slices; ++t)
+                msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), p.nbw, nullptr, t1.data(), B, head.data(), tail.data(), tail_bucket.data());
+            for (size_t t = 0; t < slices + 1; ++t)
+                msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), B, head.data(), tail.data(), tail_bucket.data());
+        }
+    }
+    XYZZ<C> total = XYZZ<C>::inf();
+    for (int w = p.W - 1; w >= 0; --w) {
+        for (int k = 0; k < p.c; ++k) total = total.dbl();
+        for (uint32_t sid = 0; sid < (p.nbw + 63) / 64; ++sid) total.add(msm_reduce_segment<C>(buckets.data() + (size_t)w * p.nbw, p.nbw, 64, sid));
+    }
+    Affine<C> r = total.to_affine();
+    memcpy(out96, r.x.v, 48);
+    memcpy(out96 + 12, r.y.v, 48);
+    return p.c;
+}
+extern "C" int msm_emul_paired(int curve, const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t G,
+                               uint32_t G2, uint32_t* out96) {
+    if (curve == 377) return emul_paired<G1_377Params>(bases, scalars, n, forced_c, L, chunk, G, G2, out96);
+    if (curve == 381) return emul_paired<G1_381Params>(bases, scalars, n, forced_c, L, chunk, G, G2, out96);
+    return -1;
+}
+
 extern "C" int msm_emul(int curve, const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t seg,
                         uint32_t* out96) {
     if (curve == 377) return emul<G1_377Params>(bases, scalars, n, forced_c, L, chunk, seg, out96);

@@ -147,6 +147,25 @@ def test_msm_window_sizes(ctx, oracle, window):
         ctx.set_msm_window(0)
 
 
+@pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}])
+def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
+    curve, n = 377, 20000
+    rng = np.random.default_rng(5)
+    bases = oracle.g1_walk(curve, 17, 3, n)
+    sc = rand_fr(rng, curve, n)
+    sc[:64] = sc[64]  # a bucket heavy enough to straddle several accumulation slices
+    exp = oracle.g1_msm(curve, bases, sc)
+    try:
+        for k, v in tuning.items():
+            ctx.set_tuning(k, v)
+        assert (ctx.msm_g1(curve, bases, sc) == exp).all()
+    finally:
+        ctx.set_tuning("msm_acc_blocks", 3)
+        ctx.set_tuning("msm_window_max", 22)
+    with pytest.raises(Exception):
+        ctx.set_tuning("no_such_knob", 1)
+
+
 def test_msm_edge_cases(ctx, oracle):
     curve = 377
     bases = oracle.g1_walk(curve, 3, 2, 16)
