@@ -1,6 +1,7 @@
 // Shared host-side plumbing for libzkaes_b200: context, error reporting, stream-ordered scratch memory.
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -22,6 +23,7 @@ struct zkaes_ctx {
     std::map<uint64_t, void*> tables;
     // tuning knobs (0 = automatic)
     int msm_window_bits = 0;
+    int msm_pair_round = 0;  // 1 = batched-affine pair round before the XYZZ accumulation (msm_core.cuh); off by default: the two extra gather passes cost what the cheaper additions save (profiles/r1_launches_msm_2p26_pair_round.txt)
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
     int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
     // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)
@@ -67,15 +69,28 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
+    // host time spent inside the stream-ordered allocator (ZKAES_TRACE prints it per phase: the pool remaps physical memory
+    // when a large request does not fit a cached block, which is host-synchronous work)
+    static double& alloc_seconds() {
+        static double t = 0;
+        return t;
+    }
     cudaError_t alloc(size_t n, cudaStream_t stream) {
         release();
         s = stream;
         bytes = n;
         if (n == 0) return cudaSuccess;
-        return cudaMallocAsync(&p, n, stream);
+        auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMallocAsync(&p, n, stream);
+        alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return e;
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) {
+            auto t0 = std::chrono::steady_clock::now();
+            cudaFreeAsync(p, s);
+            alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
         p = nullptr;
     }
     ~DevBuf() { release(); }

@@ -46,20 +46,88 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, s
 // DRAM-missing atomics over all W 2^(c-1) counters).
 template <class FrP>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
-                                                    MsmPlan p, uint32_t* __restrict__ counts,
+                                                    MsmPlan p, int w_base, uint32_t* __restrict__ counts,
                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar<FrP>(scalars, i, stride, mont, s);
     const uint32_t flip = msm_fold_scalar<FrP>(s);
-    const int w = blockIdx.y;
+    const int w = w_base + blockIdx.y;
     uint32_t neg;
     const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
     if (!d) return;
-    const uint32_t key = (uint32_t)w * p.nbw + d - 1;
+    const uint32_t key = (uint32_t)blockIdx.y * p.nbw + d - 1;  // counts / offsets start at window w_base
     const uint32_t pos = atomicAdd(&counts[key], 1u);
     if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
+}
+
+// The partly filled top window (253 = 11 x 22 + 11 bits at c = 22) has only 2^11 possible digits: 2^26 global atomics on
+// 2^11 addresses serialise in L2 (9.2 ms per pass against 0.7-2.5 ms for a full window, profiles/
+// r1_launches_msm_2p26_pair_round.txt).  For such a window each block histograms a tile of 16,384 scalars in shared
+// memory and touches every global counter once; positions inside the tile come from shared-memory cursors.
+static constexpr int DIG_TILE_ITERS = 64;  // x 256 threads
+static constexpr uint32_t DIG_SMALL_KEYS = 4096;
+template <class FrP>
+__global__ void __launch_bounds__(256) k_msm_digits_small(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
+                                                          MsmPlan p, int w, uint32_t nkeys, uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+    __shared__ uint32_t hist[DIG_SMALL_KEYS], cursor[DIG_SMALL_KEYS];
+    for (uint32_t k = threadIdx.x; k < nkeys; k += 256) hist[k] = 0;
+    __syncthreads();
+    const size_t tile = (size_t)blockIdx.x * (256 * DIG_TILE_ITERS);
+    for (int it = 0; it < DIG_TILE_ITERS; ++it) {
+        const size_t i = tile + (size_t)it * 256 + threadIdx.x;
+        if (i >= n) break;
+        uint32_t s[8], neg;
+        load_scalar<FrP>(scalars, i, stride, mont, s);
+        const uint32_t flip = msm_fold_scalar<FrP>(s);
+        const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
+        if (d) atomicAdd(&hist[d - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < nkeys; k += 256) {
+        const uint32_t c = hist[k];
+        cursor[k] = c ? atomicAdd(&counts[k], c) : 0u;  // this tile's first position inside bucket k
+    }
+    if (!sorted) return;
+    __syncthreads();
+    for (int it = 0; it < DIG_TILE_ITERS; ++it) {
+        const size_t i = tile + (size_t)it * 256 + threadIdx.x;
+        if (i >= n) break;
+        uint32_t s[8], neg;
+        load_scalar<FrP>(scalars, i, stride, mont, s);
+        const uint32_t flip = msm_fold_scalar<FrP>(s);
+        const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
+        if (!d) continue;
+        const uint32_t pos = atomicAdd(&cursor[d - 1], 1u);
+        sorted[offsets[d - 1] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
+    }
+}
+// number of distinct |digits| the top window can take, or 0 if it is a full window / too large for the shared-memory path
+static uint32_t msm_small_top_keys(const MsmPlan& p, int fr_bits) {
+    const int top_bits = fr_bits - (p.W - 1) * p.c;
+    if (top_bits >= p.c || top_bits < 1 || ((uint32_t)1 << top_bits) > DIG_SMALL_KEYS) return 0;
+    return (uint32_t)1 << top_bits;
+}
+// histogram (sorted == nullptr) or scatter pass over windows [w0, w0 + nw); counts / offsets point at window w0's first bucket
+template <class FrP>
+static void msm_launch_digits(zkaes_ctx* ctx, const uint32_t* sc, size_t m, size_t stride, uint32_t idx_base, int mont, const MsmPlan& p, int w0, int nw,
+                              uint32_t* counts, const uint32_t* offsets, uint32_t* sorted) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t small = msm_small_top_keys(p, FrP::BITS);
+    int n_full = nw;
+    if (small && w0 + nw == p.W) {  // the range ends with the partly filled top window
+        --n_full;
+        const size_t off = (size_t)n_full * p.nbw;
+        k_msm_digits_small<FrP><<<cdiv(m, 256 * DIG_TILE_ITERS), 256, 0, st>>>(sc, m, stride, idx_base, mont, p, p.W - 1, small, counts + off,
+                                                                               offsets ? offsets + off : nullptr, sorted);
+        ctx->launches++;
+    }
+    if (n_full > 0) {
+        k_msm_digits<FrP><<<dim3(cdiv(m, 256), n_full), 256, 0, st>>>(sc, m, stride, idx_base, mont, p, w0, counts, offsets, sorted);
+        ctx->launches++;
+    }
 }
 
 // ---- exclusive scan over <= 2^22 counters: per-block scan, scan of block sums, add-back -----------------
@@ -167,6 +235,29 @@ __global__ void __launch_bounds__(128) k_msm_merge(const uint32_t* __restrict__ 
                                                    const uint32_t* __restrict__ tail_bucket) {
     msm_merge_slice<C>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, buckets, head, tail, tail_bucket);
 }
+// 4 warps per block, one slice per warp; only the slices whose bucket runs on for more than MSM_MERGE_SERIAL_MAX slices do work
+template <class C>
+__global__ void __launch_bounds__(128) k_msm_merge_heavy(const uint32_t* __restrict__ offsets, uint32_t n_slices, uint32_t L, XYZZ<C>* __restrict__ buckets,
+                                                   const XYZZ<C>* __restrict__ head, const XYZZ<C>* __restrict__ tail,
+                                                   const uint32_t* __restrict__ tail_bucket) {
+    __shared__ XYZZ<C> sh[128];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * 4 + warp;
+    XYZZ<C> acc;
+    uint32_t b;
+    if (!msm_merge_lane<C>(t, lane, n_slices, L, offsets, head, tail, tail_bucket, &acc, &b)) return;  // warp-uniform
+    sh[threadIdx.x] = acc;
+    __syncwarp();
+    for (int s = 16; s > 0; s >>= 1) {
+        if ((int)lane < s) {
+            XYZZ<C> x = sh[threadIdx.x];
+            x.add(sh[threadIdx.x + s]);  // most lanes hold infinity: add() returns at once
+            sh[threadIdx.x] = x;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) msm_store_xyzz<C>(buckets + b, sh[threadIdx.x]);
+}
 
 // ---- bucket reduction: S_w = sum_{j<nbw} (j+1) * B[w][j] ---------------------------------------------------
 static constexpr int RED_BS = 128;
@@ -210,10 +301,120 @@ __global__ void __launch_bounds__(32) k_msm_window_final(const XYZZ<C>* __restri
     if (threadIdx.x == 0) out[w] = sh[0];
 }
 
+// ---- pair round (msm_core.cuh): batched-affine first level of the bucket sums -------------------------------------------------
+__global__ void __launch_bounds__(256) k_pad_even(const uint32_t* __restrict__ counts, uint32_t* __restrict__ padded, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) padded[i] = (counts[i] + 1u) & ~1u;
+}
+__global__ void __launch_bounds__(256) k_halve(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] >> 1;
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_pair_products(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, const uint32_t* __restrict__ sorted2,
+                                                       const uint32_t* __restrict__ bases, typename Affine<C>::Fq* __restrict__ prefix,
+                                                       typename Affine<C>::Fq* __restrict__ tprod) {
+    msm_pair_products<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> 1, sorted2, bases, prefix, tprod);
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_pair_invert(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, uint32_t G2,
+                                                     typename Affine<C>::Fq* __restrict__ tprod, typename Affine<C>::Fq* __restrict__ scratch) {
+    const uint32_t n_pairs = off2[nbw] >> 1;
+    msm_pair_invert<typename Affine<C>::Fq>(blockIdx.x * blockDim.x + threadIdx.x, G2, (n_pairs + G - 1) / G, tprod, scratch);
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_pair_add(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, const uint32_t* __restrict__ sorted2,
+                                                  const uint32_t* __restrict__ bases, const typename Affine<C>::Fq* __restrict__ prefix,
+                                                  const typename Affine<C>::Fq* __restrict__ tinv, uint32_t* __restrict__ out) {
+    msm_pair_add<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> 1, sorted2, bases, prefix, tinv, out);
+}
+
+static uint32_t msm_slice_len(uint64_t max_entries);
+
+// One window at a time (the pair sums of a window are 96 B per two entries: 3.3 GB for 2^26 points, so they cannot be
+// kept for all windows at once): even-aligned sort, pair round, slice accumulation of the pair sums into the window's buckets.
+template <class C>
+int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t* scalars, size_t n, int scalars_mont, const MsmPlan& p,
+                          size_t scalar_stride, size_t chunk_max, XYZZ<C>* buckets) {
+    using FrP = typename C::FrP;
+    using Fq = typename Affine<C>::Fq;
+    cudaStream_t st = ctx->stream;
+    constexpr uint32_t G = 64, G2 = 128;
+    const size_t max_entries2 = chunk_max + p.nbw + 2;  // entries after padding odd buckets, rounded up
+    const size_t max_pairs = max_entries2 / 2 + 1;
+    const size_t max_groups = (max_pairs + G - 1) / G + 1;
+    const uint32_t L = msm_slice_len(max_pairs);
+    const size_t max_slices = (max_pairs + L - 1) / L + 1;
+    DevBuf counts, padded, off2, poff, sorted2, prefix, tprod, scratch, sums, head, tail, tail_bucket;
+    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
+    ZK_CUDA(ctx, padded.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
+    ZK_CUDA(ctx, off2.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
+    ZK_CUDA(ctx, poff.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
+    ZK_CUDA(ctx, sorted2.alloc(sizeof(uint32_t) * 2 * max_pairs, st));
+    ZK_CUDA(ctx, prefix.alloc(sizeof(Fq) * max_pairs, st));
+    ZK_CUDA(ctx, tprod.alloc(sizeof(Fq) * max_groups, st));
+    ZK_CUDA(ctx, scratch.alloc(sizeof(Fq) * max_groups, st));
+    ZK_CUDA(ctx, sums.alloc(96 * max_pairs, st));
+    ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<C>) * max_slices, st));
+    ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<C>) * max_slices, st));
+    ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
+    for (size_t base = 0; base < n; base += chunk_max) {
+        const size_t m = n - base < chunk_max ? n - base : chunk_max;
+        const uint32_t* sc = scalars + 8 * base * scalar_stride;
+        const size_t pairs_ub = (m + p.nbw) / 2 + 1;  // upper bound of this chunk's pair count (the kernels read the exact one)
+        const unsigned groups = cdiv(pairs_ub, G);
+        const size_t slices = (pairs_ub + L - 1) / L;
+        for (int w = 0; w < p.W; ++w) {
+            ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
+            msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), nullptr, nullptr);
+            k_pad_even<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(counts.as<uint32_t>(), padded.as<uint32_t>(), p.nbw + 1);
+            ctx->launches++;
+            ZK_TRY(exclusive_scan_u32(ctx, padded.as<uint32_t>(), off2.as<uint32_t>(), p.nbw + 1));
+            k_halve<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(off2.as<uint32_t>(), poff.as<uint32_t>(), p.nbw + 1);
+            ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nbw, st));
+            ZK_CUDA(ctx, cudaMemsetAsync(sorted2.p, 0xff, sizeof(uint32_t) * 2 * pairs_ub, st));  // MSM_NONE in the padding slots
+            msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), off2.as<uint32_t>(),
+                                   sorted2.as<uint32_t>());
+            k_pair_products<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, sorted2.as<uint32_t>(), bases, prefix.as<Fq>(),
+                                                                  tprod.as<Fq>());
+            k_pair_invert<C><<<cdiv(cdiv(groups, G2), 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, G2, tprod.as<Fq>(), scratch.as<Fq>());
+            k_pair_add<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, sorted2.as<uint32_t>(), bases, prefix.as<Fq>(),
+                                                             tprod.as<Fq>(), sums.as<uint32_t>());
+            ctx->launches += 4;
+            XYZZ<C>* B = buckets + (size_t)w * p.nbw;
+            zkaes_ctx::ProfSpan span{};
+            if (ctx->prof) {
+                cudaEventCreate(&span.e0);
+                cudaEventCreate(&span.e1);
+                cudaEventRecord(span.e0, st);
+            }
+            if (ctx->msm_acc_blocks == 4)
+                k_msm_accumulate<C, 4><<<cdiv(slices, 128), 128, 0, st>>>(sums.as<uint32_t>(), nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
+                                                                          head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+            else
+                k_msm_accumulate<C, 3><<<cdiv(slices, 128), 128, 0, st>>>(sums.as<uint32_t>(), nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
+                                                                          head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+            if (ctx->prof) {
+                cudaEventRecord(span.e1, st);
+                span.terms = w == 0 ? m : 0;       // each term is counted once per chunk
+                span.madds = (uint64_t)((m + p.nbw) / 2);  // upper bound: one mixed addition per pair sum (odd buckets padded)
+                ctx->prof_spans.push_back(span);
+            }
+            k_msm_merge<C><<<cdiv(slices, 128), 128, 0, st>>>(poff.as<uint32_t>(), (uint32_t)slices, L, B, head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(),
+                                                              tail_bucket.as<uint32_t>());
+            k_msm_merge_heavy<C><<<cdiv(slices, 4), 128, 0, st>>>(poff.as<uint32_t>(), (uint32_t)slices, L, B, head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(),
+                                                                  tail_bucket.as<uint32_t>());
+            ctx->launches += 3;
+            ZK_CUDA(ctx, cudaGetLastError());
+        }
+    }
+    return ZK_OK;
+}
+
 // slice length of the accumulation: long enough to amortise the per-slice bookkeeping and keep the partial arrays
-// small, short enough for >= ~16 waves of threads on 148 SMs x 384 resident threads
+// small, short enough for >= ~8 waves of threads on 148 SMs x 384 resident threads
 static uint32_t msm_slice_len(uint64_t max_entries) {
-    uint64_t L = max_entries / (148ull * 384 * 16);
+    uint64_t L = max_entries / (148ull * 384 * 8);
     if (L < 32) L = 32;
     if (L > 512) L = 512;
     return (uint32_t)L;
@@ -237,15 +438,20 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     const uint64_t max_entries = (uint64_t)chunk_max * p.W;
     const uint32_t L = msm_slice_len(max_entries);
     const size_t max_slices = (size_t)((max_entries + L - 1) / L);
+    // the pair round (batched-affine first level) pays off once buckets hold several entries; it needs the field inversion,
+    // which only the default (arkworks-limb) form of the curve arithmetic provides
+    const bool paired = ctx->msm_pair_round && std::is_same<CI, C>::value && n >= ((size_t)1 << 16) && n / p.nbw >= 4;
     DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket;
-    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
-    ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
-    ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
-    ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<CI>) * max_slices, st));
-    ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<CI>) * max_slices, st));
-    ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
     ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<CI>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
+    if (!paired) {
+        ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+        ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+        ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
+        ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+        ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+        ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
+    }
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
     DevBuf conv;
     if (!bases_internal && !std::is_same<CI, C>::value) {  // arkworks-form bases, kernels in another form: convert into scratch
@@ -255,19 +461,20 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         bases = conv.as<uint32_t>();
     }
     const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
-    for (size_t base = 0; base < n; base += chunk_max) {
+    if (paired) {
+        if constexpr (std::is_same<CI, C>::value)
+            ZK_TRY(msm_accumulate_paired<C>(ctx, bases, scalars, n, scalars_mont, p, scalar_stride, chunk_max, buckets.as<XYZZ<C>>()));
+    }
+    for (size_t base = 0; !paired && base < n; base += chunk_max) {
         size_t m = n - base < chunk_max ? n - base : chunk_max;
         const uint32_t* sc = scalars + 8 * base * scalar_stride;
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nb + 1), st));
-        k_msm_digits<FrP><<<dim3(cdiv(m, 256), p.W), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
-                                                                   nullptr, nullptr);
-        ctx->launches++;
+        msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, 0, p.W, counts.as<uint32_t>(), nullptr, nullptr);
         // scanning nb + 1 counters (the last one is zero) leaves the total entry count in offsets[nb]
         ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb + 1));
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
-        k_msm_digits<FrP><<<dim3(cdiv(m, 256), p.W), 256, 0, st>>>(sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, counts.as<uint32_t>(),
-                                                                   offsets.as<uint32_t>(), sorted.as<uint32_t>());
-        ctx->launches++;
+        msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, 0, p.W, counts.as<uint32_t>(), offsets.as<uint32_t>(),
+                               sorted.as<uint32_t>());
         const size_t slices = (size_t)(((uint64_t)m * p.W + L - 1) / L);  // upper bound: zero digits produce no entry
         zkaes_ctx::ProfSpan span{};
         if (ctx->prof) {
@@ -292,6 +499,9 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         }
         k_msm_merge<CI><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
                                                            tail.as<XYZZ<CI>>(), tail_bucket.as<uint32_t>());
+        k_msm_merge_heavy<CI><<<cdiv(slices, 4), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
+                                                               tail.as<XYZZ<CI>>(), tail_bucket.as<uint32_t>());
+        ctx->launches++;
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
     }

@@ -306,8 +306,14 @@ ZK_HD void msm_pair_add(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t
     }
 }
 
-// ---- merge: one thread per slice -- the bucket that began in slice t and ran past its end = tail[t] + the heads of the
-// slices it continues into (one thread per BUCKET left 30 of 32 lanes idle: ~1 bucket in 16 is cut at L = 512) -------------
+// ---- merge: the bucket that began in slice t and ran past its end = tail[t] + the heads of the slices it continues into.
+// Usually that is one head, handled by one thread per slice (msm_merge_slice).  A heavy bucket (the partly filled top
+// window: 2^10 buckets share all the entries; or many equal scalars) continues through hundreds of slices: one thread adding
+// them one after the other took 35 ms per MSM, one warp per slice for ALL slices 34 ms (latency-bound at 8 warps per SM;
+// profiles/r1_launches_msm_2p26_pair_round.txt, r1_launches_msm_2p26_warp_merge.txt).  So: chains longer than
+// MSM_MERGE_SERIAL_MAX are left to a second kernel with one warp per slice in which lane l sums the heads t+1+l, t+1+l+32, ...
+// and the 32 lane sums are folded (shared-memory tree in the kernel, a plain loop in the CPU emulation).
+static constexpr uint32_t MSM_MERGE_SERIAL_MAX = 32;
 template <class C>
 ZK_HD void msm_merge_slice(uint32_t t, uint32_t n_slices, uint32_t L, const uint32_t* offsets, XYZZ<C>* buckets, const XYZZ<C>* head,
                            const XYZZ<C>* tail, const uint32_t* tail_bucket) {
@@ -315,9 +321,24 @@ ZK_HD void msm_merge_slice(uint32_t t, uint32_t n_slices, uint32_t L, const uint
     const uint32_t b = tail_bucket[t];
     if (b == MSM_NO_BUCKET) return;
     const uint32_t t1 = (offsets[b + 1] - 1) / L;  // last slice the bucket reaches (> t)
+    if (t1 - t > MSM_MERGE_SERIAL_MAX) return;     // msm_merge_lane's job
     XYZZ<C> acc = msm_load_xyzz<C>(tail + t);
     for (uint32_t u = t + 1; u <= t1; ++u) acc.add(msm_load_xyzz<C>(head + u));
     msm_store_xyzz<C>(buckets + b, acc);
+}
+template <class C>
+ZK_HD bool msm_merge_lane(uint32_t t, uint32_t lane, uint32_t n_slices, uint32_t L, const uint32_t* offsets, const XYZZ<C>* head,
+                          const XYZZ<C>* tail, const uint32_t* tail_bucket, XYZZ<C>* lane_sum, uint32_t* bucket) {
+    if (t >= n_slices) return false;
+    const uint32_t b = tail_bucket[t];
+    if (b == MSM_NO_BUCKET) return false;
+    const uint32_t t1 = (offsets[b + 1] - 1) / L;
+    if (t1 - t <= MSM_MERGE_SERIAL_MAX) return false;
+    *bucket = b;
+    XYZZ<C> acc = lane == 0 ? msm_load_xyzz<C>(tail + t) : XYZZ<C>::inf();
+    for (uint64_t u = (uint64_t)t + 1 + lane; u <= t1; u += 32) acc.add(msm_load_xyzz<C>(head + u));
+    *lane_sum = acc;
+    return true;
 }
 
 // ---- reduce: segment `seg_id` of window w covers buckets [seg_id * seg, ...) ------------------------------------------------

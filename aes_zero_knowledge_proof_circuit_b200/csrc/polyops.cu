@@ -267,6 +267,17 @@ __global__ void k_fma3(F* acc, const F* a, const F* b, const F* c, F s, size_t n
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_fr(acc + i, ld_fr(acc + i) + ld_fr(a + i) * ld_fr(b + i) * ld_fr(c + i) * s);
 }
+// four coset interpolants R_j = sum_b c_b i^(j b) (i = a primitive 4th root of unity) -> c_b = 1/4 sum_j w^(j b) R_j, w = 1/i, in place
+__global__ void k_coset4_combine(F* v, size_t k, F w, F quarter) {
+    size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= k) return;
+    F r0 = ld_fr(v + a), r1 = ld_fr(v + k + a), r2 = ld_fr(v + 2 * k + a), r3 = ld_fr(v + 3 * k + a);
+    F s02 = r0 + r2, d02 = r0 - r2, s13 = r1 + r3, d13 = (r1 - r3) * w;
+    st_fr(v + a, (s02 + s13) * quarter);
+    st_fr(v + k + a, (d02 + d13) * quarter);
+    st_fr(v + 2 * k + a, (s02 - s13) * quarter);
+    st_fr(v + 3 * k + a, (d02 - d13) * quarter);
+}
 // three coset interpolants p_j = c_0 + u_j c_1 + u_j^2 c_2 (block 3 of the quotient is zero) -> c_b = sum_j m[3 b + j] p_j, in place
 struct Mat3 { F m[9]; };
 __global__ void k_coset3_combine(F* v, size_t k, Mat3 M) {
@@ -430,6 +441,10 @@ int po_lincomb_den(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, c
 }
 int po_mul3(zkaes_ctx* ctx, F* out, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_mul3, n, TB, out, a, b, c, s, n); return ZK_OK; }
 int po_fma3(zkaes_ctx* ctx, F* acc, const F* a, const F* b, const F* c, const F& s, size_t n) { LAUNCH(ctx, k_fma3, n, TB, acc, a, b, c, s, n); return ZK_OK; }
+int po_coset4_combine(zkaes_ctx* ctx, F* v, size_t k, const F& i4_inv) {
+    LAUNCH(ctx, k_coset4_combine, k, TB, v, k, i4_inv, F::from_u64(4).inverse());
+    return ZK_OK;
+}
 int po_coset3_combine(zkaes_ctx* ctx, F* v, size_t k, const F u[3]) {
     // inverse Vandermonde through the Lagrange basis on the nodes u_j: l_j(y) = (y - u_a)(y - u_b) / ((u_j - u_a)(u_j - u_b))
     Mat3 M;

@@ -65,6 +65,9 @@ int po_lincomb_den(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const F
 int po_mul3(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
 // acc += s * a * b * c
 int po_fma3(zkaes_ctx* ctx, FrS* acc, const FrS* a, const FrS* b, const FrS* c, const FrS& s, size_t n);
+// v = four k-blocks: block j holds the coefficients of p mod (X^k - i^j) for a polynomial p of degree < 4k, i = i4 a primitive
+// 4th root of unity (i.e. its interpolant on the coset w_4k^j * <w_k>, shift undone); replaces them by p's four coefficient blocks
+int po_coset4_combine(zkaes_ctx* ctx, FrS* v, size_t k, const FrS& i4_inv);
 // v = three |K|-blocks holding the interpolants of a polynomial of degree < 3|K| on the cosets with u_j = s_j^|K|
 // (each with its shift undone); replaces them by the polynomial's three coefficient blocks
 int po_coset3_combine(zkaes_ctx* ctx, FrS* v, size_t k, const FrS u[3]);

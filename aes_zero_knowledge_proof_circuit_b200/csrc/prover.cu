@@ -202,10 +202,23 @@ struct PhaseTrace {
         if (!on) return;
         cudaStreamSynchronize(st);
         auto t1 = std::chrono::steady_clock::now();
+        // device memory: in use overall (includes what the stream-ordered pool keeps cached), and the pool's own peak of live
+        // allocations during this phase (the high-water mark is reset at every phase boundary)
         size_t mfree = 0, mtotal = 0;
-        cudaMemGetInfo(&mfree, &mtotal);  // device memory in use at the phase boundary (the pool keeps what the phase peaked at)
-        fprintf(stderr, "[zkaes] %-28s %9.2f ms   %6.1f GB in use\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                (double)(mtotal - mfree) / 1e9);
+        cudaMemGetInfo(&mfree, &mtotal);
+        uint64_t used_high = 0, reserved = 0, zero = 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used_high);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
+        }
+        fprintf(stderr, "[zkaes] %-28s %9.2f ms (allocator %7.2f ms)   device %6.1f GB in use | pool: phase peak %6.1f GB live, %6.1f GB reserved\n",
+                what, std::chrono::duration<double, std::milli>(t1 - t0).count(), DevBuf::alloc_seconds() * 1e3, (double)(mtotal - mfree) / 1e9,
+                (double)used_high / 1e9, (double)reserved / 1e9);
+        DevBuf::alloc_seconds() = 0;
         t0 = t1;
     }
 };
@@ -446,6 +459,7 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     }
     // the VerifyingKey half of synthesize_keys' result (src/lib.rs:138): index vk + KZG verifier key + the two shift powers
     pk.vk_full = build_verifying_key(pk.vk_bytes, x, pk.D, tau, gamma, {h - 2, k - 2});
+    PhaseTrace(st).mark("synthesize_keys (end)");
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     *out = pkp.release();
     return ZK_OK;
@@ -572,26 +586,44 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));
     ZK_TRY(po_z_poly(ctx, zpoly.as<Fr>(), w_poly.as<Fr>(), len_w, x_poly.as<Fr>(), x));
     tr.mark("r2: r_alpha, t, z polys");
-    // products on the 4|H| domain
+    // rhs = r_alpha (eta_a z_a + eta_b z_b + eta_c z_a z_b) - t z has degree <= 3|H| + 1: the reference multiplies on the 4|H|
+    // domain (five forward NTTs of 4|H| live at once: 43 GB at 4 KiB, the prover's memory peak).  Here the 4|H| domain is walked
+    // as its four cosets s_j H, s_j = w_4H^j: every buffer is |H|-sized, each coset yields rhs mod (X^|H| - i^j), and a 4-point
+    // transform across the cosets returns the four coefficient blocks.  Same polynomial, 19 GB instead of 43 GB.
     const size_t n4 = 4 * h;
     const int log4h = pk.log_h + 2;
-    DevBuf e_ra, e_za, e_zb, e_t, e_z;
-    auto to_evals4 = [&](DevBuf& dst, const Fr* src, size_t len) -> int {
-        ZK_CUDA(ctx, dst.alloc(sizeof(Fr) * n4, st));
-        ZK_CUDA(ctx, cudaMemsetAsync(dst.as<Fr>() + len, 0, sizeof(Fr) * (n4 - len), st));
-        ZK_CUDA(ctx, cudaMemcpyAsync(dst.p, src, sizeof(Fr) * len, cudaMemcpyDeviceToDevice, st));
-        return ntt(ctx, dst.as<Fr>(), log4h, false, false);
-    };
-    ZK_TRY(to_evals4(e_ra, ra.as<Fr>(), h));
-    ZK_TRY(to_evals4(e_za, za.as<Fr>(), h + 1));
-    ZK_TRY(to_evals4(e_zb, zb.as<Fr>(), h + 1));
-    ZK_TRY(to_evals4(e_t, tpoly.as<Fr>(), h));
-    ZK_TRY(to_evals4(e_z, zpoly.as<Fr>(), h + 1));
+    DevBuf e_ra, k_ra, k_za, k_zb, k_t, k_z;
+    ZK_CUDA(ctx, e_ra.alloc(sizeof(Fr) * n4, st));
+    for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) ZK_CUDA(ctx, bfr->alloc(sizeof(Fr) * h, st));
+    {
+        const Fr w4h = domain_gen(log4h);
+        const Fr i4 = fr_pow_u64(w4h, h);  // s_j^|H| = i4^j
+        // dst[a] = p(s w_H^a) for a polynomial of len <= |H| + 1 coefficients: reduce mod X^|H| - s^|H|, shift, transform
+        auto to_coset_h = [&](Fr* dst, const Fr* poly, size_t len, const Fr& s, const Fr& s_h) -> int {
+            const size_t lo = len < h ? len : h;
+            ZK_CUDA(ctx, cudaMemcpyAsync(dst, poly, sizeof(Fr) * lo, cudaMemcpyDeviceToDevice, st));
+            if (lo < h) ZK_CUDA(ctx, cudaMemsetAsync(dst + lo, 0, sizeof(Fr) * (h - lo), st));
+            if (len > h) ZK_TRY(po_axpy(ctx, dst, poly + h, s_h, len - h));  // X^|H| = s^|H| on the coset
+            ZK_TRY(po_scale_powers(ctx, dst, dst, s, h));
+            return ntt(ctx, dst, pk.log_h, false, false);
+        };
+        Fr sj = Fr::one(), sjh = Fr::one();
+        for (int j = 0; j < 4; ++j, sj = sj * w4h, sjh = sjh * i4) {
+            Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
+            ZK_TRY(to_coset_h(k_ra.as<Fr>(), ra.as<Fr>(), h, sj, sjh));
+            ZK_TRY(to_coset_h(k_za.as<Fr>(), za.as<Fr>(), h + 1, sj, sjh));
+            ZK_TRY(to_coset_h(k_zb.as<Fr>(), zb.as<Fr>(), h + 1, sj, sjh));
+            ZK_TRY(to_coset_h(k_t.as<Fr>(), tpoly.as<Fr>(), h, sj, sjh));
+            ZK_TRY(to_coset_h(k_z.as<Fr>(), zpoly.as<Fr>(), h + 1, sj, sjh));
+            ZK_TRY(po_round2(ctx, Rj, k_ra.as<Fr>(), k_za.as<Fr>(), k_zb.as<Fr>(), k_t.as<Fr>(), k_z.as<Fr>(), eta, h));
+            ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
+            ZK_TRY(po_scale_powers(ctx, Rj, Rj, sj.inverse(), h));
+        }
+        ZK_TRY(po_coset4_combine(ctx, e_ra.as<Fr>(), h, i4.inverse()));  // rhs coefficients (degree <= 3|H| + 1)
+    }
+    for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) bfr->release();
     ra.release();
     zpoly.release();
-    ZK_TRY(po_round2(ctx, e_ra.as<Fr>(), e_ra.as<Fr>(), e_za.as<Fr>(), e_zb.as<Fr>(), e_t.as<Fr>(), e_z.as<Fr>(), eta, n4));
-    e_za.release(); e_zb.release(); e_t.release(); e_z.release();
-    ZK_TRY(ntt(ctx, e_ra.as<Fr>(), log4h, true, false));  // rhs coefficients (degree <= 3|H| + 1)
     ZK_TRY(po_vec(ctx, 0, e_ra.as<Fr>(), e_ra.as<Fr>(), mask.as<Fr>(), len_mask));  // q_1 = mask + rhs
     DevBuf h1, xg1;
     ZK_CUDA(ctx, h1.alloc(sizeof(Fr) * (n4 - h), st));

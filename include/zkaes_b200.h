@@ -70,7 +70,9 @@ int zkaes_ctx_profile_read(zkaes_ctx* ctx, double out[4]);
 /* Tuning: force the MSM window width (0 = automatic). */
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
 /* Tuning knobs that never change results: "msm_window_max" (cap of the automatic window choice, 3..24; the bucket array
- * is 2^(c-1) * ceil(253/c) points of 192 B), "msm_acc_blocks" (resident blocks per SM of the bucket accumulation: 3 or 4). */
+ * is 2^(c-1) * ceil(253/c) points of 192 B), "msm_acc_blocks" (resident blocks per SM of the bucket accumulation: 3 or 4),
+ * "msm_pair_round" (1 = add the entries of every bucket in pairs as affine points with a shared inversion before the XYZZ
+ * accumulation, 0 = plain accumulation). */
 int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value);
 
 /* ---- device memory (thin wrappers so non-CUDA hosts can keep inputs resident in HBM) -------------------- */

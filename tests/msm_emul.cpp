@@ -55,8 +55,19 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
         for (size_t t = 0; t < slices; ++t)
             msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), p.nb, sorted.data(), bases, buckets.data(), head.data(), tail.data(),
                                     tail_bucket.data());
-        for (size_t t = 0; t < slices + 1; ++t)  // one thread past the end, as a partly filled last block launches
+        for (size_t t = 0; t < slices + 1; ++t)  // one thread / warp past the end, as a partly filled last block launches
             msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), buckets.data(), head.data(), tail.data(), tail_bucket.data());
+        for (size_t t = 0; t < slices + 1; ++t) {
+            XYZZ<C> sum = XYZZ<C>::inf(), lane_sum;
+            uint32_t b = 0;
+            bool any = false;
+            for (uint32_t lane = 0; lane < 32; ++lane)
+                if (msm_merge_lane<C>((uint32_t)t, lane, (uint32_t)slices, L, offsets.data(), head.data(), tail.data(), tail_bucket.data(), &lane_sum, &b)) {
+                    sum.add(lane_sum);
+                    any = true;
+                }
+            if (any) buckets[b] = sum;
+        }
     }
     XYZZ<C> total = XYZZ<C>::inf();
     for (int w = p.W - 1; w >= 0; --w) {
@@ -123,6 +134,17 @@ static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n,
                 msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), p.nbw, nullptr, t1.data(), B, head.data(), tail.data(), tail_bucket.data());
             for (size_t t = 0; t < slices + 1; ++t)
                 msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), B, head.data(), tail.data(), tail_bucket.data());
+            for (size_t t = 0; t < slices + 1; ++t) {
+                XYZZ<C> sum = XYZZ<C>::inf(), lane_sum;
+                uint32_t b = 0;
+                bool any = false;
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    if (msm_merge_lane<C>((uint32_t)t, lane, (uint32_t)slices, L, poff.data(), head.data(), tail.data(), tail_bucket.data(), &lane_sum, &b)) {
+                        sum.add(lane_sum);
+                        any = true;
+                    }
+                if (any) B[b] = sum;
+            }
         }
     }
     XYZZ<C> total = XYZZ<C>::inf();

@@ -147,13 +147,22 @@ def test_msm_window_sizes(ctx, oracle, window):
         ctx.set_msm_window(0)
 
 
-@pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}])
+@pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
+                                    {"msm_pair_round": 1, "msm_window_max": 10}])
 def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
-    curve, n = 377, 20000
+    """70,000 terms: large enough for the batched-affine pair round (on by default) -- checked against the oracle with the
+    round on and off, with degenerate pairs in the buckets (equal points, opposite points, infinity, repeated scalars)."""
+    curve, n = 377, 70000
     rng = np.random.default_rng(5)
     bases = oracle.g1_walk(curve, 17, 3, n)
     sc = rand_fr(rng, curve, n)
-    sc[:64] = sc[64]  # a bucket heavy enough to straddle several accumulation slices
+    sc[:64] = sc[64]            # a bucket heavy enough to straddle several accumulation slices
+    bases[100:164] = bases[100]  # the same point 64 times with the same scalar: doublings inside pairs
+    sc[100:164] = sc[100]
+    bases[201] = bases[200]      # P and -P in the same buckets: s P + (r - s) P
+    sc[201] = ints_to_limbs([FR[curve] - limbs_to_ints(sc[200:201])[0]], 4)[0]
+    bases[300] = 0               # infinity
+    sc[301] = 0
     exp = oracle.g1_msm(curve, bases, sc)
     try:
         for k, v in tuning.items():
@@ -162,6 +171,7 @@ def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
     finally:
         ctx.set_tuning("msm_acc_blocks", 3)
         ctx.set_tuning("msm_window_max", 22)
+        ctx.set_tuning("msm_pair_round", 0)
     with pytest.raises(Exception):
         ctx.set_tuning("no_such_knob", 1)
 
