@@ -608,7 +608,9 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             return ntt(ctx, dst, pk.log_h, false, false);
         };
         Fr sj = Fr::one(), sjh = Fr::one();
+        // Multi-GPU: like the round-3 cosets below, coset j is evaluated by rank (j mod N) and broadcast (2.1 GB at 4 KiB)
         for (int j = 0; j < 4; ++j, sj = sj * w4h, sjh = sjh * i4) {
+            if (j % ctx->nranks != ctx->rank) continue;
             Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
             ZK_TRY(to_coset_h(k_ra.as<Fr>(), ra.as<Fr>(), h, sj, sjh));
             ZK_TRY(to_coset_h(k_za.as<Fr>(), za.as<Fr>(), h + 1, sj, sjh));
@@ -619,6 +621,8 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
             ZK_TRY(po_scale_powers(ctx, Rj, Rj, sj.inverse(), h));
         }
+        if (ctx->nranks > 1)
+            for (int j = 0; j < 4; ++j) ZK_TRY(comm_broadcast(ctx, e_ra.as<Fr>() + (size_t)j * h, sizeof(Fr) * h, j % ctx->nranks));
         ZK_TRY(po_coset4_combine(ctx, e_ra.as<Fr>(), h, i4.inverse()));  // rhs coefficients (degree <= 3|H| + 1)
     }
     for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) bfr->release();
