@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(F* data, const F* __re
                 y.v[l] = sm[l * tsize + i1];
             }
             F o0, o1;
-            if (e == 0) {
+            // w^0 = 1 needs no product, but only the very first stage has e = 0 for a whole warp: in the stages after it a
+            // per-lane shortcut splits the warp (half, a quarter, ... of the lanes idle through the product the others still
+            // execute; ncu: 26.5 of 32 lanes active, profiles/r1_ncu_full_ntt_pass_2p24.txt), so the test is block-uniform
+            if (s == 1) {
                 o0 = x + y;
                 o1 = x - y;
             } else if (!inverse) {
@@ -164,9 +167,11 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(F* data, const F* __re
                 o0 = x + y;
                 o1 = x - y;
             } else {
-                y = y * load_fr_ro(tw + (half_n - e));  // w^-e = -w^(n/2-e)
-                o0 = x - y;
-                o1 = x + y;
+                // w^-e = -w^(n/2-e) for e > 0; the lanes with e = 0 multiply by w^0 and keep the signs (w^(n/2) is not in the table)
+                y = y * load_fr_ro(tw + (e ? half_n - e : 0));
+                const F a = x + y, b = x - y;
+                o0 = e ? b : a;
+                o1 = e ? a : b;
             }
 #pragma unroll
             for (int l = 0; l < 8; ++l) {

@@ -31,8 +31,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own banner / debug output (printed to stdout by default) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  NCCL prints its banner / debug output to fd 1 from native code (seen on the GPU box:
+# "NCCL version ..." ahead of the JSON), so fd 1 is pointed at stderr for the whole process and the result line is written to
+# a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 CURVE = 377
 FR_BITS = 253
@@ -167,7 +175,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": "constraints/s", "cores": s.cores, "kind": "port", "sample": s.describe()},
         "e2e": {"value": val, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -383,7 +391,7 @@ def main():
             s = CpuSample()
             dt, _ = s.prove()
             line["cpu_baseline"] = {"value": s.n_constraints / dt, "unit": "constraints/s", "cores": s.cores, "kind": "port", "sample": s.describe()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
