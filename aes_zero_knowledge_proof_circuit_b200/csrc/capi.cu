@@ -95,6 +95,7 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     zk::comm_destroy(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <chrono>
+#include <iterator>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -13,6 +14,61 @@
 #define ZK_ERR_CUDA (-2)
 #define ZK_ERR_STATE (-3)
 #define ZK_ERR_UNSUPPORTED (-4)
+
+// Host-managed arena for the prover's large temporaries.  The stream-ordered pool (cudaMallocAsync) reuses cached
+// physical memory by REMAPPING it when a request does not match a cached block; with the prover's mix of multi-GB buffers
+// that is host-synchronous driver work whose amount depends on the pool's fragmentation state: identical runs of the 256-byte
+// proof took 1.28 s or 2.12 s with identical kernel times (profiles/r1_alloc_bimodal_256B.txt).  After the first proof has
+// shown the peak of live scratch, the context carves one cudaMalloc'ed arena of that size (+15 %) and DevBuf serves from it
+// with a best-fit free list on the host -- no driver calls, the same addresses every proof.  Everything runs on the
+// context's single stream, so a freed block may be handed out again at once (stream order = program order), exactly the
+// guarantee cudaFreeAsync gives.  A request that does not fit falls back to the pool.
+struct DevArena {
+    char* base = nullptr;
+    size_t size = 0, live = 0, high = 0;
+    std::map<size_t, size_t> free_segs;  // offset -> length, coalesced
+    static size_t round_up(size_t n) { return (n + 511) & ~(size_t)511; }
+    void reset(char* b, size_t s) {
+        base = b;
+        size = s;
+        live = high = 0;
+        free_segs.clear();
+        if (s) free_segs[0] = s;
+    }
+    void* alloc(size_t n) {
+        n = round_up(n);
+        auto best = free_segs.end();
+        for (auto it = free_segs.begin(); it != free_segs.end(); ++it)
+            if (it->second >= n && (best == free_segs.end() || it->second < best->second)) best = it;
+        if (best == free_segs.end()) return nullptr;
+        const size_t off = best->first, len = best->second;
+        free_segs.erase(best);
+        if (len > n) free_segs[off + n] = len - n;
+        live += n;
+        if (live > high) high = live;
+        return base + off;
+    }
+    bool owns(const void* p) const { return base && (const char*)p >= base && (const char*)p < base + size; }
+    void free(void* p, size_t n) {
+        n = round_up(n);
+        size_t off = (size_t)((char*)p - base);
+        live -= n;
+        auto next = free_segs.lower_bound(off);
+        if (next != free_segs.begin()) {
+            auto prev = std::prev(next);
+            if (prev->first + prev->second == off) {
+                off = prev->first;
+                n += prev->second;
+                free_segs.erase(prev);
+            }
+        }
+        if (next != free_segs.end() && off + n == next->first) {
+            n += next->second;
+            free_segs.erase(next);
+        }
+        free_segs[off] = n;
+    }
+};
 
 struct zkaes_ctx {
     int device = 0;
@@ -37,6 +93,10 @@ struct zkaes_ctx {
         uint64_t terms, madds;
     };
     std::vector<ProfSpan> prof_spans;
+    // scratch arena (see DevArena): created by the second encrypt() on this context from the first one's measured peak
+    DevArena arena;
+    uint64_t scratch_peak = 0;   // pool high-water mark of the last encrypt() that ran without the arena
+    int arena_state = 0;         // 0 = not tried yet, 1 = active, -1 = disabled / allocation failed
 };
 
 namespace zk {
@@ -75,11 +135,19 @@ struct DevBuf {
         static double t = 0;
         return t;
     }
+    // the arena of the (single) context that is currently proving; null = stream-ordered pool only
+    static DevArena*& arena() {
+        static DevArena* a = nullptr;
+        return a;
+    }
     cudaError_t alloc(size_t n, cudaStream_t stream) {
         release();
         s = stream;
         bytes = n;
         if (n == 0) return cudaSuccess;
+        if (DevArena* a = arena()) {
+            if ((p = a->alloc(n)) != nullptr) return cudaSuccess;
+        }
         auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMallocAsync(&p, n, stream);
         alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -87,9 +155,14 @@ struct DevBuf {
     }
     void release() {
         if (p) {
-            auto t0 = std::chrono::steady_clock::now();
-            cudaFreeAsync(p, s);
-            alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            DevArena* a = arena();
+            if (a && a->owns(p)) {
+                a->free(p, bytes);
+            } else {
+                auto t0 = std::chrono::steady_clock::now();
+                cudaFreeAsync(p, s);
+                alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            }
         }
         p = nullptr;
     }

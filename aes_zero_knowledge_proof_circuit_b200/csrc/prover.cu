@@ -223,6 +223,52 @@ struct PhaseTrace {
     }
 };
 
+// Scratch policy of one encrypt() (DevArena, common.cuh): the first call on a context runs on the stream-ordered pool and
+// records its peak of live scratch; the next call returns the pool's cache to the driver, carves an arena of that peak + 15 %
+// and every later call allocates from it.  ZKAES_ARENA=0 keeps the pool.
+struct ScratchScope {
+    zkaes_ctx* ctx;
+    cudaMemPool_t pool = nullptr;
+    bool measuring = false;
+    explicit ScratchScope(zkaes_ctx* c) : ctx(c) {
+        static const bool enabled = !(getenv("ZKAES_ARENA") && getenv("ZKAES_ARENA")[0] == '0');
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) pool = nullptr;
+        if (enabled && ctx->arena_state == 0 && ctx->scratch_peak && pool) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemPoolTrimTo(pool, 0);
+            const size_t want = DevArena::round_up((size_t)(ctx->scratch_peak * 1.15) + ((size_t)256 << 20));
+            void* base = nullptr;
+            if (cudaMalloc(&base, want) == cudaSuccess) {
+                ctx->arena.reset((char*)base, want);
+                ctx->arena_state = 1;
+            } else {
+                cudaGetLastError();
+                ctx->arena_state = -1;
+            }
+        }
+        if (ctx->arena_state == 1) {
+            DevBuf::arena() = &ctx->arena;
+        } else if (pool) {
+            uint64_t zero = 0;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
+            measuring = true;
+        }
+    }
+    ~ScratchScope() {
+        DevBuf::arena() = nullptr;
+        if (getenv("ZKAES_ALLOC_STATS")) {  // no synchronisation: safe to leave on in timed runs
+            fprintf(stderr, "[zkaes] encrypt: %.1f ms of host time in cudaMallocAsync/cudaFreeAsync; arena %s (%.1f GB, peak %.1f GB live)\n",
+                    DevBuf::alloc_seconds() * 1e3, ctx->arena_state == 1 ? "active" : ctx->arena_state == 0 ? "not yet" : "off",
+                    (double)ctx->arena.size / 1e9, (double)ctx->arena.high / 1e9);
+            DevBuf::alloc_seconds() = 0;
+        }
+        if (measuring) {
+            uint64_t high = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) == cudaSuccess && high > ctx->scratch_peak) ctx->scratch_peak = high;
+        }
+    }
+};
+
 template <class T>
 cudaError_t dev_upload(T** dst, const std::vector<T>& src, cudaStream_t st) {
     cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(src.size() * sizeof(T), 16));
@@ -488,6 +534,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const size_t nvar = (size_t)c.num_instance + c.num_witness;
     ChaCha20Rng zk(zk_seed);
     PhaseTrace tr(st);
+    ScratchScope scratch(ctx);
 
     // ---- K1: witness ---------------------------------------------------------------------------------------------------
     DevBuf dmsg, dkey, dz, dct;
