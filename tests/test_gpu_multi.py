@@ -1,4 +1,4 @@
-"""Sharded-MSM prover on two GPUs (skipped on single-GPU boxes): each rank keeps half of the SRS, the library all-gathers
+"""Sharded-MSM prover on 2 / 3 / 4 / 8 GPUs (skipped where the box has fewer): each rank keeps its share of the SRS, the library all-gathers
 the per-rank window sums over NCCL; both ranks must emit the oracle's golden proof bytes."""
 import json
 import os
@@ -43,16 +43,20 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_proof_matches_golden():
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_multi_rank_proof_matches_golden(world):
+    """every rank of a `world`-GPU proof must emit the golden bytes (3 ranks: the SRS share and the coset ownership do not
+    divide evenly; 4: one round-2 coset per rank; 8: more ranks than cosets)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(600)
         assert p.exitcode == 0
-    res = sorted(q.get(timeout=5) for _ in range(2))
-    assert res == [(0, True, True), (1, True, True)]
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert res == [(r, True, True) for r in range(world)]
