@@ -130,7 +130,7 @@ static void msm_launch_digits(zkaes_ctx* ctx, const uint32_t* sc, size_t m, size
     }
 }
 
-// ---- exclusive scan over <= 2^22 counters: per-block scan, scan of block sums, add-back -----------------
+// ---- exclusive scan over <= 2^30 counters: per-block scan, scan of block sums (two levels), add-back -------
 static constexpr int SCAN_BS = 1024;
 __global__ void __launch_bounds__(SCAN_BS) k_scan_blocks(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
                                                          uint32_t* __restrict__ block_sums) {
