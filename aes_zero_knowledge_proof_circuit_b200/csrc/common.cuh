@@ -135,9 +135,9 @@ struct DevBuf {
         static double t = 0;
         return t;
     }
-    // the arena of the (single) context that is currently proving; null = stream-ordered pool only
+    // the arena of the context that is proving on THIS host thread (one context per thread); null = stream-ordered pool only
     static DevArena*& arena() {
-        static DevArena* a = nullptr;
+        static thread_local DevArena* a = nullptr;
         return a;
     }
     cudaError_t alloc(size_t n, cudaStream_t stream) {
