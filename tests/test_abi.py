@@ -82,3 +82,26 @@ def test_host_g1_formulas_match_oracle(oracle, curve):
     out = np.zeros_like(A)
     assert zk.lib().zkaes_selftest_host_g1(curve, 2, A.ctypes.data, A.ctypes.data, out.ctypes.data, n) == 0
     assert (out == np.stack([oracle.g1_add(curve, A[i], A[i]) for i in range(n)])).all()
+
+
+def test_header_is_plain_c_and_verifier_links_from_c(tmp_path):
+    """include/zkaes_b200.h compiles as C99 and a C program verifies the golden proof through the shared library -- the view
+    a cgo / Rust -sys / JNI binding has of the boundary."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "aes_zero_knowledge_proof_circuit_b200")
+    exe = str(tmp_path / "c_abi_verify")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", os.path.join(root, "tests", "c_abi_verify.c"), "-o", exe,
+                           "-L" + libdir, "-lzkaes_b200", "-Wl,-rpath," + libdir])
+    with open(os.path.join(root, "tests", "golden", "marlin_proof_16B.json")) as f:
+        gold = json.load(f)
+    ct = bytes.fromhex(gold["ciphertext"])
+    for name, data in (("vk", bytes.fromhex(gold["verifying_key"])), ("proof", bytes.fromhex(gold["proof"])), ("ct", ct),
+                       ("ct_bad", bytes([ct[0] ^ 1]) + ct[1:])):
+        (tmp_path / name).write_bytes(data)
+    run = lambda c: subprocess.run([exe, str(tmp_path / "vk"), str(tmp_path / "proof"), str(tmp_path / c)], capture_output=True, text=True)
+    ok, bad = run("ct"), run("ct_bad")
+    assert (ok.returncode, ok.stdout.strip()) == (0, "accepted"), ok.stderr
+    assert (bad.returncode, bad.stdout.strip()) == (1, "rejected"), bad.stderr
