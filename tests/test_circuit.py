@@ -22,7 +22,7 @@ def csr_rows(row_ptr, col, coeff):
     return [list(zip(col[row_ptr[r]:row_ptr[r + 1]].tolist(), coeff[row_ptr[r]:row_ptr[r + 1]].tolist())) for r in range(len(row_ptr) - 1)]
 
 
-@pytest.mark.parametrize("n_blocks", [1, 2])
+@pytest.mark.parametrize("n_blocks", [1, 2, 3])  # 3 blocks: 385 instance variables padded to 512 (not a power of two of blocks)
 def test_matrices_match_gadget_model(n_blocks):
     msg = bytes((i * 131 + 7) & 0xFF for i in range(16 * n_blocks))
     padded, inst, wit, _ = model_r1cs(msg)

@@ -68,7 +68,7 @@ def _verify(pk, ct, proof_bytes):
     return bool(oracle)
 
 
-@pytest.mark.parametrize("msg_len", [16, 64, 256])
+@pytest.mark.parametrize("msg_len", [16, 48, 64, 256])  # 48 bytes: three blocks, 385 instance variables padded to 512
 def test_verifier_accepts_and_rejects(ctx, msg_len):
     rng = np.random.default_rng(msg_len)
     msg = rng.integers(0, 256, msg_len, dtype=np.uint8).tobytes()
