@@ -173,6 +173,56 @@ struct Fp {
         for (int i = 0; i < N; ++i) r[i] = t[i];
     }
 
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+    // Host-only CIOS over 64-bit limbs (the same little-endian memory as the 32-bit limbs): ~4x the portable loop.  Used by
+    // everything the host computes -- the MSM Horner fold, hiding commitments, the verifier's pairing (csrc/pairing.h).
+    static inline uint64_t host_inv64() {
+        // -p^-1 mod 2^64 from -p^-1 mod 2^32 by one Newton step: x' = x (2 - p x)
+        const uint64_t p0 = (uint64_t)P::MOD(0) | ((uint64_t)P::MOD(1) << 32);
+        uint64_t x = (uint64_t)(0u - P::INV);  // p^-1 mod 2^32
+        x = x * (2 - p0 * x);                  // mod 2^64
+        return 0 - x;
+    }
+    static inline void mont_mul_host64(uint32_t* r32, const uint32_t* a32, const uint32_t* b32) {
+        constexpr int M = N / 2;
+        static_assert(N % 2 == 0, "64-bit host path needs an even number of 32-bit limbs");
+        uint64_t a[M], b[M], p[M], t[M + 2];
+        for (int i = 0; i < M; ++i) {
+            a[i] = (uint64_t)a32[2 * i] | ((uint64_t)a32[2 * i + 1] << 32);
+            b[i] = (uint64_t)b32[2 * i] | ((uint64_t)b32[2 * i + 1] << 32);
+            p[i] = (uint64_t)P::MOD(2 * i) | ((uint64_t)P::MOD(2 * i + 1) << 32);
+        }
+        static const uint64_t inv = host_inv64();
+        for (int i = 0; i < M + 2; ++i) t[i] = 0;
+        for (int i = 0; i < M; ++i) {
+            unsigned __int128 c = 0;
+            for (int j = 0; j < M; ++j) {
+                c += (unsigned __int128)a[j] * b[i] + t[j];
+                t[j] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[M];
+            t[M] = (uint64_t)c;
+            t[M + 1] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * inv;
+            c = (unsigned __int128)m * p[0] + t[0];
+            c >>= 64;
+            for (int j = 1; j < M; ++j) {
+                c += (unsigned __int128)m * p[j] + t[j];
+                t[j - 1] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[M];
+            t[M - 1] = (uint64_t)c;
+            t[M] = t[M + 1] + (uint64_t)(c >> 64);
+        }
+        for (int i = 0; i < M; ++i) {
+            r32[2 * i] = (uint32_t)t[i];
+            r32[2 * i + 1] = (uint32_t)(t[i] >> 32);
+        }
+    }
+#endif
+
     friend ZK_HD Fp operator*(const Fp& a, const Fp& b) {
         Fp r;
 #if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
@@ -184,6 +234,8 @@ struct Fp {
             mont_mul_raw_8(r.v, a.v, b.v, m, inv, zk_c_zero);
         else
             mont_mul_raw_12(r.v, a.v, b.v, m, inv, zk_c_zero);
+#elif !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && !defined(ZK_FF_PORTABLE)
+        mont_mul_host64(r.v, a.v, b.v);
 #else
         mont_mul_portable(r.v, a.v, b.v);
 #endif
