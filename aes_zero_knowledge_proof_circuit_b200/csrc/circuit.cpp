@@ -82,7 +82,8 @@ struct Builder {
         int ne = 0;
         for (int i = 0; i < k; ++i)
             if (tmp[i].coeff != 0) e[ne++] = {col_of(tmp[i].var), tmp[i].coeff};
-        std::sort(e, e + ne);
+        for (int i = 1; i < ne; ++i)  // at most 8 entries: insertion sort by column (std::sort's 16-element unrolling trips -Warray-bounds)
+            for (int j = i; j > 0 && e[j] < e[j - 1]; --j) std::swap(e[j], e[j - 1]);
         for (int i = 0; i < ne; ++i) {
             if (e[i].second < -128 || e[i].second > 127) throw std::runtime_error("circuit: coefficient out of int8 range");
             m.col.push_back(e[i].first);
