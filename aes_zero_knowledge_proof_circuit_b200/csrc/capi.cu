@@ -158,7 +158,7 @@ int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
         if (value < 3 || value > 24) return fail(ctx, ZK_ERR_ARG, "msm_window_max must be in 3..24");
         ctx->msm_window_max = value;
     } else if (k == "msm_pair_round") {
-        if (value != 0 && value != 1) return fail(ctx, ZK_ERR_ARG, "msm_pair_round must be 0 or 1");
+        if (value < 0 || value > 4) return fail(ctx, ZK_ERR_ARG, "msm_pair_round must be in 0..4");
         ctx->msm_pair_round = value;
     } else if (k == "msm_acc_blocks") {
         if (value != 3 && value != 4) return fail(ctx, ZK_ERR_ARG, "msm_acc_blocks must be 3 or 4");

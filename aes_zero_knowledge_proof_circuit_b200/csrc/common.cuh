@@ -79,7 +79,8 @@ struct zkaes_ctx {
     std::map<uint64_t, void*> tables;
     // tuning knobs (0 = automatic)
     int msm_window_bits = 0;
-    int msm_pair_round = 0;  // 1 = batched-affine pair round before the XYZZ accumulation (msm_core.cuh); off by default: the two extra gather passes cost what the cheaper additions save (profiles/r1_launches_msm_2p26_pair_round.txt)
+    int msm_pair_round = 0;  // R = number of batched-affine pair rounds before the XYZZ accumulation (msm_core.cuh); 0 = plain accumulation.
+                             // Off by default: one round measured break-even (profiles/r1_launches_msm_2p26_pair_round.txt)
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
     int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
     // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)

@@ -301,38 +301,41 @@ __global__ void __launch_bounds__(32) k_msm_window_final(const XYZZ<C>* __restri
     if (threadIdx.x == 0) out[w] = sh[0];
 }
 
-// ---- pair round (msm_core.cuh): batched-affine first level of the bucket sums -------------------------------------------------
-__global__ void __launch_bounds__(256) k_pad_even(const uint32_t* __restrict__ counts, uint32_t* __restrict__ padded, uint32_t n) {
+// ---- pair rounds (msm_core.cuh): batched-affine first levels of the bucket sums ------------------------------------------------
+__global__ void __launch_bounds__(256) k_pad_pow2(const uint32_t* __restrict__ counts, uint32_t* __restrict__ padded, uint32_t n, uint32_t align) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) padded[i] = (counts[i] + 1u) & ~1u;
+    if (i < n) padded[i] = (counts[i] + align - 1) & ~(align - 1);
 }
-__global__ void __launch_bounds__(256) k_halve(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
+__global__ void __launch_bounds__(256) k_shift_right(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, int shift) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i] >> 1;
+    if (i < n) out[i] = in[i] >> shift;
+}
+// `round` = 1, 2, ...: the round's pair count is (padded entry count) >> round, read from off2[nbw] on the device
+template <class C>
+__global__ void __launch_bounds__(128) k_pair_products(const uint32_t* __restrict__ off2, uint32_t nbw, int round, uint32_t G,
+                                                       const uint32_t* __restrict__ idx, const uint32_t* __restrict__ pts,
+                                                       typename Affine<C>::Fq* __restrict__ prefix, typename Affine<C>::Fq* __restrict__ tprod) {
+    msm_pair_products<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> round, idx, pts, prefix, tprod);
 }
 template <class C>
-__global__ void __launch_bounds__(128) k_pair_products(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, const uint32_t* __restrict__ sorted2,
-                                                       const uint32_t* __restrict__ bases, typename Affine<C>::Fq* __restrict__ prefix,
-                                                       typename Affine<C>::Fq* __restrict__ tprod) {
-    msm_pair_products<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> 1, sorted2, bases, prefix, tprod);
-}
-template <class C>
-__global__ void __launch_bounds__(128) k_pair_invert(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, uint32_t G2,
+__global__ void __launch_bounds__(128) k_pair_invert(const uint32_t* __restrict__ off2, uint32_t nbw, int round, uint32_t G, uint32_t G2,
                                                      typename Affine<C>::Fq* __restrict__ tprod, typename Affine<C>::Fq* __restrict__ scratch) {
-    const uint32_t n_pairs = off2[nbw] >> 1;
+    const uint32_t n_pairs = off2[nbw] >> round;
     msm_pair_invert<typename Affine<C>::Fq>(blockIdx.x * blockDim.x + threadIdx.x, G2, (n_pairs + G - 1) / G, tprod, scratch);
 }
 template <class C>
-__global__ void __launch_bounds__(128) k_pair_add(const uint32_t* __restrict__ off2, uint32_t nbw, uint32_t G, const uint32_t* __restrict__ sorted2,
-                                                  const uint32_t* __restrict__ bases, const typename Affine<C>::Fq* __restrict__ prefix,
-                                                  const typename Affine<C>::Fq* __restrict__ tinv, uint32_t* __restrict__ out) {
-    msm_pair_add<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> 1, sorted2, bases, prefix, tinv, out);
+__global__ void __launch_bounds__(128) k_pair_add(const uint32_t* __restrict__ off2, uint32_t nbw, int round, uint32_t G,
+                                                  const uint32_t* __restrict__ idx, const uint32_t* __restrict__ pts,
+                                                  const typename Affine<C>::Fq* __restrict__ prefix, const typename Affine<C>::Fq* __restrict__ tinv,
+                                                  uint32_t* __restrict__ out) {
+    msm_pair_add<C>(blockIdx.x * blockDim.x + threadIdx.x, G, off2[nbw] >> round, idx, pts, prefix, tinv, out);
 }
 
 static uint32_t msm_slice_len(uint64_t max_entries);
 
 // One window at a time (the pair sums of a window are 96 B per two entries: 3.3 GB for 2^26 points, so they cannot be
-// kept for all windows at once): even-aligned sort, pair round, slice accumulation of the pair sums into the window's buckets.
+// kept for all windows at once): 2^R-aligned sort, R pair rounds, slice accumulation of the last round's sums into the
+// window's buckets.
 template <class C>
 int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t* scalars, size_t n, int scalars_mont, const MsmPlan& p,
                           size_t scalar_stride, size_t chunk_max, XYZZ<C>* buckets) {
@@ -340,47 +343,59 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
     using Fq = typename Affine<C>::Fq;
     cudaStream_t st = ctx->stream;
     constexpr uint32_t G = 64, G2 = 128;
-    const size_t max_entries2 = chunk_max + p.nbw + 2;  // entries after padding odd buckets, rounded up
-    const size_t max_pairs = max_entries2 / 2 + 1;
+    const int R = ctx->msm_pair_round;
+    const uint32_t align = 1u << R;
+    // entries after padding every non-empty bucket up to a multiple of 2^R
+    const size_t max_entries2 = ((chunk_max + (size_t)(align - 1) * p.nbw) + align) & ~(size_t)(align - 1);
+    const size_t max_pairs = max_entries2 / 2 + 1;       // round 1; every later round has half of the one before
     const size_t max_groups = (max_pairs + G - 1) / G + 1;
-    const uint32_t L = msm_slice_len(max_pairs);
-    const size_t max_slices = (max_pairs + L - 1) / L + 1;
-    DevBuf counts, padded, off2, poff, sorted2, prefix, tprod, scratch, sums, head, tail, tail_bucket;
+    const size_t max_final = (max_entries2 >> R) + 1;    // sums left for the accumulation
+    const uint32_t L = msm_slice_len(max_final);
+    const size_t max_slices = (max_final + L - 1) / L + 1;
+    DevBuf counts, padded, off2, poff, sorted2, prefix, tprod, scratch, sums[2], head, tail, tail_bucket;
     ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
     ZK_CUDA(ctx, padded.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
     ZK_CUDA(ctx, off2.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
     ZK_CUDA(ctx, poff.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
-    ZK_CUDA(ctx, sorted2.alloc(sizeof(uint32_t) * 2 * max_pairs, st));
+    ZK_CUDA(ctx, sorted2.alloc(sizeof(uint32_t) * max_entries2, st));
     ZK_CUDA(ctx, prefix.alloc(sizeof(Fq) * max_pairs, st));
     ZK_CUDA(ctx, tprod.alloc(sizeof(Fq) * max_groups, st));
     ZK_CUDA(ctx, scratch.alloc(sizeof(Fq) * max_groups, st));
-    ZK_CUDA(ctx, sums.alloc(96 * max_pairs, st));
+    ZK_CUDA(ctx, sums[1].alloc(96 * max_pairs, st));                       // rounds 1, 3, ...
+    if (R > 1) ZK_CUDA(ctx, sums[0].alloc(96 * (max_pairs / 2 + 1), st));  // rounds 2, 4, ...
     ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<C>) * max_slices, st));
     ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<C>) * max_slices, st));
     ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
     for (size_t base = 0; base < n; base += chunk_max) {
         const size_t m = n - base < chunk_max ? n - base : chunk_max;
         const uint32_t* sc = scalars + 8 * base * scalar_stride;
-        const size_t pairs_ub = (m + p.nbw) / 2 + 1;  // upper bound of this chunk's pair count (the kernels read the exact one)
-        const unsigned groups = cdiv(pairs_ub, G);
-        const size_t slices = (pairs_ub + L - 1) / L;
+        // upper bounds of this chunk's counts (the kernels read the exact ones from off2[nbw])
+        const size_t entries_ub = ((m + (size_t)(align - 1) * p.nbw) + align) & ~(size_t)(align - 1);
+        const size_t slices = ((entries_ub >> R) + L) / L;
         for (int w = 0; w < p.W; ++w) {
             ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
             msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), nullptr, nullptr);
-            k_pad_even<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(counts.as<uint32_t>(), padded.as<uint32_t>(), p.nbw + 1);
+            k_pad_pow2<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(counts.as<uint32_t>(), padded.as<uint32_t>(), p.nbw + 1, align);
             ctx->launches++;
             ZK_TRY(exclusive_scan_u32(ctx, padded.as<uint32_t>(), off2.as<uint32_t>(), p.nbw + 1));
-            k_halve<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(off2.as<uint32_t>(), poff.as<uint32_t>(), p.nbw + 1);
+            k_shift_right<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(off2.as<uint32_t>(), poff.as<uint32_t>(), p.nbw + 1, R);
             ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nbw, st));
-            ZK_CUDA(ctx, cudaMemsetAsync(sorted2.p, 0xff, sizeof(uint32_t) * 2 * pairs_ub, st));  // MSM_NONE in the padding slots
+            ZK_CUDA(ctx, cudaMemsetAsync(sorted2.p, 0xff, sizeof(uint32_t) * entries_ub, st));  // MSM_NONE in the padding slots
             msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), off2.as<uint32_t>(),
                                    sorted2.as<uint32_t>());
-            k_pair_products<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, sorted2.as<uint32_t>(), bases, prefix.as<Fq>(),
-                                                                  tprod.as<Fq>());
-            k_pair_invert<C><<<cdiv(cdiv(groups, G2), 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, G2, tprod.as<Fq>(), scratch.as<Fq>());
-            k_pair_add<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, G, sorted2.as<uint32_t>(), bases, prefix.as<Fq>(),
-                                                             tprod.as<Fq>(), sums.as<uint32_t>());
-            ctx->launches += 4;
+            ctx->launches++;
+            const uint32_t* idx = sorted2.as<uint32_t>();
+            const uint32_t* pts = bases;
+            for (int r = 1; r <= R; ++r) {
+                const unsigned groups = cdiv((entries_ub >> r) + 1, G);
+                uint32_t* out = sums[r & 1].as<uint32_t>();
+                k_pair_products<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, r, G, idx, pts, prefix.as<Fq>(), tprod.as<Fq>());
+                k_pair_invert<C><<<cdiv(cdiv(groups, G2), 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, r, G, G2, tprod.as<Fq>(), scratch.as<Fq>());
+                k_pair_add<C><<<cdiv(groups, 128), 128, 0, st>>>(off2.as<uint32_t>(), p.nbw, r, G, idx, pts, prefix.as<Fq>(), tprod.as<Fq>(), out);
+                ctx->launches += 3;
+                idx = nullptr;
+                pts = out;
+            }
             XYZZ<C>* B = buckets + (size_t)w * p.nbw;
             zkaes_ctx::ProfSpan span{};
             if (ctx->prof) {
@@ -389,15 +404,15 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
                 cudaEventRecord(span.e0, st);
             }
             if (ctx->msm_acc_blocks == 4)
-                k_msm_accumulate<C, 4><<<cdiv(slices, 128), 128, 0, st>>>(sums.as<uint32_t>(), nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
+                k_msm_accumulate<C, 4><<<cdiv(slices, 128), 128, 0, st>>>(pts, nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
                                                                           head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
             else
-                k_msm_accumulate<C, 3><<<cdiv(slices, 128), 128, 0, st>>>(sums.as<uint32_t>(), nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
+                k_msm_accumulate<C, 3><<<cdiv(slices, 128), 128, 0, st>>>(pts, nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
                                                                           head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
             if (ctx->prof) {
                 cudaEventRecord(span.e1, st);
-                span.terms = w == 0 ? m : 0;       // each term is counted once per chunk
-                span.madds = (uint64_t)((m + p.nbw) / 2);  // upper bound: one mixed addition per pair sum (odd buckets padded)
+                span.terms = w == 0 ? m : 0;               // each term is counted once per chunk
+                span.madds = (uint64_t)(entries_ub >> R);  // upper bound: one mixed addition per remaining sum
                 ctx->prof_spans.push_back(span);
             }
             k_msm_merge<C><<<cdiv(slices, 128), 128, 0, st>>>(poff.as<uint32_t>(), (uint32_t)slices, L, B, head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(),
@@ -440,7 +455,7 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     const size_t max_slices = (size_t)((max_entries + L - 1) / L);
     // the pair round (batched-affine first level) pays off once buckets hold several entries; it needs the field inversion,
     // which only the default (arkworks-limb) form of the curve arithmetic provides
-    const bool paired = ctx->msm_pair_round && std::is_same<CI, C>::value && n >= ((size_t)1 << 16) && n / p.nbw >= 4;
+    const bool paired = ctx->msm_pair_round > 0 && std::is_same<CI, C>::value && n >= ((size_t)1 << 16) && (n / p.nbw) >> ctx->msm_pair_round >= 2;
     DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket;
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
     ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<CI>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity

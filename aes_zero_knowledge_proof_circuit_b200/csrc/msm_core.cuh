@@ -183,14 +183,17 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
     }
 }
 
-// ---- pair round (batched-affine first level of the bucket sums) ---------------------------------------------------------
-// Before the XYZZ accumulation the entries of every bucket are added in PAIRS as affine points: with the inverse of
-// x1 - x0 in hand an affine addition is 3 field products (lambda, lambda^2, y) instead of the 10 of a mixed XYZZ addition,
-// and Montgomery's trick shares one inversion over a whole launch (3 more products per pair): 6 + 10 = 16 products per two
-// entries instead of 20.  The sort places every bucket at an EVEN offset (odd buckets are padded with MSM_NONE), so pair j
-// is simply entries (2j, 2j+1) and its sum lands at slot j of a dense array whose bucket offsets are the sorted offsets / 2.
+// ---- pair rounds (batched-affine first levels of the bucket sums) -----------------------------------------------------------
+// Before the XYZZ accumulation the entries of every bucket are added in PAIRS as affine points, R times over: with the
+// inverse of x1 - x0 in hand an affine addition is 3 field products (lambda, lambda^2, y) instead of the 10 of a mixed XYZZ
+// addition, and Montgomery's trick shares one inversion over a whole launch (3 more products per pair).  The sort places
+// every bucket at an offset that is a multiple of 2^R (buckets are padded with MSM_NONE), so in every round pair j is
+// simply entries (2j, 2j+1), its sum lands at slot j of a dense array, and after R rounds the bucket offsets are the sorted
+// offsets >> R.  Round 1 gathers SRS points through the sorted indices (sign in bit 31); later rounds read the previous
+// round's sums, which are contiguous.  Per round:
 //   A  msm_pair_products: thread t walks pairs [tG, tG+G): den_j (x1-x0, or 2y for a doubling, or 1 when nothing is to be
-//      inverted), prefix[j] = product of the earlier den in the group, tprod[t] = product of the whole group
+//      inverted), prefix[j] = product of the earlier den in the group, tprod[t] = product of the whole group.  In round 1
+//      only the x coordinates are gathered (48 of the 96 bytes) unless the pair is degenerate.
 //   B  msm_pair_invert  : thread u inverts G2 consecutive group products with one Fermat inversion (every lane busy)
 //   C  msm_pair_add     : thread t walks its group backwards: 1/den_j = (running inverse) * prefix[j], then the addition
 static constexpr uint32_t MSM_NONE = 0xffffffffu;
@@ -201,6 +204,22 @@ ZK_HD Affine<C> msm_load_entry(const uint32_t* bases, uint32_t e) {
     Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
     if (e >> 31) pt.y = pt.y.neg();
     return pt;
+}
+template <class C>
+ZK_HD typename Affine<C>::Fq msm_load_x(const uint32_t* bases, uint32_t idx) {
+    using Fq = typename Affine<C>::Fq;
+    uint32_t w[12];
+#if defined(__CUDA_ARCH__)
+    const uint4* p = reinterpret_cast<const uint4*>(bases + (size_t)idx * 24);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint4 v = __ldg(p + k);
+        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+#else
+    for (int k = 0; k < 12; ++k) w[k] = bases[(size_t)idx * 24 + k];
+#endif
+    return Fq::unpack(w);
 }
 // what is to be inverted for the pair (p0, p1); p1 is absent for the padding slot of an odd bucket
 template <class C>
@@ -220,8 +239,41 @@ ZK_HD int msm_pair_den(const Affine<C>& p0, bool has1, const Affine<C>& p1, type
     }
     return MSM_PAIR_INF;  // P + (-P), or a point of order two doubled
 }
+// the two operands of pair j: through the sorted indices (round 1) or straight from the previous round's sums (idx == nullptr)
 template <class C>
-ZK_HD void msm_pair_products(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* sorted2, const uint32_t* bases,
+ZK_HD void msm_pair_operands(const uint32_t* idx, const uint32_t* pts, uint32_t j, Affine<C>* p0, Affine<C>* p1, bool* has1) {
+    if (idx) {
+        const uint32_t e0 = idx[2 * (size_t)j], e1 = idx[2 * (size_t)j + 1];
+        *p0 = e0 != MSM_NONE ? msm_load_entry<C>(pts, e0) : Affine<C>::inf();  // (NONE, NONE): padding up to the 2^R alignment
+        *has1 = e1 != MSM_NONE;
+        *p1 = *has1 ? msm_load_entry<C>(pts, e1) : Affine<C>::inf();
+    } else {
+        *p0 = msm_load_affine<C>(pts, 2 * j);
+        *p1 = msm_load_affine<C>(pts, 2 * j + 1);
+        *has1 = true;
+    }
+}
+// den_j for pass A.  Round 1 reads x coordinates only: a non-zero difference of two non-zero x is an ordinary addition (the
+// point at infinity is stored as (0, 0)); anything else is classified on the full points, exactly as pass C will.
+template <class C>
+ZK_HD typename Affine<C>::Fq msm_pair_den_lazy(const uint32_t* idx, const uint32_t* pts, uint32_t j) {
+    using Fq = typename Affine<C>::Fq;
+    if (idx) {
+        const uint32_t e0 = idx[2 * (size_t)j], e1 = idx[2 * (size_t)j + 1];
+        if (e1 == MSM_NONE) return Fq::one();
+        const Fq x0 = msm_load_x<C>(pts, e0 & 0x7fffffffu), x1 = msm_load_x<C>(pts, e1 & 0x7fffffffu);
+        const Fq dx = x1 - x0;
+        if (!dx.is_zero() && !x0.is_zero() && !x1.is_zero()) return dx;
+    }
+    Affine<C> p0, p1;
+    bool has1;
+    msm_pair_operands<C>(idx, pts, j, &p0, &p1, &has1);
+    Fq den;
+    msm_pair_den<C>(p0, has1, p1, &den);
+    return den;
+}
+template <class C>
+ZK_HD void msm_pair_products(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* idx, const uint32_t* pts,
                              typename Affine<C>::Fq* prefix, typename Affine<C>::Fq* tprod) {
     using Fq = typename Affine<C>::Fq;
     const uint64_t lo = (uint64_t)t * G;
@@ -229,12 +281,7 @@ ZK_HD void msm_pair_products(uint32_t t, uint32_t G, uint32_t n_pairs, const uin
     const uint32_t hi = n_pairs - lo > G ? (uint32_t)lo + G : n_pairs;
     Fq run = Fq::one();
     for (uint32_t j = (uint32_t)lo; j < hi; ++j) {
-        const uint32_t e0 = sorted2[2 * (size_t)j], e1 = sorted2[2 * (size_t)j + 1];
-        const Affine<C> p0 = msm_load_entry<C>(bases, e0);
-        const bool has1 = e1 != MSM_NONE;
-        const Affine<C> p1 = has1 ? msm_load_entry<C>(bases, e1) : Affine<C>::inf();
-        Fq den;
-        msm_pair_den<C>(p0, has1, p1, &den);
+        const Fq den = msm_pair_den_lazy<C>(idx, pts, j);
         prefix[j] = run;
         run = run * den;
     }
@@ -259,7 +306,7 @@ ZK_HD void msm_pair_invert(uint32_t u, uint32_t G2, uint32_t count, Fq* vals, Fq
     }
 }
 template <class C>
-ZK_HD void msm_pair_add(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* sorted2, const uint32_t* bases,
+ZK_HD void msm_pair_add(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t* idx, const uint32_t* pts,
                         const typename Affine<C>::Fq* prefix, const typename Affine<C>::Fq* tinv, uint32_t* out /* n_pairs x 24 words */) {
     using Fq = typename Affine<C>::Fq;
     const uint64_t lo = (uint64_t)t * G;
@@ -267,10 +314,9 @@ ZK_HD void msm_pair_add(uint32_t t, uint32_t G, uint32_t n_pairs, const uint32_t
     const uint32_t hi = n_pairs - lo > G ? (uint32_t)lo + G : n_pairs;
     Fq inv = tinv[t];  // 1 / (product of the group's den)
     for (uint32_t j = hi; j-- > (uint32_t)lo;) {
-        const uint32_t e0 = sorted2[2 * (size_t)j], e1 = sorted2[2 * (size_t)j + 1];
-        const Affine<C> p0 = msm_load_entry<C>(bases, e0);
-        const bool has1 = e1 != MSM_NONE;
-        const Affine<C> p1 = has1 ? msm_load_entry<C>(bases, e1) : Affine<C>::inf();
+        Affine<C> p0, p1;
+        bool has1;
+        msm_pair_operands<C>(idx, pts, j, &p0, &p1, &has1);
         Fq den;
         const int kind = msm_pair_den<C>(p0, has1, p1, &den);
         const Fq dinv = inv * prefix[j];  // 1 / den_j

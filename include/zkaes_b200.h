@@ -71,8 +71,8 @@ int zkaes_ctx_profile_read(zkaes_ctx* ctx, double out[4]);
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
 /* Tuning knobs that never change results: "msm_window_max" (cap of the automatic window choice, 3..24; the bucket array
  * is 2^(c-1) * ceil(253/c) points of 192 B), "msm_acc_blocks" (resident blocks per SM of the bucket accumulation: 3 or 4),
- * "msm_pair_round" (1 = add the entries of every bucket in pairs as affine points with a shared inversion before the XYZZ
- * accumulation, 0 = plain accumulation). */
+ * "msm_pair_round" (R = 0..4: add the entries of every bucket in pairs as affine points with a shared inversion, R times
+ * over, before the XYZZ accumulation; 0 = plain accumulation). */
 int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value);
 
 /* ---- device memory (thin wrappers so non-CUDA hosts can keep inputs resident in HBM) -------------------- */
@@ -85,7 +85,9 @@ int zkaes_dev_download(zkaes_ctx* ctx, void* host, const void* dev, size_t bytes
  * Stands in for ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul(&[G1Affine], &[BigInteger256]) -> G1Projective`
  * (reference Cargo.lock:118-120, reached from src/lib.rs:111).  Result is returned in affine form.
  */
-/* host buffers in, 96-byte affine result out (host) */
+/* host buffers in, 96-byte affine result out (host).
+ * Bases must lie in the prime-order subgroup G1 (as every arkworks G1Affine does) and scalars must be canonical (< r):
+ * the kernels fold s to min(s, r - s) with the point negated, which presupposes r P = O. */
 int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases_host, const void* scalars_host, size_t n, void* out_affine96);
 /* device-resident inputs.  flags: bit 0 (ZKAES_MSM_SCALARS_MONTGOMERY) = the scalars are Fr elements in Montgomery form
  * (as the prover's coefficient vectors are) and are converted on the fly; bit 1 (ZKAES_MSM_BASES_PREPARED) = the bases

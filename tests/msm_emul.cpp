@@ -81,15 +81,16 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
     return p.c;
 }
 
-// The pair-round pipeline (per window: even-aligned sort, pair products / inversion / affine additions, then the slice
-// accumulation over the pair sums), as msm.cu's msm_window_sums_paired sequences it.
+// The pair-round pipeline (per window: 2^R-aligned sort, R rounds of pair products / inversion / affine additions, then the
+// slice accumulation over the pair sums), as msm.cu's msm_accumulate_paired sequences it.
 template <class C>
 static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t G, uint32_t G2,
-                       uint32_t* out96) {
+                       int R, uint32_t* out96) {
     using FrP = typename C::FrP;
     using Fq = typename Affine<C>::Fq;
     MsmPlan p = msm_make_plan(n ? n : 1, FrP::BITS, forced_c);
     std::vector<XYZZ<C>> buckets(p.nb, XYZZ<C>::inf());
+    const uint32_t align = 1u << R;
     for (size_t base = 0; base < n; base += chunk) {
         size_t m = n - base < chunk ? n - base : chunk;
         for (int w = 0; w < p.W; ++w) {
@@ -107,23 +108,33 @@ static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n,
             uint32_t run = 0;
             for (size_t k = 0; k <= p.nbw; ++k) {
                 off2[k] = run;
-                run += (counts[k] + 1) & ~1u;
-                poff[k] = off2[k] / 2;
+                run += (counts[k] + align - 1) & ~(align - 1);
+                poff[k] = off2[k] >> R;
             }
-            const uint32_t n_pairs = off2[p.nbw] / 2;
-            std::vector<uint32_t> sorted2((size_t)2 * n_pairs + 2, MSM_NONE);
+            const uint32_t n_entries = off2[p.nbw];
+            std::vector<uint32_t> sorted2((size_t)n_entries + 2, MSM_NONE);
             std::fill(counts.begin(), counts.end(), 0u);
             for (size_t i = 0; i < m; ++i) {
                 uint32_t neg, d = digit(i, &neg);
                 if (d) sorted2[off2[d - 1] + counts[d - 1]++] = (uint32_t)(base + i) | (neg << 31);
             }
-            const uint32_t T = (n_pairs + G - 1) / G;
-            std::vector<Fq> prefix(n_pairs + 1), tprod(T + 1), scratch(T + 1);
-            memset((void*)prefix.data(), 0x5a, sizeof(Fq) * prefix.size());
-            std::vector<uint32_t> t1((size_t)24 * (n_pairs + 1), 0x5a5a5a5au);
-            for (uint32_t t = 0; t < T + 1; ++t) msm_pair_products<C>(t, G, n_pairs, sorted2.data(), bases, prefix.data(), tprod.data());
-            for (uint32_t u = 0; u < (T + G2 - 1) / G2 + 1; ++u) msm_pair_invert<Fq>(u, G2, T, tprod.data(), scratch.data());
-            for (uint32_t t = 0; t < T + 1; ++t) msm_pair_add<C>(t, G, n_pairs, sorted2.data(), bases, prefix.data(), tprod.data(), t1.data());
+            std::vector<uint32_t> sums[2];
+            const uint32_t* pts = bases;
+            const uint32_t* idx = sorted2.data();
+            uint32_t n_pairs = n_entries;
+            for (int r = 1; r <= R; ++r) {
+                n_pairs >>= 1;
+                const uint32_t T = (n_pairs + G - 1) / G;
+                std::vector<Fq> prefix(n_pairs + 1), tprod(T + 1), scratch(T + 1);
+                memset((void*)prefix.data(), 0x5a, sizeof(Fq) * prefix.size());
+                std::vector<uint32_t>& out = sums[r & 1];
+                out.assign((size_t)24 * (n_pairs + 1), 0x5a5a5a5au);
+                for (uint32_t t = 0; t < T + 1; ++t) msm_pair_products<C>(t, G, n_pairs, idx, pts, prefix.data(), tprod.data());
+                for (uint32_t u = 0; u < (T + G2 - 1) / G2 + 1; ++u) msm_pair_invert<Fq>(u, G2, T, tprod.data(), scratch.data());
+                for (uint32_t t = 0; t < T + 1; ++t) msm_pair_add<C>(t, G, n_pairs, idx, pts, prefix.data(), tprod.data(), out.data());
+                pts = out.data();
+                idx = nullptr;
+            }
             size_t slices = ((size_t)n_pairs + L - 1) / L + 1;
             std::vector<XYZZ<C>> head(slices + 1), tail(slices + 1);
             std::vector<uint32_t> tail_bucket(slices + 1, 0x12345678u);
@@ -131,7 +142,7 @@ static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n,
             memset((void*)tail.data(), 0x5a, sizeof(XYZZ<C>) * tail.size());
             XYZZ<C>* B = buckets.data() + (size_t)w * p.nbw;
             for (size_t t = 0; t < slices; ++t)
-                msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), p.nbw, nullptr, t1.data(), B, head.data(), tail.data(), tail_bucket.data());
+                msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), p.nbw, nullptr, pts, B, head.data(), tail.data(), tail_bucket.data());
             for (size_t t = 0; t < slices + 1; ++t)
                 msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, poff.data(), B, head.data(), tail.data(), tail_bucket.data());
             for (size_t t = 0; t < slices + 1; ++t) {
@@ -158,9 +169,9 @@ static int emul_paired(const uint32_t* bases, const uint32_t* scalars, size_t n,
     return p.c;
 }
 extern "C" int msm_emul_paired(int curve, const uint32_t* bases, const uint32_t* scalars, size_t n, int forced_c, uint32_t L, size_t chunk, uint32_t G,
-                               uint32_t G2, uint32_t* out96) {
-    if (curve == 377) return emul_paired<G1_377Params>(bases, scalars, n, forced_c, L, chunk, G, G2, out96);
-    if (curve == 381) return emul_paired<G1_381Params>(bases, scalars, n, forced_c, L, chunk, G, G2, out96);
+                               uint32_t G2, int R, uint32_t* out96) {
+    if (curve == 377) return emul_paired<G1_377Params>(bases, scalars, n, forced_c, L, chunk, G, G2, R, out96);
+    if (curve == 381) return emul_paired<G1_381Params>(bases, scalars, n, forced_c, L, chunk, G, G2, R, out96);
     return -1;
 }
 

@@ -148,7 +148,8 @@ def test_msm_window_sizes(ctx, oracle, window):
 
 
 @pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
-                                    {"msm_pair_round": 1, "msm_window_max": 10}])
+                                    {"msm_pair_round": 1, "msm_window_max": 10}, {"msm_pair_round": 2, "msm_window_max": 10},
+                                    {"msm_pair_round": 3, "msm_window_max": 9}])
 def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
     """70,000 terms: large enough for the batched-affine pair round (on by default) -- checked against the oracle with the
     round on and off, with degenerate pairs in the buckets (equal points, opposite points, infinity, repeated scalars)."""

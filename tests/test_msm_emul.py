@@ -36,13 +36,13 @@ def emul():
 
     lib.msm_emul_paired.restype = ctypes.c_int
     lib.msm_emul_paired.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t,
-                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
+                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
 
-    def run_paired(curve, bases, scalars, c=0, L=32, chunk=1 << 27, G=64, G2=128):
+    def run_paired(curve, bases, scalars, c=0, L=32, chunk=1 << 27, G=64, G2=128, R=1):
         bases = np.ascontiguousarray(bases, dtype=np.uint64)
         scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
         out = np.zeros(12, dtype=np.uint64)
-        rc = lib.msm_emul_paired(curve, bases.ctypes.data, scalars.ctypes.data, len(scalars), c, L, chunk, G, G2, out.ctypes.data)
+        rc = lib.msm_emul_paired(curve, bases.ctypes.data, scalars.ctypes.data, len(scalars), c, L, chunk, G, G2, R, out.ctypes.data)
         assert rc > 0
         return out
 
@@ -80,24 +80,30 @@ def test_emulated_pipeline_matches_oracle(emul, oracle, curve, c, L, chunk, seg)
 
 
 @pytest.mark.parametrize("curve", [377, 381])
+@pytest.mark.parametrize("R", [1, 2, 3])
 @pytest.mark.parametrize("c,L,chunk,G,G2", [(4, 3, 1000, 1, 1), (4, 5, 37, 3, 2), (5, 7, 64, 64, 128), (3, 64, 1000, 7, 3), (9, 5, 200, 16, 4), (2, 4, 16, 2, 5)])
-def test_emulated_pair_round_matches_oracle(emul, oracle, curve, c, L, chunk, G, G2):
+def test_emulated_pair_round_matches_oracle(emul, oracle, curve, c, L, chunk, G, G2, R):
     """batched-affine pair round: equal points with equal scalars (doubling inside a pair), P + (-P), infinity, odd buckets"""
     n = 150
     bases, sc = _inputs(oracle, curve, n, c * 100 + L)
     bases[20] = bases[21]
     sc[21] = ints_to_limbs([FR[curve] - limbs_to_ints(sc[20:21])[0]], 4)[0]   # s P + (r - s) P: opposite points meet in every bucket
     exp = oracle.g1_msm(curve, bases, sc).reshape(-1)
-    assert (emul.paired(curve, bases, sc, c=c, L=L, chunk=chunk, G=G, G2=G2) == exp).all()
+    bases[30] = 0                                 # the point at infinity as a pair operand
+    exp = oracle.g1_msm(curve, bases, sc).reshape(-1)
+    assert (emul.paired(curve, bases, sc, c=c, L=L, chunk=chunk, G=G, G2=G2, R=R) == exp).all()
 
 
 def test_emulated_pair_round_degenerate_inputs(emul, oracle):
     curve = 377
     bases = oracle.g1_walk(curve, 5, 2, 64)
     same = np.tile(ints_to_limbs([FR[curve] - 12345], 4), (64, 1))
-    assert (emul.paired(curve, bases, same, c=6, L=5, chunk=40, G=4, G2=3) == oracle.g1_msm(curve, bases, same).reshape(-1)).all()
-    eq = np.tile(bases[:1], (64, 1))                                       # the same point 64 times: every pair is a doubling
-    assert (emul.paired(curve, eq, same, c=6, L=5, G=4, G2=3) == oracle.g1_msm(curve, eq, same).reshape(-1)).all()
+    for R in (1, 2, 4):
+        assert (emul.paired(curve, bases, same, c=6, L=5, chunk=40, G=4, G2=3, R=R) == oracle.g1_msm(curve, bases, same).reshape(-1)).all()
+        eq = np.tile(bases[:1], (64, 1))                                   # the same point 64 times: every pair is a doubling, in every round
+        assert (emul.paired(curve, eq, same, c=6, L=5, G=4, G2=3, R=R) == oracle.g1_msm(curve, eq, same).reshape(-1)).all()
+    # (the only points with x = 0, (0, +-1), have order 3: they are outside G1, and the MSM's scalar folding s -> r - s
+    #  presupposes points of order r, as every arkworks G1Affine is; so x = 0 can only be the encoded point at infinity)
     zero = np.zeros((64, 4), dtype=np.uint64)
     assert (emul.paired(curve, bases, zero, c=6, L=8) == 0).all()
     one = zero.copy()
