@@ -51,6 +51,15 @@ def test_proof_bytes_match_oracle_golden(ctx, pk16, golden):
     assert ct2 == ct and proof2 != proof
 
 
+def test_proof_bytes_match_second_golden(ctx, pk16):
+    """another message, key and zk seed (FIPS-197 Appendix C.1) under the same proving key: byte-identical to the oracle prover again"""
+    with open(os.path.join(GOLD, "marlin_proof_16B_fips_c1.json")) as f:
+        g2 = json.load(f)
+    ct, proof = ctx.encrypt(pk16, bytes.fromhex(g2["message"]), bytes.fromhex(g2["key"]), bytes.fromhex(g2["zk_seed"]))
+    assert ct.hex() == g2["ciphertext"] == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    assert proof.hex() == g2["proof"]
+
+
 def _verify(pk, ct, proof_bytes):
     """Both verifiers must agree: the oracle's (trapdoor check in G1) and the product's verify_encryption (pairing check)."""
     try:

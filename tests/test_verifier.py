@@ -75,3 +75,16 @@ def test_malformed_inputs_are_errors(golden):
     t = bytearray(proof)
     t[16:16 + 48], t[16 + 49:16 + 49 + 48] = proof[16 + 49:16 + 49 + 48], proof[16:16 + 48]
     assert zk.verify_encryption(vk, bytes(t), ct) is False
+
+
+def test_second_golden_proof_and_cross_statements(golden):
+    """FIPS-197 Appendix C.1 under the same keys: accepted for its own ciphertext, and neither proof verifies the other statement"""
+    with open(os.path.join(os.path.dirname(GOLD), "marlin_proof_16B_fips_c1.json")) as f:
+        g2 = json.load(f)
+    assert g2["ciphertext"] == "69c4e0d86a7b0430d8cdb78070b4c55a" and g2["verifying_key"] == golden["verifying_key"]
+    vk = bytes.fromhex(golden["verifying_key"])
+    p1, c1 = bytes.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
+    p2, c2 = bytes.fromhex(g2["proof"]), bytes.fromhex(g2["ciphertext"])
+    assert zk.verify_encryption(vk, p2, c2) is True
+    assert zk.verify_encryption(vk, p2, c1) is False
+    assert zk.verify_encryption(vk, p1, c2) is False

@@ -18,7 +18,21 @@ MSG = bytes.fromhex("3243f6a8885a308d313198a2e0370734")
 TAU_SEED, GAMMA_SEED, ZK_SEED = bytes(range(32)), bytes(range(1, 33)), bytes([7] * 32)
 
 
+# second fixture: FIPS-197 Appendix C.1 (key 00..0f, plaintext 00 11 .. ff -> 69c4e0d8 6a7b0430 d8cdb780 70b4c55a), another zk seed, same SRS
+VARIANTS = {
+    "marlin_proof_16B.json": (MSG, KEY, ZK_SEED),
+    "marlin_proof_16B_fips_c1.json": (bytes.fromhex("00112233445566778899aabbccddeeff"), bytes(range(16)), bytes([0xA5] * 32)),
+}
+
+
 def main():
+    for name, (msg, key, zk_seed) in VARIANTS.items():
+        if len(sys.argv) > 1 and sys.argv[1] != name:
+            continue
+        generate(name, msg, key, zk_seed)
+
+
+def generate(name, MSG, KEY, ZK_SEED):
     t0 = time.time()
     cs, ct = model.synthesize(MSG, KEY)
     A, B, C = cs.matrices()
@@ -42,7 +56,7 @@ def main():
                                                 TAU_SEED, GAMMA_SEED).hex(),
         "proof": pb.hex(),
     }
-    path = os.path.join(ROOT, "tests", "golden", "marlin_proof_16B.json")
+    path = os.path.join(ROOT, "tests", "golden", name)
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", path, "in %.0f s" % (time.time() - t0))
