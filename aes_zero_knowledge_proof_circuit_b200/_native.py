@@ -74,6 +74,8 @@ def _load():
         "zkaes_pk_verifying_key": (c_int, [vp, vp, POINTER(c_size_t)]),
         "zkaes_verify_encryption": (c_int, [vp, c_size_t, vp, c_size_t, vp, c_size_t, POINTER(c_int)]),
         "zkaes_selftest_pairing": (c_int, [vp, vp, vp]),
+        "zkaes_proof_deserialize": (c_int, [vp, c_size_t, vp]),
+        "zkaes_proof_serialize": (c_int, [vp, vp, POINTER(c_size_t)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
@@ -386,6 +388,44 @@ def verify_encryption(verifying_key: bytes, proof: bytes, ciphertext: bytes) -> 
         msg = lib().zkaes_last_error(None)
         raise ZkAesError(f"libzkaes_b200 error {rc}: {msg.decode() if msg else ''}")
     return bool(ok.value)
+
+
+class _Commitment(ctypes.Structure):
+    _fields_ = [("comm", c_uint8 * 96), ("has_shifted", c_uint8), ("shifted", c_uint8 * 96)]
+
+
+class _Opening(ctypes.Structure):
+    _fields_ = [("w", c_uint8 * 96), ("has_random_v", c_uint8), ("random_v", c_uint8 * 32)]
+
+
+class ProofFields(ctypes.Structure):
+    """include/zkaes_b200.h: zkaes_proof_fields"""
+    _fields_ = [("n_rounds", c_uint32), ("round_sizes", c_uint32 * 3), ("commitments", _Commitment * 9), ("n_evaluations", c_uint32),
+                ("evaluations", (c_uint8 * 32) * 7), ("n_openings", c_uint32), ("openings", _Opening * 2)]
+
+
+def _host_check(rc):
+    if rc != 0:
+        msg = lib().zkaes_last_error(None)
+        raise ZkAesError(f"libzkaes_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def deserialize_proof(proof: bytes) -> ProofFields:
+    """`deserialize_proof(bytes) -> MarlinProof` (re-exported at reference src/lib.rs:52): the proof's commitments (uncompressed),
+    evaluations and opening proofs as plain fields.  Host only."""
+    out = ProofFields()
+    pf = np.frombuffer(bytes(proof), dtype=np.uint8)
+    _host_check(lib().zkaes_proof_deserialize(_ptr(pf), len(proof), ctypes.byref(out)))
+    return out
+
+
+def serialize_proof(fields: ProofFields) -> bytes:
+    """`serialize_proof(proof) -> bytes`: the ark-serialize 0.3.0 compressed form zkaes_encrypt emits"""
+    n = c_size_t(0)
+    _host_check(lib().zkaes_proof_serialize(ctypes.byref(fields), None, ctypes.byref(n)))
+    buf = np.zeros(n.value, dtype=np.uint8)
+    _host_check(lib().zkaes_proof_serialize(ctypes.byref(fields), _ptr(buf), ctypes.byref(n)))
+    return buf[: n.value].tobytes()
 
 
 def pairing_selftest(a: int, b: int) -> bytes:

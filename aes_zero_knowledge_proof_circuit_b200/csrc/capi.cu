@@ -21,8 +21,15 @@ template <class P29> int selftest_field_r29(zkaes_ctx*, int, const void*, const 
 }
 using namespace zk;
 
-#define NEED_CTX(ctx) \
-    if (!(ctx)) return ZK_ERR_ARG
+// context-free entry points (the host verifier, the proof wire format) and calls made without a context report through a
+// per-thread string, read with zkaes_last_error(NULL)
+static thread_local std::string g_host_err;
+#define NEED_CTX(ctx)                   \
+    if (!(ctx)) {                       \
+        g_host_err = "null context";    \
+        return ZK_ERR_ARG;              \
+    }                                   \
+    (void)0
 #define CURVE_DISPATCH(ctx, curve_id, expr377, expr381)                    \
     ((curve_id) == 377 ? (expr377) : (curve_id) == 381 ? (expr381) : fail((ctx), ZK_ERR_ARG, "unknown curve_id (use 377 or 381)"))
 
@@ -99,8 +106,6 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
-// context-free entry points (the host verifier) report through a per-thread string, read with zkaes_last_error(NULL)
-static thread_local std::string g_host_err;
 const char* zkaes_last_error(const zkaes_ctx* ctx) { return ctx ? ctx->err.c_str() : g_host_err.empty() ? "null context" : g_host_err.c_str(); }
 void* zkaes_ctx_stream(zkaes_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -499,6 +504,32 @@ int zkaes_verify_encryption(const uint8_t* vk, size_t vk_len, const uint8_t* pro
     g_host_err.clear();
     int rc = zk::verify_encryption_host(vk, vk_len, proof, proof_len, ciphertext, ct_len, accepted, &g_host_err);
     return rc == 0 ? ZK_OK : ZK_ERR_ARG;
+}
+int zkaes_proof_deserialize(const uint8_t* proof, size_t proof_len, zkaes_proof_fields* out) {
+    if (!proof || !out) {
+        g_host_err = "proof_deserialize: null pointer";
+        return ZK_ERR_ARG;
+    }
+    g_host_err.clear();
+    return zk::proof_deserialize_host(proof, proof_len, out, &g_host_err) == 0 ? ZK_OK : ZK_ERR_ARG;
+}
+int zkaes_proof_serialize(const zkaes_proof_fields* in, uint8_t* out, size_t* len) {
+    if (!in || !len) {
+        g_host_err = "proof_serialize: null pointer";
+        return ZK_ERR_ARG;
+    }
+    g_host_err.clear();
+    std::vector<uint8_t> bytes;
+    if (zk::proof_serialize_host(in, bytes, &g_host_err) != 0) return ZK_ERR_ARG;
+    if (out) {
+        if (*len < bytes.size()) {
+            g_host_err = "proof_serialize: buffer too small";
+            return ZK_ERR_ARG;
+        }
+        memcpy(out, bytes.data(), bytes.size());
+    }
+    *len = bytes.size();
+    return ZK_OK;
 }
 int zkaes_selftest_pairing(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]) {
     if (!a32 || !b32 || !out576) return ZK_ERR_ARG;

@@ -8,6 +8,7 @@
 // no device is needed.  Deviation: the two query points are checked one after the other instead of through ark's
 // randomised batch (which draws from the caller's rng); accept/reject is the same up to the batch's soundness error.
 #include "verifier.h"
+#include "../../include/zkaes_b200.h"
 
 #include <cstring>
 #include <stdexcept>
@@ -467,6 +468,125 @@ int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t
         }
         (void)D;
         *accepted = 1;
+        return 0;
+    } catch (const std::exception& e) {
+        if (err) *err = e.what();
+        return -1;
+    }
+}
+
+// ---- proof wire format <-> plain fields ------------------------------------------------------------------------------------
+namespace {
+void g1_to_xy96(const Aff& p, uint8_t out[96]) {
+    if (p.is_inf()) {
+        memset(out, 0, 96);
+        return;
+    }
+    Fq x = p.x.from_mont(), y = p.y.from_mont();
+    memcpy(out, x.v, 48);
+    memcpy(out + 48, y.v, 48);
+}
+Aff g1_from_xy96(const uint8_t b[96]) {
+    bool zero = true;
+    for (int i = 0; i < 96; ++i) zero = zero && b[i] == 0;
+    if (zero) return Aff::inf();
+    Aff p;
+    if (!fq_from_canonical(b, &p.x) || !fq_from_canonical(b + 48, &p.y)) throw std::runtime_error("G1 coordinate out of range");
+    if (!p.on_curve()) throw std::runtime_error("G1 point not on the curve");
+    return p;
+}
+// ark-serialize 0.3.0 compressed GroupAffine: x canonical LE, bit 7 of the last byte = "y > -y", bit 6 = infinity
+void g1_serialize(const Aff& p, std::vector<uint8_t>& out) {
+    uint8_t b[48];
+    if (p.is_inf()) {
+        memset(b, 0, 48);
+        b[47] |= 1 << 6;
+    } else {
+        Fq x = p.x.from_mont(), y = p.y.from_mont(), ny = p.y.neg().from_mont();
+        memcpy(b, x.v, 48);
+        if (y.canonical_gt(ny)) b[47] |= 1 << 7;
+    }
+    out.insert(out.end(), b, b + 48);
+}
+}  // namespace
+
+int proof_deserialize_host(const uint8_t* proof, size_t len, zkaes_proof_fields* out, std::string* err) {
+    try {
+        memset(out, 0, sizeof(*out));
+        Reader pr(proof, len);
+        static const uint32_t sizes[3] = {4, 3, 2};
+        if (pr.u64() != 3) throw std::runtime_error("proof: expected three rounds of commitments");
+        out->n_rounds = 3;
+        int k = 0;
+        for (int r = 0; r < 3; ++r) {
+            if (pr.u64() != sizes[r]) throw std::runtime_error("proof: unexpected number of commitments in a round");
+            out->round_sizes[r] = sizes[r];
+            for (uint32_t i = 0; i < sizes[r]; ++i, ++k) {
+                g1_to_xy96(g1_deserialize(pr.take(48)), out->commitments[k].comm);
+                out->commitments[k].has_shifted = pr.u8() != 0;
+                if (out->commitments[k].has_shifted) g1_to_xy96(g1_deserialize(pr.take(48)), out->commitments[k].shifted);
+            }
+        }
+        if (pr.u64() != 7) throw std::runtime_error("proof: expected seven evaluations");
+        out->n_evaluations = 7;
+        bool ok = true;
+        for (int i = 0; i < 7; ++i) {
+            const uint8_t* e = pr.take(32);
+            fr_from_canonical(e, &ok);
+            memcpy(out->evaluations[i], e, 32);
+        }
+        const uint64_t nmsg = pr.u64();
+        for (uint64_t i = 0; i < nmsg; ++i)
+            if (pr.u8()) throw std::runtime_error("proof: non-empty prover message");  // this AHP sends none
+        if (nmsg != 3) throw std::runtime_error("proof: expected three prover messages");
+        if (pr.u64() != 2) throw std::runtime_error("proof: expected two opening proofs");
+        out->n_openings = 2;
+        for (int i = 0; i < 2; ++i) {
+            g1_to_xy96(g1_deserialize(pr.take(48)), out->openings[i].w);
+            out->openings[i].has_random_v = pr.u8() != 0;
+            if (out->openings[i].has_random_v) {
+                const uint8_t* e = pr.take(32);
+                fr_from_canonical(e, &ok);
+                memcpy(out->openings[i].random_v, e, 32);
+            }
+        }
+        if (pr.u8() != 0) throw std::runtime_error("proof: unexpected BatchLCProof evaluations");
+        if (!pr.done()) throw std::runtime_error("proof: trailing bytes");
+        if (!ok) throw std::runtime_error("proof: field element out of range");
+        return 0;
+    } catch (const std::exception& e) {
+        if (err) *err = e.what();
+        return -1;
+    }
+}
+
+int proof_serialize_host(const zkaes_proof_fields* in, std::vector<uint8_t>& out, std::string* err) {
+    try {
+        if (in->n_rounds != 3 || in->round_sizes[0] != 4 || in->round_sizes[1] != 3 || in->round_sizes[2] != 2 || in->n_evaluations != 7 ||
+            in->n_openings != 2)
+            throw std::runtime_error("proof fields: not the shape of this protocol's proof");
+        out.clear();
+        put_u64(out, 3);
+        int k = 0;
+        for (int r = 0; r < 3; ++r) {
+            put_u64(out, in->round_sizes[r]);
+            for (uint32_t i = 0; i < in->round_sizes[r]; ++i, ++k) {
+                g1_serialize(g1_from_xy96(in->commitments[k].comm), out);
+                out.push_back(in->commitments[k].has_shifted ? 1 : 0);
+                if (in->commitments[k].has_shifted) g1_serialize(g1_from_xy96(in->commitments[k].shifted), out);
+            }
+        }
+        put_u64(out, 7);
+        for (int i = 0; i < 7; ++i) out.insert(out.end(), in->evaluations[i], in->evaluations[i] + 32);
+        put_u64(out, 3);
+        out.insert(out.end(), 3, (uint8_t)0);  // three ProverMsg::EmptyMessage
+        put_u64(out, 2);
+        for (int i = 0; i < 2; ++i) {
+            g1_serialize(g1_from_xy96(in->openings[i].w), out);
+            out.push_back(in->openings[i].has_random_v ? 1 : 0);
+            if (in->openings[i].has_random_v) out.insert(out.end(), in->openings[i].random_v, in->openings[i].random_v + 32);
+        }
+        out.push_back(0);  // BatchLCProof.evals = None
         return 0;
     } catch (const std::exception& e) {
         if (err) *err = e.what();

@@ -6,6 +6,8 @@
 
 #include "ff.cuh"
 
+struct zkaes_proof_fields;
+
 namespace zk {
 
 // Verifying key = everything `verify_encryption` (reference src/lib.rs:116-136) needs, as one byte string:
@@ -20,6 +22,10 @@ std::vector<uint8_t> build_verifying_key(const std::vector<uint8_t>& index_vk, u
 // Returns 0 and sets *accepted to 0/1, or -1 (with *err) when the key or the proof cannot be parsed.
 int verify_encryption_host(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* ciphertext, size_t ct_len,
                            int* accepted, std::string* err);
+
+// ark_marlin::Proof bytes <-> plain fields (include/zkaes_b200.h: zkaes_proof_fields); -1 with *err on malformed input
+int proof_deserialize_host(const uint8_t* proof, size_t len, struct zkaes_proof_fields* out, std::string* err);
+int proof_serialize_host(const struct zkaes_proof_fields* in, std::vector<uint8_t>& out, std::string* err);
 
 // e(a G1, b G2) as 12 x 48 canonical LE bytes (c[0].c0, c[0].c1, c[1].c0, ...): test hook against oracle/pairing_ref.py
 void pairing_selftest(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]);

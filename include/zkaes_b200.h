@@ -197,6 +197,32 @@ int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t
 int zkaes_pk_verifying_key(const zkaes_pk* pk, uint8_t* out, size_t* len);
 int zkaes_verify_encryption(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* ciphertext, size_t ct_len,
                             int* accepted);
+/* ---- proof wire format (src/lib.rs:52 re-exports simpleworks' serialize_proof / deserialize_proof) -----------------------
+ * The proof bytes zkaes_encrypt emits are the ark-serialize 0.3.0 CanonicalSerialize form of ark_marlin::Proof (compressed
+ * G1 points).  zkaes_proof_deserialize unpacks them into plain fields -- what `deserialize_proof(bytes) -> MarlinProof` gives
+ * a Rust caller -- and zkaes_proof_serialize packs them again (byte-identical round trip).  HOST ONLY.
+ * Points: x || y, 48 + 48 bytes canonical little-endian (not Montgomery); the point at infinity is all zero.  Field elements:
+ * 32 bytes canonical little-endian.  Commitments are in protocol order: w, z_a, z_b, mask | t, g_1, h_1 | g_2, h_2. */
+typedef struct zkaes_proof_fields {
+    uint32_t n_rounds;               /* 3 */
+    uint32_t round_sizes[3];         /* 4, 3, 2 */
+    struct {
+        uint8_t comm[96];
+        uint8_t has_shifted;         /* degree-bounded polynomials (g_1, g_2) carry a second commitment */
+        uint8_t shifted[96];
+    } commitments[9];
+    uint32_t n_evaluations;          /* 7: a_denom b_denom c_denom g_1 g_2 t z_b (sorted by label) */
+    uint8_t evaluations[7][32];
+    uint32_t n_openings;             /* 2: at beta, at gamma */
+    struct {
+        uint8_t w[96];
+        uint8_t has_random_v;
+        uint8_t random_v[32];
+    } openings[2];
+} zkaes_proof_fields;
+int zkaes_proof_deserialize(const uint8_t* proof, size_t proof_len, zkaes_proof_fields* out);
+int zkaes_proof_serialize(const zkaes_proof_fields* in, uint8_t* out, size_t* len);  /* out may be NULL to query the size */
+
 /* Test hook: e(a G1, b G2) for canonical 32-byte LE scalars, as 12 x 48 canonical LE bytes (oracle/pairing_ref.py layout). */
 int zkaes_selftest_pairing(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]);
 

@@ -88,3 +88,37 @@ def test_second_golden_proof_and_cross_statements(golden):
     assert zk.verify_encryption(vk, p2, c2) is True
     assert zk.verify_encryption(vk, p2, c1) is False
     assert zk.verify_encryption(vk, p1, c2) is False
+
+
+@pytest.mark.parametrize("name", ["marlin_proof_16B.json", "marlin_proof_16B_fips_c1.json"])
+def test_proof_wire_format_round_trip(name):
+    """deserialize_proof / serialize_proof (src/lib.rs:52): fields equal the oracle's reading of the same bytes, and packing
+    them again reproduces the bytes"""
+    from oracle import marlin_oracle as mo
+
+    with open(os.path.join(os.path.dirname(GOLD), name)) as f:
+        proof = bytes.fromhex(json.load(f)["proof"])
+    fields = zk.deserialize_proof(proof)
+    assert (fields.n_rounds, list(fields.round_sizes), fields.n_evaluations, fields.n_openings) == (3, [4, 3, 2], 7, 2)
+    ref = mo.deserialize_proof(proof)
+    flat = [c for rnd in ref["commitments"] for c in rnd]
+    xy = lambda pt: b"".join(int(v).to_bytes(48, "little") for v in mo.g1_xy(pt))
+    for got, (comm, shifted) in zip(fields.commitments, flat):
+        assert bytes(got.comm) == xy(comm)
+        assert bool(got.has_shifted) == (shifted is not None)
+        if shifted is not None:
+            assert bytes(got.shifted) == xy(shifted)
+    assert [bool(c.has_shifted) for c in fields.commitments] == [False] * 5 + [True, False, True, False]   # g_1 and g_2 are degree-bounded
+    assert [int.from_bytes(bytes(e), "little") for e in fields.evaluations] == ref["evaluations"]
+    for got, o in zip(fields.openings, ref["pc_proof"]):
+        assert bytes(got.w) == xy(o["w"])
+        assert bool(got.has_random_v) == (o["random_v"] is not None)
+        if o["random_v"] is not None:
+            assert int.from_bytes(bytes(got.random_v), "little") == o["random_v"]
+    assert zk.serialize_proof(fields) == proof
+    # a point moved off the curve is refused when packing; a truncated proof when unpacking
+    fields.commitments[0].comm[3] ^= 1
+    with pytest.raises(zk.ZkAesError):
+        zk.serialize_proof(fields)
+    with pytest.raises(zk.ZkAesError):
+        zk.deserialize_proof(proof[:-1])
