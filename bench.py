@@ -52,6 +52,16 @@ MADD_PEAK_PER_S = 2.48e9  # XYZZ += affine on one B200, tools/ubench.cu (profile
 NCU_TRAFFIC_BYTES_PER_TERM = 171.2e9 / 2**26
 
 
+FR_377_TOP_LIMB = 0x12ab655e9a2ca556  # top 64 bits of the BLS12-377 scalar modulus
+
+
+def rand_fr(rng, n):
+    """n canonical BLS12-377 scalars < r as (n, 4) uint64: uniform limbs, the top one reduced below the modulus' top limb"""
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] %= np.uint64(FR_377_TOP_LIMB)
+    return a
+
+
 def synth_message(n):
     return bytes((i * 131 + 7) & 0xFF for i in range(n))
 
@@ -278,8 +288,6 @@ def bench_msm(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import aes_zero_knowledge_proof_circuit_b200 as zk
-    from oracle.cpu import rand_fr
-
     ctx = zk.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream)
     log_n = args.log_n
@@ -291,7 +299,7 @@ def bench_msm(args, rank, world, local_rank):
     ctx.sync()
     bases = all_bases[lo * 96:(lo + n_local) * 96].clone()
     del all_bases
-    scal_host = np.ascontiguousarray(rand_fr(np.random.default_rng(2024), CURVE, n_total)[lo:lo + n_local])
+    scal_host = np.ascontiguousarray(rand_fr(np.random.default_rng(2024), n_total)[lo:lo + n_local])
     scalars = torch.from_numpy(scal_host.view(np.int64)).cuda()
     wbytes = ctx.msm_g1_windows_bytes(CURVE, n_total)
     win = torch.zeros(wbytes, dtype=torch.uint8, device="cuda")
