@@ -17,7 +17,7 @@ namespace zk {
 template <class F> int selftest_field_asm(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class F> int selftest_field_portable(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class C> int selftest_g1(zkaes_ctx*, int, const void*, const void*, void*, size_t);
-template <class P29> int selftest_field_r29(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template <class F> int selftest_field_call(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 }
 using namespace zk;
 
@@ -168,6 +168,9 @@ int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
     } else if (k == "msm_acc_blocks") {
         if (value != 3 && value != 4) return fail(ctx, ZK_ERR_ARG, "msm_acc_blocks must be 3 or 4");
         ctx->msm_acc_blocks = value;
+    } else if (k == "msm_madd_call") {
+        if (value != 0 && value != 1) return fail(ctx, ZK_ERR_ARG, "msm_madd_call must be 0 or 1");
+        ctx->msm_madd_call = value;
     } else {
         return fail(ctx, ZK_ERR_ARG, "tuning: unknown key " + k);
     }
@@ -283,10 +286,9 @@ int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int va
     NEED_CTX(ctx);
     if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
     if (curve_id != 377 && curve_id != 381) return fail(ctx, ZK_ERR_ARG, "unknown curve_id");
-    if (variant == 2) {  // Fq through the radix-2^29 internal form
-        if (field != 1) return fail(ctx, ZK_ERR_ARG, "selftest: the radix-2^29 form exists for Fq only");
-        return curve_id == 377 ? selftest_field_r29<Fq377R29Params>(ctx, op, a, b, out, count)
-                               : selftest_field_r29<Fq381R29Params>(ctx, op, a, b, out, count);
+    if (variant == 2) {  // products through the out-of-line multiplier of the MSM inner loop (Fp::mul_call)
+        if (curve_id == 377) return field ? selftest_field_call<Fq377>(ctx, op, a, b, out, count) : selftest_field_call<Fr377>(ctx, op, a, b, out, count);
+        return field ? selftest_field_call<Fq381>(ctx, op, a, b, out, count) : selftest_field_call<Fr381>(ctx, op, a, b, out, count);
     }
     int sel = (curve_id == 381 ? 4 : 0) | (field ? 2 : 0) | (variant ? 1 : 0);
     switch (sel) {
@@ -327,31 +329,6 @@ int zkaes_selftest_host_field(int curve_id, int field, int op, const void* a, co
         }
         return ZK_OK;
     };
-    // field 2: Fq through the radix-2^29 internal form (fq29.cuh): from_std -> op -> to_std
-    auto run29 = [&](auto tag) {
-        using P29 = decltype(tag);
-        using G = Fq29<P29>;
-        const uint32_t* x = reinterpret_cast<const uint32_t*>(a);
-        const uint32_t* y = reinterpret_cast<const uint32_t*>(b);
-        uint32_t* o = reinterpret_cast<uint32_t*>(out);
-        for (size_t i = 0; i < count; ++i) {
-            G u = G::from_std(x + 12 * i), v = G::from_std(y + 12 * i), r;
-            switch (op) {
-                case 0: r = u + v; break;
-                case 1: r = u - v; break;
-                case 2: r = u * v; break;
-                case 4: r = u.neg(); break;
-                default: return ZK_ERR_ARG;
-            }
-            r.to_std(o + 12 * i);
-        }
-        return ZK_OK;
-    };
-    if (field == 2) {
-        if (curve_id == 377) return run29(Fq377R29Params());
-        if (curve_id == 381) return run29(Fq381R29Params());
-        return ZK_ERR_ARG;
-    }
     if (curve_id == 377) return field ? run(Fq377()) : run(Fr377());
     if (curve_id == 381) return field ? run(Fq381()) : run(Fr381());
     return ZK_ERR_ARG;

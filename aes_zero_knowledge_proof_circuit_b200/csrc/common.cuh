@@ -82,6 +82,7 @@ struct zkaes_ctx {
     int msm_pair_round = 0;  // R = number of batched-affine pair rounds before the XYZZ accumulation (msm_core.cuh); 0 = plain accumulation.
                              // Off by default: one round measured break-even (profiles/r1_launches_msm_2p26_pair_round.txt)
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
+    int msm_madd_call = 1;   // 1: the mixed addition issues its ten products through one out-of-line multiplier (XYZZ::madd_call)
     int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
     // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)
     int rank = 0, nranks = 1;

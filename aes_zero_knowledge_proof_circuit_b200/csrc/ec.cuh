@@ -12,10 +12,10 @@
 #include <type_traits>
 
 #include "ff.cuh"
-#include "fq29.cuh"
 
-// Point doubling / full addition are off the inner loop (bucket reduction, rare mixed-add corner cases):
-// keeping them out of line cuts both compile time and instruction-cache footprint of the hot kernels.
+// Point doubling / full addition are off the mixed-addition loop (bucket reduction, rare mixed-add corner cases): they are
+// out of line and issue their products through the out-of-line multiplier (Fp::mul_call), so a kernel that uses them carries
+// one copy of the multiplier instead of fourteen per formula (60 KB of SASS each in round 1).
 #if defined(__CUDACC__)
 #define ZK_HD_COLD __host__ __device__ __noinline__
 #else
@@ -24,37 +24,10 @@
 
 namespace zk {
 
-// base-field type of a curve description: Fp<FqP> (arkworks layout) unless the description names its own (C::FqCustom:
-// the radix-2^29 form the MSM kernels compute in)
-template <class C, class = void>
+template <class C>
 struct FqOf {
     using type = Fp<typename C::FqP>;
 };
-template <class C>
-struct FqOf<C, std::void_t<typename C::FqCustom>> {
-    using type = typename C::FqCustom;
-};
-// internal curve descriptions used by msm.cu
-struct G1_377R29 {
-    using FqP = Fq377Params;
-    using FrP = Fr377Params;
-    using FqCustom = Fq29<Fq377R29Params>;
-    static constexpr int CURVE_ID = 377;
-};
-struct G1_381R29 {
-    using FqP = Fq381Params;
-    using FrP = Fr381Params;
-    using FqCustom = Fq29<Fq381R29Params>;
-    static constexpr int CURVE_ID = 381;
-};
-// Which form the MSM kernels compute in.  Default: the arkworks 32-bit-limb form.  -DZK_MSM_R29 selects the radix-2^29
-// form; it is bit-exact (tests run both) but SLOWER on B200: every 32x32->64 IMAD (WIDE or HI, with or without carry)
-// issues at half rate, so 13 x 13 limb products cannot beat 12 x 12 (profiles/ubench_r1.txt).
-template <class C> struct InternalCurve { using type = C; };
-#if defined(ZK_MSM_R29)
-template <> struct InternalCurve<G1_377Params> { using type = G1_377R29; };
-template <> struct InternalCurve<G1_381Params> { using type = G1_381R29; };
-#endif
 
 template <class C>
 struct Affine {
@@ -116,17 +89,19 @@ struct XYZZ {
     }
 
     // 2*P for an affine P (mdbl-2008-s-1, a = 0)
-    static ZK_HD_COLD XYZZ dbl_affine(const Affine<C>& p) {
+    // (argument by value: a reference would force the caller's point into local memory on every loop iteration -- the
+    // 96-byte stack frame and the 843 M dead local stores of the round-1 ncu capture)
+    static ZK_HD_COLD XYZZ dbl_affine(Affine<C> p) {
         if (p.is_inf() || p.y.is_zero()) return inf();
         XYZZ r;
         Fq u = p.y.dbl();
-        Fq v = u.sqr();
-        Fq w = u * v;
-        Fq s = p.x * v;
-        Fq x2 = p.x.sqr();
+        Fq v = Fq::mul_call(u, u);
+        Fq w = Fq::mul_call(u, v);
+        Fq s = Fq::mul_call(p.x, v);
+        Fq x2 = Fq::mul_call(p.x, p.x);
         Fq m = x2.dbl() + x2;
-        r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * p.y;
+        r.x = Fq::mul_call(m, m) - s.dbl();
+        r.y = Fq::mul_call(m, s - r.x) - Fq::mul_call(w, p.y);
         r.zz = v;
         r.zzz = w;
         return r;
@@ -137,15 +112,15 @@ struct XYZZ {
         if (is_inf() || y.is_zero()) return inf();
         XYZZ r;
         Fq u = y.dbl();
-        Fq v = u.sqr();
-        Fq w = u * v;
-        Fq s = x * v;
-        Fq x2 = x.sqr();
+        Fq v = Fq::mul_call(u, u);
+        Fq w = Fq::mul_call(u, v);
+        Fq s = Fq::mul_call(x, v);
+        Fq x2 = Fq::mul_call(x, x);
         Fq m = x2.dbl() + x2;
-        r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * y;
-        r.zz = v * zz;
-        r.zzz = w * zzz;
+        r.x = Fq::mul_call(m, m) - s.dbl();
+        r.y = Fq::mul_call(m, s - r.x) - Fq::mul_call(w, y);
+        r.zz = Fq::mul_call(v, zz);
+        r.zzz = Fq::mul_call(w, zzz);
         return r;
     }
 
@@ -182,6 +157,36 @@ struct XYZZ {
         x = x3;
     }
 
+    // madd with the ten products issued through the out-of-line multiplier (Fp::mul_call): same values, ~1/8 of the code
+    ZK_HD void madd_call(const Affine<C>& p) {
+        if (p.is_inf()) return;
+        if (is_inf()) {
+            *this = from_affine(p);
+            return;
+        }
+        Fq u2 = Fq::mul_call(p.x, zz);
+        Fq s2 = Fq::mul_call(p.y, zzz);
+        Fq pp_ = u2 - x;
+        Fq r_ = s2 - y;
+        if (pp_.is_zero()) {
+            if (r_.is_zero())
+                *this = dbl_affine(p);
+            else
+                *this = inf();
+            return;
+        }
+        Fq pp = Fq::mul_call(pp_, pp_);
+        Fq ppp = Fq::mul_call(pp_, pp);
+        Fq q = Fq::mul_call(x, pp);
+        Fq r2 = Fq::mul_call(r_, r_);
+        Fq x3 = r2 - ppp - q.dbl();
+        Fq yp = Fq::mul_call(y, ppp);
+        zz = Fq::mul_call(zz, pp);
+        zzz = Fq::mul_call(zzz, ppp);
+        y = Fq::mul_call(r_, q - x3) - yp;
+        x = x3;
+    }
+
     // this += o, add-2008-s
     ZK_HD_COLD void add(const XYZZ& o) {
         if (o.is_inf()) return;
@@ -189,10 +194,10 @@ struct XYZZ {
             *this = o;
             return;
         }
-        Fq u1 = x * o.zz;
-        Fq u2 = o.x * zz;
-        Fq s1 = y * o.zzz;
-        Fq s2 = o.y * zzz;
+        Fq u1 = Fq::mul_call(x, o.zz);
+        Fq u2 = Fq::mul_call(o.x, zz);
+        Fq s1 = Fq::mul_call(y, o.zzz);
+        Fq s2 = Fq::mul_call(o.y, zzz);
         Fq pp_ = u2 - u1;
         Fq r_ = s2 - s1;
         if (pp_.is_zero()) {
@@ -202,14 +207,14 @@ struct XYZZ {
                 *this = inf();
             return;
         }
-        Fq pp = pp_.sqr();
-        Fq ppp = pp_ * pp;
-        Fq q = u1 * pp;
-        Fq x3 = r_.sqr() - ppp - q.dbl();
-        y = r_ * (q - x3) - s1 * ppp;
+        Fq pp = Fq::mul_call(pp_, pp_);
+        Fq ppp = Fq::mul_call(pp_, pp);
+        Fq q = Fq::mul_call(u1, pp);
+        Fq x3 = Fq::mul_call(r_, r_) - ppp - q.dbl();
+        y = Fq::mul_call(r_, q - x3) - Fq::mul_call(s1, ppp);
         x = x3;
-        zz = zz * o.zz * pp;
-        zzz = zzz * o.zzz * ppp;
+        zz = Fq::mul_call(Fq::mul_call(zz, o.zz), pp);
+        zzz = Fq::mul_call(Fq::mul_call(zzz, o.zzz), ppp);
     }
 
     ZK_HD XYZZ neg() const {

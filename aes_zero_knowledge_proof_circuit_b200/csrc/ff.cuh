@@ -33,8 +33,6 @@ static __constant__ uint32_t zk_c_mont_inv[4] = {Fr377Params::INV, Fq377Params::
 // products: without it ptxas interleaves their carry chains, runs out of the 7 predicate registers and spills carries
 // through P2R/LOP3/ISETP (about one extra ALU instruction per IMAD.WIDE in the madd inner loop).
 static __constant__ uint32_t zk_c_zero = 0;
-// -p^-1 mod 2^29 for the radix-2^29 base fields (fq29.cuh), opaque to ptxas for the same reason
-static __constant__ uint32_t zk_c_r29_inv[2] = {Fq377R29Params::INV, Fq381R29Params::INV};
 #endif
 
 template <int N>
@@ -259,7 +257,13 @@ struct Fp {
 #endif
     }
 
-    // wire-format hooks shared with the radix-2^29 form (fq29.cuh): for Fp the arkworks limbs ARE the working form
+    // a * b through ONE out-of-line copy of the multiplier (device: a real CALL with both operands and the result in registers --
+    // nvcc passes the 2 x N words by value in registers, no stack traffic; checked in SASS, profiles/r2_sass_madd_call.txt).
+    // The MSM inner loop issues its ten products through this so that the loop body is ~10 KB of SASS instead of the 84 KB of ten
+    // inlined copies, which thrashed the 32 KB instruction cache (20 % "no instruction" stalls in the round-1 ncu capture).
+    static ZK_HD Fp mul_call(const Fp& a, const Fp& b);
+
+    // wire-format hooks: the arkworks limbs ARE the working form
     static ZK_HD Fp unpack(const uint32_t* w) {
         Fp r;
 #pragma unroll
@@ -321,6 +325,45 @@ struct Fp {
         return false;
     }
 };
+
+#if defined(__CUDACC__)
+template <class P>
+struct FpWords {
+    uint32_t v[P::N];
+};
+template <class P>
+__device__ __noinline__ FpWords<P> fp_mul_out_of_line(FpWords<P> a, FpWords<P> b) {
+    Fp<P> x, y;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) {
+        x.v[i] = a.v[i];
+        y.v[i] = b.v[i];
+    }
+    const Fp<P> r = x * y;
+    FpWords<P> o;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) o.v[i] = r.v[i];
+    return o;
+}
+#endif
+template <class P>
+ZK_HD Fp<P> Fp<P>::mul_call(const Fp<P>& a, const Fp<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
+    FpWords<P> x, y;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) {
+        x.v[i] = a.v[i];
+        y.v[i] = b.v[i];
+    }
+    const FpWords<P> o = fp_mul_out_of_line<P>(x, y);
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) r.v[i] = o.v[i];
+    return r;
+#else
+    return a * b;
+#endif
+}
 
 using Fr377 = Fp<Fr377Params>;
 using Fq377 = Fp<Fq377Params>;

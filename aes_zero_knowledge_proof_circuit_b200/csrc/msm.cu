@@ -182,51 +182,31 @@ int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32
 }
 
 // ---- bucket accumulation ---------------------------------------------------------------------------------
-// Bases are read in the INTERNAL packed form (for the default build this IS the arkworks form: 12 x u32 Montgomery limbs
-// per coordinate, 96 B per point, 6 x 128-bit loads; -DZK_MSM_R29 selects the radix-2^29 representative in the same 96 B).
-// arkworks wire form (Montgomery R = 2^384 limbs) -> internal packed form; in place when dst == src
-template <class C>
-__global__ void __launch_bounds__(128) k_bases_to_internal(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
-    using CI = typename InternalCurve<C>::type;
-    using Fq = typename Affine<CI>::Fq;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t w[24];
-    const uint4* p = reinterpret_cast<const uint4*>(src + i * 24);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        uint4 v = p[k];
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-    }
-    Fq x = Fq::from_std(w), y = Fq::from_std(w + 12);
-    x.pack(w);
-    y.pack(w + 12);
-    uint4* o = reinterpret_cast<uint4*>(dst + i * 24);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-}
-// internal XYZZ window sums -> arkworks-form XYZZ for the host fold
-template <class C>
-__global__ void k_windows_to_std(const XYZZ<typename InternalCurve<C>::type>* __restrict__ in, XYZZ<C>* __restrict__ out, int W) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= W) return;
-    XYZZ<typename InternalCurve<C>::type> p = in[w];
-    XYZZ<C> r;
-    p.x.to_std(r.x.v);
-    p.y.to_std(r.y.v);
-    p.zz.to_std(r.zz.v);
-    p.zzz.to_std(r.zzz.v);
-    out[w] = r;
-}
-
+// Bases are read in the arkworks form (12 x u32 Montgomery limbs per coordinate, 96 B per point, 6 x 128-bit loads).
 // BLOCKS = resident blocks per SM the register allocation is held to: 3 (166 registers, no spills) or 4 (128 registers,
 // 92 bytes of spills, 16 instead of 12 warps per SM to cover the IMAD dependency waits).
-template <class C, int BLOCKS>
+// CALL: the ten field products of a mixed addition go through one out-of-line multiplier (XYZZ::madd_call) instead of ten
+// inlined copies -- the loop body then fits the instruction cache.
+template <class C, int BLOCKS, bool CALL>
 __global__ void __launch_bounds__(128, BLOCKS) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                                 const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t n_slices, uint32_t L,
                                                                 XYZZ<C>* __restrict__ buckets, XYZZ<C>* __restrict__ head,
                                                                 XYZZ<C>* __restrict__ tail, uint32_t* __restrict__ tail_bucket) {
-    msm_slice_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, nb, sorted, bases, buckets, head, tail, tail_bucket);
+    msm_slice_accumulate<C, CALL>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, nb, sorted, bases, buckets, head, tail, tail_bucket);
+}
+template <class C>
+static void msm_launch_accumulate(zkaes_ctx* ctx, size_t slices, const uint32_t* bases, const uint32_t* sorted, const uint32_t* offsets, uint32_t nb,
+                                  uint32_t L, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket) {
+    const unsigned grid = cdiv(slices, 128);
+    cudaStream_t st = ctx->stream;
+#define ZK_ACC(B, CALLV) k_msm_accumulate<C, B, CALLV><<<grid, 128, 0, st>>>(bases, sorted, offsets, nb, (uint32_t)slices, L, buckets, head, tail, tail_bucket)
+    if (ctx->msm_madd_call) {
+        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, true); else ZK_ACC(3, true);
+    } else {
+        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, false); else ZK_ACC(3, false);
+    }
+#undef ZK_ACC
+    ctx->launches++;
 }
 
 template <class C>
@@ -403,12 +383,8 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
                 cudaEventCreate(&span.e1);
                 cudaEventRecord(span.e0, st);
             }
-            if (ctx->msm_acc_blocks == 4)
-                k_msm_accumulate<C, 4><<<cdiv(slices, 128), 128, 0, st>>>(pts, nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
-                                                                          head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
-            else
-                k_msm_accumulate<C, 3><<<cdiv(slices, 128), 128, 0, st>>>(pts, nullptr, poff.as<uint32_t>(), p.nbw, (uint32_t)slices, L, B,
-                                                                          head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+            msm_launch_accumulate<C>(ctx, slices, pts, nullptr, poff.as<uint32_t>(), p.nbw, L, B, head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(),
+                                     tail_bucket.as<uint32_t>());
             if (ctx->prof) {
                 cudaEventRecord(span.e1, st);
                 span.terms = w == 0 ? m : 0;               // each term is counted once per chunk
@@ -419,7 +395,7 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
                                                               tail_bucket.as<uint32_t>());
             k_msm_merge_heavy<C><<<cdiv(slices, 4), 128, 0, st>>>(poff.as<uint32_t>(), (uint32_t)slices, L, B, head.as<XYZZ<C>>(), tail.as<XYZZ<C>>(),
                                                                   tail_bucket.as<uint32_t>());
-            ctx->launches += 3;
+            ctx->launches += 2;
             ZK_CUDA(ctx, cudaGetLastError());
         }
     }
@@ -439,7 +415,6 @@ template <class C>
 int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, size_t n, int scalars_mont, const MsmPlan& p,
                     void* d_window_sums, int bases_internal, size_t scalar_stride) {
     using FrP = typename C::FrP;
-    using CI = typename InternalCurve<C>::type;  // the form the curve arithmetic below runs in
     cudaStream_t st = ctx->stream;
     if (n == 0) {
         ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * p.W, st));
@@ -455,30 +430,23 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     const size_t max_slices = (size_t)((max_entries + L - 1) / L);
     // the pair round (batched-affine first level) pays off once buckets hold several entries; it needs the field inversion,
     // which only the default (arkworks-limb) form of the curve arithmetic provides
-    const bool paired = ctx->msm_pair_round > 0 && std::is_same<CI, C>::value && n >= ((size_t)1 << 16) && (n / p.nbw) >> ctx->msm_pair_round >= 2;
+    const bool paired = ctx->msm_pair_round > 0 && n >= ((size_t)1 << 16) && (n / p.nbw) >> ctx->msm_pair_round >= 2;
     DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket;
-    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<CI>) * (size_t)p.nb, st));
-    ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<CI>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
+    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<C>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
     if (!paired) {
         ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
         ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
         ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
-        ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<CI>) * max_slices, st));
-        ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<CI>) * max_slices, st));
+        ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<C>) * max_slices, st));
+        ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<C>) * max_slices, st));
         ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
     }
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
-    DevBuf conv;
-    if (!bases_internal && !std::is_same<CI, C>::value) {  // arkworks-form bases, kernels in another form: convert into scratch
-        ZK_CUDA(ctx, conv.alloc(96 * n, st));
-        k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, st>>>(bases, conv.as<uint32_t>(), n);
-        ctx->launches++;
-        bases = conv.as<uint32_t>();
-    }
+    (void)bases_internal;  // the kernels compute in the arkworks form: prepared and unprepared bases are the same bytes
     const auto* scalars = reinterpret_cast<const uint32_t*>(d_scalars);
     if (paired) {
-        if constexpr (std::is_same<CI, C>::value)
-            ZK_TRY(msm_accumulate_paired<C>(ctx, bases, scalars, n, scalars_mont, p, scalar_stride, chunk_max, buckets.as<XYZZ<C>>()));
+        ZK_TRY(msm_accumulate_paired<C>(ctx, bases, scalars, n, scalars_mont, p, scalar_stride, chunk_max, buckets.as<XYZZ<C>>()));
     }
     for (size_t base = 0; !paired && base < n; base += chunk_max) {
         size_t m = n - base < chunk_max ? n - base : chunk_max;
@@ -497,25 +465,18 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
             cudaEventCreate(&span.e1);
             cudaEventRecord(span.e0, st);
         }
-        if (ctx->msm_acc_blocks == 4)
-            k_msm_accumulate<CI, 4><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, (uint32_t)slices, L,
-                                                                       buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>(),
-                                                                       tail_bucket.as<uint32_t>());
-        else
-            k_msm_accumulate<CI, 3><<<cdiv(slices, 128), 128, 0, st>>>(bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, (uint32_t)slices, L,
-                                                                       buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(), tail.as<XYZZ<CI>>(),
-                                                                       tail_bucket.as<uint32_t>());
-        ctx->launches++;
+        msm_launch_accumulate<C>(ctx, slices, bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                                 tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
         if (ctx->prof) {
             cudaEventRecord(span.e1, st);
             span.terms = m;
             span.madds = (uint64_t)m * p.W;  // upper bound: zero digits are skipped
             ctx->prof_spans.push_back(span);
         }
-        k_msm_merge<CI><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
-                                                           tail.as<XYZZ<CI>>(), tail_bucket.as<uint32_t>());
-        k_msm_merge_heavy<CI><<<cdiv(slices, 4), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<CI>>(), head.as<XYZZ<CI>>(),
-                                                               tail.as<XYZZ<CI>>(), tail_bucket.as<uint32_t>());
+        k_msm_merge<C><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                                                           tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+        k_msm_merge_heavy<C><<<cdiv(slices, 4), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                                                               tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
         ctx->launches++;
         ctx->launches++;
         ZK_CUDA(ctx, cudaGetLastError());
@@ -526,13 +487,10 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     uint32_t seg = p.nbw / tpw;
     uint32_t bs = tpw < RED_BS ? tpw : RED_BS;
     uint32_t bpw = tpw / bs;
-    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<CI>) * (size_t)bpw * p.W, st));
-    k_msm_reduce<CI><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<CI>>(), p.nbw, seg, partials.as<XYZZ<CI>>());
-    DevBuf win_int;
-    ZK_CUDA(ctx, win_int.alloc(sizeof(XYZZ<CI>) * p.W, st));
-    k_msm_window_final<CI><<<p.W, 32, 0, st>>>(partials.as<XYZZ<CI>>(), bpw, win_int.as<XYZZ<CI>>());
-    k_windows_to_std<C><<<cdiv(p.W, 32), 32, 0, st>>>(win_int.as<XYZZ<CI>>(), reinterpret_cast<XYZZ<C>*>(d_window_sums), p.W);
-    ctx->launches += 3;
+    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<C>) * (size_t)bpw * p.W, st));
+    k_msm_reduce<C><<<dim3(bpw, p.W), bs, 0, st>>>(buckets.as<XYZZ<C>>(), p.nbw, seg, partials.as<XYZZ<C>>());
+    k_msm_window_final<C><<<p.W, 32, 0, st>>>(partials.as<XYZZ<C>>(), bpw, reinterpret_cast<XYZZ<C>*>(d_window_sums));
+    ctx->launches += 2;
     ZK_CUDA(ctx, cudaGetLastError());
     return ZK_OK;
 }
@@ -563,13 +521,10 @@ int msm_to_affine(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, si
 template int msm_to_affine<G1_377Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_377Params>*, int);
 template int msm_to_affine<G1_381Params>(zkaes_ctx*, const void*, const void*, size_t, int, Affine<G1_381Params>*, int);
 
-// arkworks-form bases -> internal packed form (in place when dst == src): for bases that stay resident (the SRS)
+// Kept for the ABI (zkaes_msm_g1_prepare_bases): the kernels read the arkworks form directly, so preparing is the identity.
 template <class C>
 int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n) {
-    if (!n) return ZK_OK;
-    k_bases_to_internal<C><<<cdiv(n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), n);
-    ctx->launches++;
-    ZK_CUDA(ctx, cudaGetLastError());
+    if (n && dst != src) ZK_CUDA(ctx, cudaMemcpyAsync(dst, src, 96 * n, cudaMemcpyDeviceToDevice, ctx->stream));
     return ZK_OK;
 }
 template int msm_bases_to_internal<G1_377Params>(zkaes_ctx*, const void*, void*, size_t);

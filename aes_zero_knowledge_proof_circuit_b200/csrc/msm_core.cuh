@@ -121,7 +121,7 @@ ZK_HD void msm_store_xyzz(XYZZ<C>* p, const XYZZ<C>& v) {
 // infinity before the first chunk).  head / tail / tail_bucket have one slot per slice; tail_bucket[t] names the bucket
 // whose partial sits in tail[t] (MSM_NO_BUCKET if none), which is all the merge pass needs.
 static constexpr uint32_t MSM_NO_BUCKET = 0xffffffffu;
-template <class C>
+template <class C, bool CALL = false>
 ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const uint32_t* offsets, uint32_t nb, const uint32_t* sorted,
                                 const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket) {
     if (t >= n_slices) return;
@@ -171,7 +171,10 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
         const uint32_t e = sorted ? sorted[pos] : pos;  // no index array: the points themselves are in bucket order (pair round output)
         Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
         if (e >> 31) pt.y = pt.y.neg();
-        acc.madd(pt);
+        if (CALL)
+            acc.madd_call(pt);
+        else
+            acc.madd(pt);
     }
     if (open_head)
         msm_store_xyzz<C>(head + t, acc);       // the whole slice lies inside a bucket that began earlier

@@ -7,42 +7,38 @@ template int selftest_field_asm<Fq377>(zkaes_ctx*, int, const void*, const void*
 template int selftest_field_asm<Fr381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template int selftest_field_asm<Fq381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 
-template <class P29>
-__global__ void k_selftest_r29(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n, int op) {
+// variant 2: the out-of-line multiplier the MSM inner loop calls (Fp::mul_call); add / sub as in variant 0
+template <class F>
+__global__ void k_selftest_field_call(const F* a, const F* b, F* out, size_t n, int op) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    using G = Fq29<P29>;
-    uint32_t wa[12], wb[12], wo[12];
-    for (int k = 0; k < 12; ++k) {
-        wa[k] = a[12 * i + k];
-        wb[k] = b[12 * i + k];
-    }
-    G x = G::from_std(wa), y = G::from_std(wb), r;
+    F x = a[i], y = b[i], r;
     if (op == 0) r = x + y;
     else if (op == 1) r = x - y;
-    else r = x * y;
-    r.to_std(wo);
-    for (int k = 0; k < 12; ++k) out[12 * i + k] = wo[k];
+    else r = F::mul_call(x, y);
+    out[i] = r;
 }
-template <class P29>
-int selftest_field_r29(zkaes_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
+template <class F>
+int selftest_field_call(zkaes_ctx* ctx, int op, const void* a, const void* b, void* out, size_t count) {
     cudaStream_t st = ctx->stream;
     DevBuf da, db, dout;
-    size_t bytes = 48 * count;
+    size_t bytes = sizeof(F) * count;
     ZK_CUDA(ctx, da.alloc(bytes, st));
     ZK_CUDA(ctx, db.alloc(bytes, st));
     ZK_CUDA(ctx, dout.alloc(bytes, st));
     ZK_CUDA(ctx, cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, st));
     ZK_CUDA(ctx, cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
-    k_selftest_r29<P29><<<cdiv(count, 128), 128, 0, st>>>(da.as<uint32_t>(), db.as<uint32_t>(), dout.as<uint32_t>(), count, op);
+    k_selftest_field_call<F><<<cdiv(count, 128), 128, 0, st>>>(da.as<F>(), db.as<F>(), dout.as<F>(), count, op);
     ctx->launches++;
     ZK_CUDA(ctx, cudaGetLastError());
     ZK_CUDA(ctx, cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st));
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     return ZK_OK;
 }
-template int selftest_field_r29<Fq377R29Params>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
-template int selftest_field_r29<Fq381R29Params>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_call<Fr377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_call<Fq377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_call<Fr381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+template int selftest_field_call<Fq381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 
 template <class C>
 __global__ void k_selftest_g1(const Affine<C>* a, const Affine<C>* b, Affine<C>* out, size_t n, int op) {

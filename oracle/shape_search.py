@@ -1,0 +1,223 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Search for the R1CS shape the reference's own constants describe.
+
+The only shape data the reference holds is `generate_universal_srs(866_944, 513, 4_062_064, ..)` (src/lib.rs:141): the
+three numbers its debug helper prints (src/helpers/mod.rs:73-80: constraints, instance variables, nnz(A)+nnz(B)+nnz(C)),
+and 513 = 1 + 64*8 says they were read at a 64-byte message.  simpleworks' `shift_left / shift_right / rotate_left`
+(called at src/aes_circuit.rs:184,310-312,369,378 and src/helpers/mod.rs:55) are un-vendored, so their expansion is
+unknown.  This script enumerates parameterised expansions on top of oracle/r1cs_model.py and reports which ones
+reproduce BOTH integers.
+
+  UInt8 shift by k        iterated (k single steps) or direct;  kept bits rewired / fresh Boolean witnesses with or
+                          without booleanity;  shifted-in bits Constant(false) / fresh witnesses with or without
+                          booleanity;  equalities: none / kept bits / all bits;  left and right chosen independently
+  [UInt8; 4] rotate by k  iterated or direct;  rewired / fresh witnesses (with/without booleanity) +- 32 equalities
+  Boolean::or (Is, Is)    lowered to NOT(nor) or to AllocatedBool::or  ((1-a)(1-b) = 1-r)
+  structure               key schedule once (as in the tree today) or once per ECB block (a plausible earlier revision);
+                          MixColumns in 9 or 10 rounds;  public-input handling (booleanity + equality, one, none)
+
+Stage 1 uses the fact that the constraint COUNT is linear in per-gadget costs; stage 2 synthesises the count hits in
+full and compares the non-zero total.   Usage:  python oracle/shape_search.py > profiles/r2_shape_search.txt
+"""
+from __future__ import annotations
+
+import os
+import sys
+from multiprocessing import Pool
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import r1cs_model as m  # noqa: E402
+
+TARGET_CONSTRAINTS, TARGET_INSTANCE, TARGET_NNZ = 866_944, 513, 4_062_064
+NOR_OR = m.OR
+BaseCS = m.CS
+
+
+def or_allocated(cs, a, b):  # ark-r1cs-std 0.3.1 Boolean::or: (Is, Is) -> AllocatedBool::or
+    if a == m.F:
+        return b
+    if b == m.F:
+        return a
+    if a == m.T or b == m.T:
+        return m.T
+    if a[0] == "I" and b[0] == "I":
+        val = a[2] or b[2]
+        r = cs.new_witness(val)
+        cs.enforce([(1, m.ONE), (-1, a[1])], [(1, m.ONE), (-1, b[1])], [(1, m.ONE), (-1, r)])
+        return ("I", r, val)
+    return m.NOT(m.AND(cs, m.NOT(a), m.NOT(b)))
+
+
+def wit(cs, val, kind):  # 'b': Boolean::new_witness (booleanity row), 'n': without booleanity
+    if kind == "b":
+        return m.alloc_bool(cs, val)
+    return ("I", cs.new_witness(val), bool(val))
+
+
+def shift_once(cs, b, k, left, kept, fill, eq):
+    tgt = ([m.F] * k + b[: 8 - k]) if left else (b[k:] + [m.F] * k)
+    fillpos = set(range(k)) if left else set(range(8 - k, 8))
+    out = []
+    for i in range(8):
+        if i in fillpos:
+            out.append(m.F if fill == "c" else wit(cs, 0, fill))
+        else:
+            out.append(tgt[i] if kept == "r" else wit(cs, int(m.bval(tgt[i])), kept))
+    if eq != "none":
+        for i in range(8):
+            if i in fillpos:
+                if eq == "all" and fill != "c":
+                    m.enforce_equal_bool(cs, out[i], m.F)
+            elif kept != "r":
+                m.enforce_equal_bool(cs, out[i], tgt[i])
+    return out
+
+
+def make_shift(spec):
+    iterated, kept, fill, eq = spec
+
+    def f(cs, b, k, left):
+        if iterated:
+            for _ in range(k):
+                b = shift_once(cs, b, 1, left, kept, fill, eq)
+            return b
+        return shift_once(cs, b, k, left, kept, fill, eq)
+    return f
+
+
+def rot_once(cs, arr, k, kind, eq):
+    tgt = arr[k:] + arr[:k]
+    if kind == "r":
+        return tgt
+    out = [[wit(cs, int(m.bval(x)), kind) for x in byte] for byte in tgt]
+    if eq == "all":
+        for nb, byte in zip(out, tgt):
+            for x, y in zip(nb, byte):
+                m.enforce_equal_bool(cs, x, y)
+    return out
+
+
+def make_rot(spec):
+    iterated, kind, eq = spec
+
+    def f(cs, arr, k):
+        if iterated:
+            for _ in range(k):
+                arr = rot_once(cs, arr, 1, kind, eq)
+            return arr
+        return rot_once(cs, arr, k, kind, eq)
+    return f
+
+
+SHIFT_SPECS = [(it, kept, fill, eq) for it in (0, 1) for kept in "rbn" for fill in "cbn" for eq in ("none", "kept", "all")
+               if not (kept == "r" and eq == "kept") and not (kept == "r" and fill == "c" and eq != "none")]
+ROT_SPECS = [(0, "r", "none")] + [(it, kind, eq) for it in (0, 1) for kind in "bn" for eq in ("none", "all")]
+
+
+def install(cs, sl, sr, rot, orv):
+    fl, fr, rt = make_shift(sl), make_shift(sr), make_rot(rot)
+    m.shift_left = lambda b, k: fl(cs, b, k, True)
+    m.shift_right = lambda b, k: fr(cs, b, k, False)
+    m.rot_bytes = lambda arr, k: rt(cs, arr, k)
+    m.OR = or_allocated if orv == "or" else NOR_OR
+
+
+def fresh_byte(cs):
+    return [wit(cs, 0, "n") for _ in range(8)]
+
+
+def xtime_constraints(sl, sr):
+    cs = BaseCS()
+    install(cs, sl, sr, ROT_SPECS[0], "nor")
+    m.gmix_column(cs, [fresh_byte(cs) for _ in range(4)])
+    return (cs.num_constraints - 128) // 4  # 128 = the 16 byte-xors of the column
+
+
+def rot_constraints(spec):
+    out = []
+    for k in (1, 2, 3):
+        cs = BaseCS()
+        make_rot(spec)(cs, [fresh_byte(cs) for _ in range(4)], k)
+        out.append(cs.num_constraints)
+    return tuple(out)
+
+
+def synth(args):
+    """Full synthesis of one hypothesis at `nblocks` ECB blocks -> (constraints, instance vars, (nnzA, nnzB, nnzC))."""
+    nblocks, sl, sr, rot, orv, per_block_keys, mix_rounds, inp = args
+    cs = BaseCS()
+    install(cs, sl, sr, rot, orv)
+    msg = [m.new_byte(cs, v) for v in bytes(range(16 * nblocks))]
+    k = [m.new_byte(cs, v) for v in bytes(16)]
+    rks = None if per_block_keys else m.derive_keys(cs, k)
+    ct = []
+    for blk in range(nblocks):
+        if per_block_keys:
+            rks = m.derive_keys(cs, k)
+        st = m.add_round_key(cs, msg[16 * blk:16 * blk + 16], k)
+        for r in range(1, 10):
+            st = [m.sub_byte(cs, x) for x in st]
+            st = m.shift_rows(st)
+            st = m.mix_columns(cs, st)
+            st = m.add_round_key(cs, st, rks[r])
+        st = [m.sub_byte(cs, x) for x in st]
+        st = m.shift_rows(st)
+        if mix_rounds == 10:
+            m.mix_columns(cs, st)  # computed and dropped
+        st = m.add_round_key(cs, st, rks[10])
+        ct += st
+    for b in ct:
+        if inp == 256:
+            p = m.new_byte(cs, m.byte_value(b), "i")
+            for x, y in zip(p, b):
+                m.enforce_equal_bool(cs, x, y)
+        elif inp == 128:
+            m.new_byte(cs, m.byte_value(b), "i")
+        else:
+            for x in b:
+                cs.new_input(int(m.bval(x)))
+    A, B, C = cs.matrices()
+    return args, cs.num_constraints, len(cs.inst_vals), (sum(map(len, A)), sum(map(len, B)), sum(map(len, C)))
+
+
+def main():
+    print(f"target (src/lib.rs:141): constraints {TARGET_CONSTRAINTS}, instance {TARGET_INSTANCE}, nnz(A+B+C) {TARGET_NNZ}\n")
+    print("== the tree as it stands (key schedule once, 9 MixColumns rounds), one expansion for both shift directions")
+    jobs = [(4, s, s, r, orv, 0, 9, 256) for orv in ("nor", "or") for s in SHIFT_SPECS if s[0] == 0 for r in ROT_SPECS if r[0] == 0]
+    with Pool() as pool:
+        for args, c, inst, n in pool.imap(synth, jobs, chunksize=4):
+            print(f"or={args[4]:3s} shift={args[1]} rot={args[3]}  constraints {c} ({c - TARGET_CONSTRAINTS:+d})  "
+                  f"instance {inst}  nnz {sum(n)} ({sum(n) - TARGET_NNZ:+d})  A/B/C {n}")
+    # ---- stage 1: constraint count is linear in the gadget costs
+    xs = {}
+    for sl in SHIFT_SPECS:
+        for sr in SHIFT_SPECS:
+            xs.setdefault(xtime_constraints(sl, sr), []).append((sl, sr))
+    rots = {sp: rot_constraints(sp) for sp in ROT_SPECS}
+    print(f"\n== stage 1: {sum(map(len, xs.values()))} shift expansions -> {len(xs)} distinct xtime costs; rotate costs {rots}")
+    hits = []
+    for per_block_keys in (0, 1):
+        nd = 4 if per_block_keys else 1
+        for mix_rounds in (9, 10):
+            for inp in (256, 128, 0):
+                base = 128 + nd * 36640 + 4 * (128 + 160 * 884 + 11 * 128 + mix_rounds * 512 + inp)
+                for X, specs in sorted(xs.items()):
+                    for rsp, (r1, r2, r3) in rots.items():
+                        if base + 4 * mix_rounds * 16 * X + nd * 10 * r1 + 40 * (r1 + r2 + r3) == TARGET_CONSTRAINTS:
+                            print(f"count hit: key schedule per block={per_block_keys} mix rounds={mix_rounds} inputs={inp} "
+                                  f"xtime={X} rot={rsp} ({len(specs)} shift expansions)")
+                            hits += [(4, sl, sr, rsp, orv, per_block_keys, mix_rounds, inp) for sl, sr in specs for orv in ("nor", "or")]
+    # ---- stage 2: full synthesis of every count hit
+    print(f"\n== stage 2: {len(hits)} full syntheses")
+    best = None
+    with Pool() as pool:
+        for args, c, inst, n in pool.imap(synth, hits, chunksize=4):
+            d = sum(n) - TARGET_NNZ
+            flag = "  <== BOTH INTEGERS" if (c == TARGET_CONSTRAINTS and d == 0 and inst == TARGET_INSTANCE) else ""
+            print(f"{args[1:]}  constraints {c} ({c - TARGET_CONSTRAINTS:+d}) instance {inst} nnz {sum(n)} ({d:+d}){flag}")
+            if c == TARGET_CONSTRAINTS and (best is None or abs(d) < abs(best[0])):
+                best = (d, args[1:])
+    print(f"\nclosest count hit: nnz off by {best[0]:+d} with {best[1]}" if best else "\nno count hit")
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,7 @@ from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 pytestmark = pytest.mark.gpu
 CURVES = [377, 381]
+TUNING_DEFAULTS = {"msm_acc_blocks": 3, "msm_window_max": 22, "msm_pair_round": 0, "msm_madd_call": 1}  # csrc/common.cuh zkaes_ctx
 
 
 def rand_fq(rng, curve, n):
@@ -40,22 +41,25 @@ def test_device_field_ops(ctx, oracle, curve, field, variant):
 
 
 @pytest.mark.parametrize("curve", CURVES)
-def test_device_fq_radix29_form(ctx, oracle, curve):
-    """Fq through the MSM kernels' internal radix-2^29 form (from_std -> op -> to_std) equals the arkworks-form result"""
-    rng = np.random.default_rng(curve + 29)
-    p = FQ[curve]
+@pytest.mark.parametrize("field", [0, 1])
+def test_device_out_of_line_multiplier(ctx, oracle, curve, field):
+    """Fp::mul_call -- the one out-of-line copy of the Montgomery multiplier that the MSM inner loop and the cold curve formulas
+    call -- gives the oracle's products (selftest variant 2)"""
+    rng = np.random.default_rng(curve + 29 + field)
+    p = (FR if field == 0 else FQ)[curve]
+    nl = 4 if field == 0 else 6
     n = 1 << 14
-    a, b = rand_fq(rng, curve, n), rand_fq(rng, curve, n)
-    edge = ints_to_limbs([0, 1, p - 1, p - 2, (1 << 376) % p, p >> 1], 6)
+    a, b = (rand_fr if field == 0 else rand_fq)(rng, curve, n), (rand_fr if field == 0 else rand_fq)(rng, curve, n)
+    edge = ints_to_limbs([0, 1, p - 1, p - 2, (1 << (64 * nl - 8)) % p, p >> 1], nl)
     a[: len(edge)] = edge
     b[: len(edge)] = edge[::-1]
     a[len(edge): 2 * len(edge)] = edge
     b[len(edge): 2 * len(edge)] = edge
     for op in (0, 1, 2):
-        got = ctx.selftest_field(curve, 1, op, 2, a, b)
-        exp = oracle.field_op(curve, 1, op, a, b)
+        got = ctx.selftest_field(curve, field, op, 2, a, b)
+        exp = oracle.field_op(curve, field, op, a, b)
         bad = np.nonzero((got != exp).any(axis=1))[0]
-        assert bad.size == 0, f"curve {curve} op {op}: {bad.size} mismatches, first at {bad[:4]}"
+        assert bad.size == 0, f"curve {curve} field {field} op {op}: {bad.size} mismatches, first at {bad[:4]}"
 
 
 @pytest.mark.parametrize("curve", CURVES)
@@ -149,7 +153,8 @@ def test_msm_window_sizes(ctx, oracle, window):
 
 @pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
                                     {"msm_pair_round": 1, "msm_window_max": 10}, {"msm_pair_round": 2, "msm_window_max": 10},
-                                    {"msm_pair_round": 3, "msm_window_max": 9}])
+                                    {"msm_pair_round": 3, "msm_window_max": 9}, {"msm_madd_call": 0}, {"msm_madd_call": 1},
+                                    {"msm_madd_call": 1, "msm_acc_blocks": 4}, {"msm_madd_call": 0, "msm_acc_blocks": 4}])
 def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
     """70,000 terms: large enough for the batched-affine pair round (on by default) -- checked against the oracle with the
     round on and off, with degenerate pairs in the buckets (equal points, opposite points, infinity, repeated scalars)."""
@@ -170,9 +175,8 @@ def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
             ctx.set_tuning(k, v)
         assert (ctx.msm_g1(curve, bases, sc) == exp).all()
     finally:
-        ctx.set_tuning("msm_acc_blocks", 3)
-        ctx.set_tuning("msm_window_max", 22)
-        ctx.set_tuning("msm_pair_round", 0)
+        for k, v in TUNING_DEFAULTS.items():
+            ctx.set_tuning(k, v)
     with pytest.raises(Exception):
         ctx.set_tuning("no_such_knob", 1)
 

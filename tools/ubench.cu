@@ -46,6 +46,33 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, int iters, uint32_t
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- FP64 pipe (round 2): DFMA issue rate alone, with a 64-bit integer add per DFMA (the hi/lo limb-product scheme adds the
+// raw bit patterns of the DFMA results as integers), and DFMA interleaved with IMAD.WIDE (do the two pipes overlap?)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe64(double* out, int iters, double seed) {
+    double d[8], b = seed + 1.0, c = seed * 3.0 + threadIdx.x;
+    uint64_t w[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d[i] = c + i * 977.0; w[i] = (uint64_t)(threadIdx.x * 2654435761u + i) << 7; acc[i] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (MODE == 0 || MODE == 1 || MODE == 2 || MODE == 3) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(b), "d"(c));
+                if (MODE == 1) asm volatile("add.u64 %0, %0, %1;" : "+l"(acc[i]) : "l"((uint64_t)__double_as_longlong(d[i])));
+                if (MODE == 2) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 3) & 7]), "r"((uint32_t)threadIdx.x | 1u));
+                if (MODE == 3 && (i & 1)) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[(i + 3) & 7]), "r"((uint32_t)threadIdx.x | 1u));
+                if (MODE == 4) asm volatile("add.rz.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(b));
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += d[i] + (double)(w[i] ^ acc[i]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---- Fq multiplier variants -------------------------------------------------------------------------------
 __constant__ uint32_t c_mod[12];
 
@@ -89,50 +116,32 @@ __global__ void __launch_bounds__(128) k_fqmul(uint32_t* out, const uint32_t* gm
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int BS>
+// CALL = 0: ten inlined products per mixed addition (round 1); 1: ten calls of one out-of-line multiplier (XYZZ::madd_call)
+template <int BS, int CALL>
 __global__ void __launch_bounds__(BS) k_madd(const G1Affine377* pts, int npts, G1XYZZ377* out, int iters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     G1XYZZ377 acc = G1XYZZ377::from_affine(pts[t % npts]);
     for (int it = 0; it < iters; ++it) {
         G1Affine377 p = pts[(t * 7 + it * 13 + 1) % npts];
-        acc.madd(p);
+        if (CALL) acc.madd_call(p); else acc.madd(p);
     }
     out[t] = acc;
 }
-
-// same loop in the radix-2^29 internal form (fq29.cuh); MINB = min blocks per SM for __launch_bounds__ (register cap)
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB) k_madd29(const G1Affine377* pts, int npts, XYZZ<G1_377R29>* out, int iters) {
-    using Fq = Fq29<Fq377R29Params>;
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    Affine<G1_377R29> p0;
-    p0.x = Fq::from_std(pts[t % npts].x.v);
-    p0.y = Fq::from_std(pts[t % npts].y.v);
-    XYZZ<G1_377R29> acc = XYZZ<G1_377R29>::from_affine(p0);
-    for (int it = 0; it < iters; ++it) {
-        const G1Affine377& q = pts[(t * 7 + it * 13 + 1) % npts];
-        Affine<G1_377R29> p;
-        p.x = Fq::unpack(q.x.v);   // treat the stored words as already-internal representatives (any field elements do for timing)
-        p.y = Fq::unpack(q.y.v);
-        p.x.v[12] &= 0xffffff; p.y.v[12] &= 0xffffff;  // keep them < p
-        acc.madd(p);
-    }
-    out[t] = acc;
-}
+// the out-of-line multiplier alone (call overhead included), ILP independent chains per thread
 template <int ILP>
-__global__ void __launch_bounds__(128) k_fqmul29(uint32_t* out, int iters) {
-    using F = Fq29<Fq377R29Params>;
+__global__ void __launch_bounds__(128) k_fqmul_call(uint32_t* out, int iters) {
+    using F = Fq377;
     F x[ILP], y;
     for (int k = 0; k < ILP; ++k)
-        for (int i = 0; i < 13; ++i) x[k].v[i] = ((threadIdx.x + 1) * (i + 3 + k) * 2654435761u) >> (i == 12 ? 9 : 3);
-    for (int i = 0; i < 13; ++i) y.v[i] = ((threadIdx.x * 31 + 7) * (i + 11) * 40503u) >> (i == 12 ? 9 : 3);
+        for (int i = 0; i < 12; ++i) x[k].v[i] = (threadIdx.x + 1) * (i + 3 + k) * 2654435761u >> (i == 11 ? 8 : 0);
+    for (int i = 0; i < 12; ++i) y.v[i] = (blockIdx.x + 7) * (i + 11) * 40503u >> (i == 11 ? 8 : 0);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < ILP; ++k) x[k] = x[k] * y;
+        for (int k = 0; k < ILP; ++k) x[k] = F::mul_call(x[k], y);
     }
     uint32_t s = 0;
     for (int k = 0; k < ILP; ++k)
-        for (int i = 0; i < 13; ++i) s ^= x[k].v[i];
+        for (int i = 0; i < 12; ++i) s ^= x[k].v[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -169,6 +178,17 @@ int main() {
         printf("pipe %-18s: %.2f Tops/s  (%.1f ops/clk/SM at %d MHz nominal)\n", names[M], ops / ms / 1e9, ops / (ms * 1e-3) / sms / (clk_khz * 1e3), clk_khz / 1000); }
     RUN_PIPE(0) RUN_PIPE(1) RUN_PIPE(2) RUN_PIPE(3) RUN_PIPE(4) RUN_PIPE(5) RUN_PIPE(6)
 
+    {
+        const char* n64[] = {"DFMA.RZ", "DFMA.RZ + IADD.64 each", "DFMA.RZ + IMAD.WIDE each", "DFMA.RZ + IMAD.WIDE per 2", "DADD.RZ"};
+        double* o64 = reinterpret_cast<double*>(out);
+#define RUN_PIPE64(M, PER) { \
+        int iters = 2000, blocks = sms * 8; \
+        k_pipe64<M><<<blocks, 256>>>(o64, 10, 1.0); \
+        cudaEventRecord(e0); k_pipe64<M><<<blocks, 256>>>(o64, iters, 3.0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
+        double ops = (double)blocks * 256 * iters * 64.0; float ms = time_ms(e0, e1); \
+        printf("pipe64 %-26s: %.2f T DFMA/s  (%.1f DFMA/clk/SM at %d MHz nominal; %s)\n", n64[M], ops / ms / 1e9, ops / (ms * 1e-3) / sms / (clk_khz * 1e3), clk_khz / 1000, PER); }
+        RUN_PIPE64(0, "alone") RUN_PIPE64(1, "one 64-bit integer add per DFMA") RUN_PIPE64(2, "one IMAD.WIDE per DFMA") RUN_PIPE64(3, "one IMAD.WIDE per two DFMA") RUN_PIPE64(4, "DADD instead of DFMA")
+    }
     uint32_t hmod[12];
     for (int i = 0; i < 12; ++i) hmod[i] = Fq377Params::MOD(i);
     CK(cudaMemcpyToSymbol(c_mod, hmod, sizeof(hmod)));
@@ -191,34 +211,24 @@ int main() {
     k_make_pts<<<npts / 64, 64>>>(pts, npts);
     CK(cudaDeviceSynchronize());
     G1XYZZ377* acc; CK(cudaMalloc(&acc, sizeof(G1XYZZ377) * sms * 16 * 256));
-#define RUN_MADD(BS) { \
+#define RUN_MADD(BS, CALL) { \
         int iters = 500; \
         for (int bps = 1; bps <= 8; bps *= 2) { \
             int blocks = sms * bps; \
-            k_madd<BS><<<blocks, BS>>>(pts, npts, acc, 3); \
-            cudaEventRecord(e0); k_madd<BS><<<blocks, BS>>>(pts, npts, acc, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
+            k_madd<BS, CALL><<<blocks, BS>>>(pts, npts, acc, 3); \
+            cudaEventRecord(e0); k_madd<BS, CALL><<<blocks, BS>>>(pts, npts, acc, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
             double n = (double)blocks * BS * iters; float ms = time_ms(e0, e1); \
-            printf("madd bs=%d blocks/SM=%d: %.1f Mmadd/s (%.0f clk/SM/madd)\n", BS, bps, n / ms / 1e3, (ms * 1e-3) * clk_khz * 1e3 * sms / n); } }
-    RUN_MADD(64) RUN_MADD(128)
-#define RUN_MUL29(ILP) { \
+            printf("madd %s bs=%d blocks/SM=%d: %.1f Mmadd/s (%.0f clk/SM/madd)\n", CALL ? "out-of-line products" : "inlined products    ", BS, bps, n / ms / 1e3, (ms * 1e-3) * clk_khz * 1e3 * sms / n); } }
+    RUN_MADD(64, 0) RUN_MADD(128, 0) RUN_MADD(64, 1) RUN_MADD(128, 1)
+#define RUN_MULC(ILP) { \
         int iters = 2000; \
         for (int bps = 2; bps <= 8; bps *= 2) { \
             int blocks = sms * bps; \
-            k_fqmul29<ILP><<<blocks, 128>>>(out, 5); \
-            cudaEventRecord(e0); k_fqmul29<ILP><<<blocks, 128>>>(out, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
+            k_fqmul_call<ILP><<<blocks, 128>>>(out, 5); \
+            cudaEventRecord(e0); k_fqmul_call<ILP><<<blocks, 128>>>(out, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
             double muls = (double)blocks * 128 * iters * ILP; float ms = time_ms(e0, e1); \
-            printf("fqmul29 ilp=%d blocks/SM=%d: %.2f Gmul/s (%.1f clk/SM/mul)\n", ILP, bps, muls / ms / 1e6, (ms * 1e-3) * clk_khz * 1e3 * sms / muls); } }
-    RUN_MUL29(1) RUN_MUL29(2)
-    XYZZ<G1_377R29>* acc29; CK(cudaMalloc(&acc29, sizeof(XYZZ<G1_377R29>) * sms * 16 * 256));
-#define RUN_MADD29(BS, MINB) { \
-        int iters = 500; \
-        for (int bps = 1; bps <= 8; bps *= 2) { \
-            int blocks = sms * bps; \
-            k_madd29<BS, MINB><<<blocks, BS>>>(pts, npts, acc29, 3); \
-            cudaEventRecord(e0); k_madd29<BS, MINB><<<blocks, BS>>>(pts, npts, acc29, iters); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
-            double n = (double)blocks * BS * iters; float ms = time_ms(e0, e1); \
-            printf("madd29 bs=%d minb=%d blocks/SM=%d: %.1f Mmadd/s (%.0f clk/SM/madd)\n", BS, MINB, bps, n / ms / 1e3, (ms * 1e-3) * clk_khz * 1e3 * sms / n); } }
-    RUN_MADD29(128, 1) RUN_MADD29(128, 2) RUN_MADD29(128, 3) RUN_MADD29(128, 4) RUN_MADD29(64, 6)
+            printf("fqmul out-of-line ilp=%d blocks/SM=%d: %.2f Gmul/s (%.1f clk/SM/mul)\n", ILP, bps, muls / ms / 1e6, (ms * 1e-3) * clk_khz * 1e3 * sms / muls); } }
+    RUN_MULC(1) RUN_MULC(2)
     CK(cudaDeviceSynchronize());
     return 0;
 }
