@@ -5,9 +5,10 @@
 // Same inputs (affine bases, canonical 256-bit scalars < r), same mathematical result; the schedule is GPU-first
 // (per-thread bodies and their rationale: msm_core.cuh):
 //
-//   1. k_msm_digits    : s -> min(s, r-s), signed c-bit digits, histogram of (window, |digit|) keys   [HBM: 32 B/term]
+//   1. k_msm_digits_all: s -> min(s, r-s), all W signed c-bit digits in one carry walk, window-major digit array   [HBM: 32 B/term read, 4 W written]
+//      k_msm_sort_pass : histogram of (window, |digit|) keys over the digit array, one grid row per window
 //   2. k_scan_*        : exclusive scan of the histogram -> bucket offsets (nb + 1 entries)
-//   3. k_msm_digits    : counting-sort scatter of point indices (sign in bit 31) by bucket key
+//   3. k_msm_sort_pass : counting-sort scatter of point indices (sign in bit 31) by bucket key
 //   4. k_msm_accumulate: equal-length slices of the sorted entries, one thread each, XYZZ += affine (8M+2S)  [ALU bound]
 //   5. k_msm_merge     : buckets cut by slice boundaries = tail + heads (one thread per slice)
 //   6. k_msm_reduce / k_msm_window_final: per-window sum_k k*B_k -> W window sums (XYZZ) on device
@@ -40,38 +41,43 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t i, s
     }
 }
 
-// pass 1 (sorted == nullptr): histogram.  pass 2: write sorted indices.  grid = (scalars / 256, W): blockIdx.y is the
-// window, so the blocks of one window run together and its 2^(c-1) counters (8 MB at c = 22) stay L2-resident under the
-// atomics; every (scalar, window) thread re-reads its 32-byte scalar (W x 32 B per term of L2/HBM traffic instead of
-// DRAM-missing atomics over all W 2^(c-1) counters).
+// Digits: one thread per scalar -- load (32 B), leave Montgomery form, fold to min(s, r - s), one carry walk over all W windows
+// (msm_digits_all), W coalesced 4-byte stores into the window-major digit array (digits[w * m + i]).
 template <class FrP>
-__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
-                                                    MsmPlan p, int w_base, uint32_t* __restrict__ counts,
-                                                    const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_msm_digits_all(const uint32_t* __restrict__ scalars, size_t n, size_t stride, int mont, MsmPlan p,
+                                                        uint32_t* __restrict__ digits) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
     load_scalar<FrP>(scalars, i, stride, mont, s);
     const uint32_t flip = msm_fold_scalar<FrP>(s);
-    const int w = w_base + blockIdx.y;
-    uint32_t neg;
-    const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
-    if (!d) return;
-    const uint32_t key = (uint32_t)blockIdx.y * p.nbw + d - 1;  // counts / offsets start at window w_base
+    msm_digits_all(s, flip, p, digits + i, n);
+}
+
+// Counting sort by (window, bucket) over the precomputed digits.  pass 1 (sorted == nullptr): histogram.  pass 2: write sorted
+// indices.  grid = (scalars / 256, windows): blockIdx.y is the window, so the blocks of one window run together and its 2^(c-1)
+// counters (8 MB at c = 22) stay L2-resident under the atomics; each thread reads ONE digit word (4 B, coalesced).
+__global__ void __launch_bounds__(256) k_msm_sort_pass(const uint32_t* __restrict__ digits, size_t n, uint32_t idx_base, uint32_t nbw, int w_base,
+                                                       uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                       uint32_t* __restrict__ sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t e = digits[(size_t)(w_base + blockIdx.y) * n + i];
+    if (e == MSM_DIGIT_NONE) return;
+    const uint32_t key = (uint32_t)blockIdx.y * nbw + (e & 0x7fffffffu);  // counts / offsets start at window w_base
     const uint32_t pos = atomicAdd(&counts[key], 1u);
-    if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
+    if (sorted) sorted[offsets[key] + pos] = (idx_base + (uint32_t)i) | (e & 0x80000000u);
 }
 
 // The partly filled top window (253 = 11 x 22 + 11 bits at c = 22) has only 2^11 possible digits: 2^26 global atomics on
 // 2^11 addresses serialise in L2 (9.2 ms per pass against 0.7-2.5 ms for a full window, profiles/
-// r1_launches_msm_2p26_pair_round.txt).  For such a window each block histograms a tile of 16,384 scalars in shared
+// r1_launches_msm_2p26_pair_round.txt).  For such a window each block histograms a tile of 16,384 digits in shared
 // memory and touches every global counter once; positions inside the tile come from shared-memory cursors.
 static constexpr int DIG_TILE_ITERS = 64;  // x 256 threads
 static constexpr uint32_t DIG_SMALL_KEYS = 4096;
-template <class FrP>
-__global__ void __launch_bounds__(256) k_msm_digits_small(const uint32_t* __restrict__ scalars, size_t n, size_t stride, uint32_t idx_base, int mont,
-                                                          MsmPlan p, int w, uint32_t nkeys, uint32_t* __restrict__ counts,
-                                                          const uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_msm_sort_pass_small(const uint32_t* __restrict__ digits_w, size_t n, uint32_t idx_base, uint32_t nkeys,
+                                                             uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ sorted) {
     __shared__ uint32_t hist[DIG_SMALL_KEYS], cursor[DIG_SMALL_KEYS];
     for (uint32_t k = threadIdx.x; k < nkeys; k += 256) hist[k] = 0;
     __syncthreads();
@@ -79,11 +85,8 @@ __global__ void __launch_bounds__(256) k_msm_digits_small(const uint32_t* __rest
     for (int it = 0; it < DIG_TILE_ITERS; ++it) {
         const size_t i = tile + (size_t)it * 256 + threadIdx.x;
         if (i >= n) break;
-        uint32_t s[8], neg;
-        load_scalar<FrP>(scalars, i, stride, mont, s);
-        const uint32_t flip = msm_fold_scalar<FrP>(s);
-        const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
-        if (d) atomicAdd(&hist[d - 1], 1u);
+        const uint32_t e = digits_w[i];
+        if (e != MSM_DIGIT_NONE) atomicAdd(&hist[e & 0x7fffffffu], 1u);
     }
     __syncthreads();
     for (uint32_t k = threadIdx.x; k < nkeys; k += 256) {
@@ -95,13 +98,11 @@ __global__ void __launch_bounds__(256) k_msm_digits_small(const uint32_t* __rest
     for (int it = 0; it < DIG_TILE_ITERS; ++it) {
         const size_t i = tile + (size_t)it * 256 + threadIdx.x;
         if (i >= n) break;
-        uint32_t s[8], neg;
-        load_scalar<FrP>(scalars, i, stride, mont, s);
-        const uint32_t flip = msm_fold_scalar<FrP>(s);
-        const uint32_t d = msm_digit_of_window(s, flip, p, w, &neg);
-        if (!d) continue;
-        const uint32_t pos = atomicAdd(&cursor[d - 1], 1u);
-        sorted[offsets[d - 1] + pos] = (idx_base + (uint32_t)i) | (neg << 31);
+        const uint32_t e = digits_w[i];
+        if (e == MSM_DIGIT_NONE) continue;
+        const uint32_t k = e & 0x7fffffffu;
+        const uint32_t pos = atomicAdd(&cursor[k], 1u);
+        sorted[offsets[k] + pos] = (idx_base + (uint32_t)i) | (e & 0x80000000u);
     }
 }
 // number of distinct |digits| the top window can take, or 0 if it is a full window / too large for the shared-memory path
@@ -110,22 +111,27 @@ static uint32_t msm_small_top_keys(const MsmPlan& p, int fr_bits) {
     if (top_bits >= p.c || top_bits < 1 || ((uint32_t)1 << top_bits) > DIG_SMALL_KEYS) return 0;
     return (uint32_t)1 << top_bits;
 }
-// histogram (sorted == nullptr) or scatter pass over windows [w0, w0 + nw); counts / offsets point at window w0's first bucket
 template <class FrP>
-static void msm_launch_digits(zkaes_ctx* ctx, const uint32_t* sc, size_t m, size_t stride, uint32_t idx_base, int mont, const MsmPlan& p, int w0, int nw,
-                              uint32_t* counts, const uint32_t* offsets, uint32_t* sorted) {
+static void msm_launch_digits_all(zkaes_ctx* ctx, const uint32_t* sc, size_t m, size_t stride, int mont, const MsmPlan& p, uint32_t* digits) {
+    k_msm_digits_all<FrP><<<cdiv(m, 256), 256, 0, ctx->stream>>>(sc, m, stride, mont, p, digits);
+    ctx->launches++;
+}
+// histogram (sorted == nullptr) or scatter pass over windows [w0, w0 + nw) of the digit array; counts / offsets point at window w0's
+// first bucket
+static void msm_launch_sort_pass(zkaes_ctx* ctx, const uint32_t* digits, size_t m, uint32_t idx_base, const MsmPlan& p, int fr_bits, int w0, int nw,
+                                 uint32_t* counts, const uint32_t* offsets, uint32_t* sorted) {
     cudaStream_t st = ctx->stream;
-    const uint32_t small = msm_small_top_keys(p, FrP::BITS);
+    const uint32_t small = msm_small_top_keys(p, fr_bits);
     int n_full = nw;
     if (small && w0 + nw == p.W) {  // the range ends with the partly filled top window
         --n_full;
         const size_t off = (size_t)n_full * p.nbw;
-        k_msm_digits_small<FrP><<<cdiv(m, 256 * DIG_TILE_ITERS), 256, 0, st>>>(sc, m, stride, idx_base, mont, p, p.W - 1, small, counts + off,
-                                                                               offsets ? offsets + off : nullptr, sorted);
+        k_msm_sort_pass_small<<<cdiv(m, 256 * DIG_TILE_ITERS), 256, 0, st>>>(digits + (size_t)(p.W - 1) * m, m, idx_base, small, counts + off,
+                                                                             offsets ? offsets + off : nullptr, sorted);
         ctx->launches++;
     }
     if (n_full > 0) {
-        k_msm_digits<FrP><<<dim3(cdiv(m, 256), n_full), 256, 0, st>>>(sc, m, stride, idx_base, mont, p, w0, counts, offsets, sorted);
+        k_msm_sort_pass<<<dim3(cdiv(m, 256), n_full), 256, 0, st>>>(digits, m, idx_base, p.nbw, w0, counts, offsets, sorted);
         ctx->launches++;
     }
 }
@@ -332,7 +338,8 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
     const size_t max_final = (max_entries2 >> R) + 1;    // sums left for the accumulation
     const uint32_t L = msm_slice_len(max_final);
     const size_t max_slices = (max_final + L - 1) / L + 1;
-    DevBuf counts, padded, off2, poff, sorted2, prefix, tprod, scratch, sums[2], head, tail, tail_bucket;
+    DevBuf counts, padded, off2, poff, sorted2, prefix, tprod, scratch, sums[2], head, tail, tail_bucket, digits;
+    ZK_CUDA(ctx, digits.alloc(sizeof(uint32_t) * chunk_max * p.W, st));
     ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
     ZK_CUDA(ctx, padded.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
     ZK_CUDA(ctx, off2.alloc(sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
@@ -352,17 +359,18 @@ int msm_accumulate_paired(zkaes_ctx* ctx, const uint32_t* bases, const uint32_t*
         // upper bounds of this chunk's counts (the kernels read the exact ones from off2[nbw])
         const size_t entries_ub = ((m + (size_t)(align - 1) * p.nbw) + align) & ~(size_t)(align - 1);
         const size_t slices = ((entries_ub >> R) + L) / L;
+        msm_launch_digits_all<FrP>(ctx, sc, m, scalar_stride, scalars_mont, p, digits.as<uint32_t>());
         for (int w = 0; w < p.W; ++w) {
             ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nbw + 1), st));
-            msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), nullptr, nullptr);
+            msm_launch_sort_pass(ctx, digits.as<uint32_t>(), m, (uint32_t)base, p, FrP::BITS, w, 1, counts.as<uint32_t>(), nullptr, nullptr);
             k_pad_pow2<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(counts.as<uint32_t>(), padded.as<uint32_t>(), p.nbw + 1, align);
             ctx->launches++;
             ZK_TRY(exclusive_scan_u32(ctx, padded.as<uint32_t>(), off2.as<uint32_t>(), p.nbw + 1));
             k_shift_right<<<cdiv((size_t)p.nbw + 1, 256), 256, 0, st>>>(off2.as<uint32_t>(), poff.as<uint32_t>(), p.nbw + 1, R);
             ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nbw, st));
             ZK_CUDA(ctx, cudaMemsetAsync(sorted2.p, 0xff, sizeof(uint32_t) * entries_ub, st));  // MSM_NONE in the padding slots
-            msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, w, 1, counts.as<uint32_t>(), off2.as<uint32_t>(),
-                                   sorted2.as<uint32_t>());
+            msm_launch_sort_pass(ctx, digits.as<uint32_t>(), m, (uint32_t)base, p, FrP::BITS, w, 1, counts.as<uint32_t>(), off2.as<uint32_t>(),
+                                 sorted2.as<uint32_t>());
             ctx->launches++;
             const uint32_t* idx = sorted2.as<uint32_t>();
             const uint32_t* pts = bases;
@@ -431,13 +439,14 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     // the pair round (batched-affine first level) pays off once buckets hold several entries; it needs the field inversion,
     // which only the default (arkworks-limb) form of the curve arithmetic provides
     const bool paired = ctx->msm_pair_round > 0 && n >= ((size_t)1 << 16) && (n / p.nbw) >> ctx->msm_pair_round >= 2;
-    DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket;
+    DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket, digits;
     ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
     ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<C>) * (size_t)p.nb, st));  // all-zero XYZZ = infinity
     if (!paired) {
         ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
         ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
         ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * max_entries, st));
+        ZK_CUDA(ctx, digits.alloc(sizeof(uint32_t) * max_entries, st));  // window-major signed digits of the chunk, computed once
         ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<C>) * max_slices, st));
         ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<C>) * max_slices, st));
         ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * max_slices, st));
@@ -452,12 +461,13 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
         size_t m = n - base < chunk_max ? n - base : chunk_max;
         const uint32_t* sc = scalars + 8 * base * scalar_stride;
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nb + 1), st));
-        msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, 0, p.W, counts.as<uint32_t>(), nullptr, nullptr);
+        msm_launch_digits_all<FrP>(ctx, sc, m, scalar_stride, scalars_mont, p, digits.as<uint32_t>());
+        msm_launch_sort_pass(ctx, digits.as<uint32_t>(), m, (uint32_t)base, p, FrP::BITS, 0, p.W, counts.as<uint32_t>(), nullptr, nullptr);
         // scanning nb + 1 counters (the last one is zero) leaves the total entry count in offsets[nb]
         ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb + 1));
         ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
-        msm_launch_digits<FrP>(ctx, sc, m, scalar_stride, (uint32_t)base, scalars_mont, p, 0, p.W, counts.as<uint32_t>(), offsets.as<uint32_t>(),
-                               sorted.as<uint32_t>());
+        msm_launch_sort_pass(ctx, digits.as<uint32_t>(), m, (uint32_t)base, p, FrP::BITS, 0, p.W, counts.as<uint32_t>(), offsets.as<uint32_t>(),
+                             sorted.as<uint32_t>());
         const size_t slices = (size_t)(((uint64_t)m * p.W + L - 1) / L);  // upper bound: zero digits produce no entry
         zkaes_ctx::ProfSpan span{};
         if (ctx->prof) {

@@ -68,6 +68,27 @@ ZK_HD uint32_t msm_digit_of_window(const uint32_t* s, uint32_t flip, const MsmPl
     return d;
 }
 
+// All W signed digits of one scalar in ONE walk (the carry propagates once).  Encoding of out[w]: MSM_DIGIT_NONE for a zero digit,
+// else (|d| - 1) | sign << 31 -- i.e. the bucket index inside the window and the sign that goes into bit 31 of the sorted entry.
+// Round 1 recomputed the digit of window w by walking windows 0..w in every (scalar, window) thread of both sort passes, after a
+// fresh Montgomery conversion each time: 9 % of the prover's kernel time for a 32 B/term pass.
+static constexpr uint32_t MSM_DIGIT_NONE = 0xffffffffu;
+ZK_HD void msm_digits_all(const uint32_t* s, uint32_t flip, const MsmPlan& p, uint32_t* out, size_t out_stride) {
+    const uint32_t half = 1u << (p.c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < p.W; ++w) {
+        uint32_t d = msm_scalar_bits(s, w * p.c, p.c) + carry, neg = 0;
+        if (d > half) {
+            d = (1u << p.c) - d;
+            carry = 1;
+            neg = 1;
+        } else {
+            carry = 0;
+        }
+        out[(size_t)w * out_stride] = d ? ((d - 1) | ((neg ^ flip) << 31)) : MSM_DIGIT_NONE;
+    }
+}
+
 // ---- 128-bit moves of points -----------------------------------------------------------------------------------------
 template <class C>
 ZK_HD Affine<C> msm_load_affine(const uint32_t* bases, uint32_t idx) {

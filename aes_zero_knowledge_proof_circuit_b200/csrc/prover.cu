@@ -504,7 +504,7 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         comm_to_bytes(cm, pk.vk_bytes);
     }
     // the VerifyingKey half of synthesize_keys' result (src/lib.rs:138): index vk + KZG verifier key + the two shift powers
-    pk.vk_full = build_verifying_key(pk.vk_bytes, x, pk.D, tau, gamma, {h - 2, k - 2});
+    pk.vk_full = build_verifying_key(nvar, c.num_constraints, nnz_max, x, pk.index_comms, pk.D, tau, gamma, {h - 2, k - 2});
     PhaseTrace(st).mark("synthesize_keys (end)");
     ZK_CUDA(ctx, cudaStreamSynchronize(st));
     *out = pkp.release();

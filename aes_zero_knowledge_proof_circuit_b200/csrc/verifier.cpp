@@ -10,6 +10,7 @@
 #include "verifier.h"
 #include "../../include/zkaes_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 
@@ -25,7 +26,7 @@ using XY = XYZZ<G1_377Params>;
 using pairing::Fq2;
 using pairing::G2A;
 
-constexpr char VK_MAGIC[8] = {'Z', 'K', 'A', 'E', 'S', 'V', 'K', '1'};
+constexpr uint64_t SIZE_LIMIT = (uint64_t)1 << 40;  // sanity bound on the sizes a key may claim (keeps next_pow2 and allocations finite)
 
 struct Reader {
     const uint8_t* p;
@@ -44,6 +45,11 @@ struct Reader {
         return v;
     }
     uint8_t u8() { return *take(1); }
+    bool boolean() {  // ark-serialize bool / Option tag: exactly 0 or 1
+        const uint8_t b = u8();
+        if (b > 1) throw std::runtime_error("boolean byte is neither 0 nor 1");
+        return b == 1;
+    }
     bool done() const { return pos == n; }
 };
 void put_u64(std::vector<uint8_t>& out, uint64_t v) {
@@ -175,20 +181,37 @@ void g1_to_bytes(const Aff& p, std::vector<uint8_t>& out) {
     }
     out.insert(out.end(), b, b + 97);
 }
-Aff g1_from_bytes(const uint8_t b[97]) {
+[[maybe_unused]] Aff g1_from_bytes(const uint8_t b[97]) {
     if (b[96]) return Aff::inf();
     Aff p;
     if (!fq_from_canonical(b, &p.x) || !fq_from_canonical(b + 48, &p.y)) throw std::runtime_error("G1 coordinate out of range");
     if (!p.on_curve()) throw std::runtime_error("G1 point not on the curve");
     return p;
 }
-// ark-serialize 0.3.0 compressed GroupAffine (48 bytes): bit 7 of the last byte = "y > -y", bit 6 = infinity
+// r P == O: ark-serialize 0.3.0's GroupAffine::deserialize checks the prime-order subgroup (BLS12-377 G1 has a cofactor)
+bool g1_in_subgroup(const Aff& p) {
+    if (p.is_inf()) return true;
+    XY acc = XY::inf();
+    for (int i = Fr377Params::BITS - 1; i >= 0; --i) {
+        acc = acc.dbl();
+        if ((Fr377Params::MOD(i >> 5) >> (i & 31)) & 1) acc.madd(p);
+    }
+    return acc.is_inf();
+}
+// ark-serialize 0.3.0 compressed GroupAffine (48 bytes): bit 7 of the last byte = "y > -y", bit 6 = infinity.  Strict: both
+// flags set is invalid (SWFlags::from_u8), infinity must come with x = 0 (the one encoding serialize() emits), x < q, the
+// point on the curve and in the prime-order subgroup.
 Aff g1_deserialize(const uint8_t b[48]) {
     uint8_t c[48];
     memcpy(c, b, 48);
     const int flags = c[47] >> 6;
     c[47] &= 0x3f;
-    if (flags & 1) return Aff::inf();
+    if (flags == 3) throw std::runtime_error("G1: infinity and sign flags both set");
+    if (flags & 1) {
+        for (int i = 0; i < 48; ++i)
+            if (c[i]) throw std::runtime_error("G1: infinity flag with a non-zero x");
+        return Aff::inf();
+    }
     Aff p;
     if (!fq_from_canonical(c, &p.x)) throw std::runtime_error("G1 x out of range");
     Fq y;
@@ -196,25 +219,90 @@ Aff g1_deserialize(const uint8_t b[48]) {
     Fq ny = y.neg();
     const bool greater = y.from_mont().canonical_gt(ny.from_mont());
     p.y = (greater == (bool)(flags & 2)) ? y : ny;
+    if (!g1_in_subgroup(p)) throw std::runtime_error("G1 point outside the prime-order subgroup");
     return p;
 }
-void g2_to_bytes(const G2A& p, std::vector<uint8_t>& out) {
-    const Fq* c[4] = {&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1};
-    for (const Fq* f : c) {
-        Fq t = f->from_mont();
-        const uint8_t* b = reinterpret_cast<const uint8_t*>(t.v);
-        out.insert(out.end(), b, b + 48);
+// ark-serialize 0.3.0 compressed GroupAffine: x canonical LE, bit 7 of the last byte = "y > -y", bit 6 = infinity
+void g1_serialize(const Aff& p, std::vector<uint8_t>& out) {
+    uint8_t b[48];
+    if (p.is_inf()) {
+        memset(b, 0, 48);
+        b[47] |= 1 << 6;
+    } else {
+        Fq x = p.x.from_mont(), y = p.y.from_mont(), ny = p.y.neg().from_mont();
+        memcpy(b, x.v, 48);
+        if (y.canonical_gt(ny)) b[47] |= 1 << 7;
     }
+    out.insert(out.end(), b, b + 48);
 }
-G2A g2_from_bytes(const uint8_t* b) {
+// ---- G2, compressed (96 bytes): x.c0 || x.c1 canonical LE, flags in the top bits of the last byte; the sign flag compares
+// y with -y as ark-ff orders quadratic extensions (c1 first, then c0)
+bool fq2_gt(const Fq2& a, const Fq2& b) {
+    const Fq a1 = a.c1.from_mont(), b1 = b.c1.from_mont();
+    if (!(a1 == b1)) return a1.canonical_gt(b1);
+    return a.c0.from_mont().canonical_gt(b.c0.from_mont());
+}
+// square root in Fq2 = Fq[u]/(u^2 + 5) by the norm method (ark-ff QuadExtField::sqrt)
+bool fq2_sqrt(const Fq2& a, Fq2* out) {
+    if (a.c1.is_zero()) {
+        Fq r;
+        if (fq_sqrt(a.c0, &r)) {
+            *out = {r, Fq::zero()};
+            return true;
+        }
+        // a.c0 is a non-residue of Fq: sqrt = sqrt(a.c0 / -5) u
+        if (!fq_sqrt((Fq2::times5(Fq::one()).neg().inverse()) * a.c0, &r)) return false;
+        *out = {Fq::zero(), r};
+        return true;
+    }
+    Fq alpha;
+    if (!fq_sqrt(a.c0 * a.c0 + Fq2::times5(a.c1 * a.c1), &alpha)) return false;  // norm = c0^2 + 5 c1^2
+    const Fq two_inv = Fq::one().dbl().inverse();
+    Fq delta = (alpha + a.c0) * two_inv, c0;
+    if (!fq_sqrt(delta, &c0)) {
+        delta = delta - alpha;
+        if (!fq_sqrt(delta, &c0)) return false;
+    }
+    *out = {c0, a.c1 * two_inv * c0.inverse()};
+    return true;
+}
+void g2_serialize(const G2A& p, std::vector<uint8_t>& out) {
+    uint8_t b[96];
+    memset(b, 0, 96);
+    if (p.inf) {
+        b[95] |= 1 << 6;
+    } else {
+        const Fq c0 = p.x.c0.from_mont(), c1 = p.x.c1.from_mont();
+        memcpy(b, c0.v, 48);
+        memcpy(b + 48, c1.v, 48);
+        if (fq2_gt(p.y, p.y.neg())) b[95] |= 1 << 7;
+    }
+    out.insert(out.end(), b, b + 96);
+}
+G2A g2_deserialize(const uint8_t b[96]) {
+    uint8_t c[96];
+    memcpy(c, b, 96);
+    const int flags = c[95] >> 6;
+    c[95] &= 0x3f;
+    if (flags == 3) throw std::runtime_error("G2: infinity and sign flags both set");
+    if (flags & 1) {
+        for (int i = 0; i < 96; ++i)
+            if (c[i]) throw std::runtime_error("G2: infinity flag with a non-zero x");
+        return G2A::infinity();
+    }
     G2A p;
-    Fq* c[4] = {&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1};
-    for (int i = 0; i < 4; ++i)
-        if (!fq_from_canonical(b + 48 * i, c[i])) throw std::runtime_error("G2 coordinate out of range");
-    if (!p.on_curve()) throw std::runtime_error("G2 point not on the twist");
+    if (!fq_from_canonical(c, &p.x.c0) || !fq_from_canonical(c + 48, &p.x.c1)) throw std::runtime_error("G2 x out of range");
+    const Fq2 twist_b = {Fq::zero(), pairing::fq_from_limbs(pairing_params::TWIST_B_C1)};
+    Fq2 y;
+    if (!fq2_sqrt(p.x * p.x * p.x + twist_b, &y)) throw std::runtime_error("G2 x not on the twist");
+    const Fq2 ny = y.neg();
+    p.y = (fq2_gt(y, ny) == (bool)(flags & 2)) ? y : ny;
+    // prime-order subgroup of the twist: r P == O
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = Fr377Params::MOD(i);
+    if (!pairing::g2_mul(p, r, 8).inf) throw std::runtime_error("G2 point outside the prime-order subgroup");
     return p;
 }
-
 struct Commitment {
     Aff comm;
     bool has_shifted = false;
@@ -235,25 +323,172 @@ enum PolyId { A_ROW, A_COL, A_VAL, A_ROW_COL, B_ROW, B_COL, B_VAL, B_ROW_COL, C_
 
 }  // namespace
 
-std::vector<uint8_t> build_verifying_key(const std::vector<uint8_t>& index_vk, uint64_t x_padded, uint64_t max_degree, const Fp<Fr377Params>& tau,
-                                         const Fp<Fr377Params>& gamma, const std::vector<uint64_t>& degree_bounds) {
-    std::vector<uint8_t> out(VK_MAGIC, VK_MAGIC + 8);
-    put_u64(out, x_padded);
-    put_u64(out, max_degree);
-    put_u64(out, index_vk.size());
-    out.insert(out.end(), index_vk.begin(), index_vk.end());
-    const Aff g = Aff::generator();
-    g1_to_bytes(g, out);
-    g1_to_bytes(g1_scale(g, gamma), out);
-    const G2A h = G2A::generator();
-    g2_to_bytes(h, out);
-    Fr tc = tau.from_mont();
-    g2_to_bytes(pairing::g2_mul(h, tc.v, 8), out);
-    put_u64(out, degree_bounds.size());
-    for (uint64_t b : degree_bounds) {  // ark-poly-commit VerifierKey::degree_bounds_and_shift_powers: tau^(D - bound) G
-        put_u64(out, b);
-        g1_to_bytes(g1_scale(g, fr_pow_u64(tau, max_degree - b)), out);
+// ---- verifying key: ark-serialize 0.3.0 CanonicalSerialize of ark_marlin::IndexVerifierKey<Fr, MarlinKZG10<Bls12_377, ..>> ------
+//   index_info          num_variables | num_constraints | num_non_zero | num_instance_variables   (4 x u64 LE; PhantomData is empty)
+//   index_comms         u64 count (12) | 12 x marlin_pc::Commitment { comm: G1 compressed 48 B, shifted_comm: Option = 0x00 }
+//   verifier_key        marlin_pc::VerifierKey { vk: kzg10::VerifierKey { g, gamma_g: G1 compressed; h, beta_h: G2 compressed 96 B }
+//                       (the prepared G2 elements are not serialised), degree_bounds_and_shift_powers: Option<Vec<(u64, G1)>>,
+//                       max_degree u64, supported_degree u64 }
+// Restated from the published 0.3.0 sources (un-vendored; "parity unpinned" like the proof bytes).
+namespace {
+struct VerifyingKey {
+    uint64_t num_variables = 0, num_constraints = 0, num_non_zero = 0, num_instance = 0;  // num_instance: padded, = |X|
+    Aff index_comms[12];
+    Aff g, gamma_g;
+    G2A h, beta_h;
+    std::vector<std::pair<uint64_t, Aff>> shift_powers;  // (degree bound, tau^(max_degree - bound) G), ascending bounds
+    uint64_t max_degree = 0, supported_degree = 0;
+};
+void vk_serialize(const VerifyingKey& k, std::vector<uint8_t>& out) {
+    out.clear();
+    put_u64(out, k.num_variables);
+    put_u64(out, k.num_constraints);
+    put_u64(out, k.num_non_zero);
+    put_u64(out, k.num_instance);
+    put_u64(out, 12);
+    for (int i = 0; i < 12; ++i) {
+        g1_serialize(k.index_comms[i], out);
+        out.push_back(0);
     }
+    g1_serialize(k.g, out);
+    g1_serialize(k.gamma_g, out);
+    g2_serialize(k.h, out);
+    g2_serialize(k.beta_h, out);
+    out.push_back(1);
+    put_u64(out, k.shift_powers.size());
+    for (const auto& sp : k.shift_powers) {
+        put_u64(out, sp.first);
+        g1_serialize(sp.second, out);
+    }
+    put_u64(out, k.max_degree);
+    put_u64(out, k.supported_degree);
+}
+VerifyingKey vk_parse(const uint8_t* bytes, size_t len) {
+    Reader r(bytes, len);
+    VerifyingKey k;
+    k.num_variables = r.u64();
+    k.num_constraints = r.u64();
+    k.num_non_zero = r.u64();
+    k.num_instance = r.u64();
+    if (k.num_variables > SIZE_LIMIT || k.num_constraints > SIZE_LIMIT || k.num_non_zero > SIZE_LIMIT || k.num_instance > SIZE_LIMIT ||
+        k.num_constraints == 0 || k.num_non_zero == 0)
+        throw std::runtime_error("verifying key: implausible index sizes");
+    if (r.u64() != 12) throw std::runtime_error("verifying key: expected 12 index commitments");
+    for (int i = 0; i < 12; ++i) {
+        k.index_comms[i] = g1_deserialize(r.take(48));
+        if (r.boolean()) throw std::runtime_error("verifying key: index commitment with a degree bound");
+    }
+    k.g = g1_deserialize(r.take(48));
+    k.gamma_g = g1_deserialize(r.take(48));
+    k.h = g2_deserialize(r.take(96));
+    k.beta_h = g2_deserialize(r.take(96));
+    if (r.boolean()) {
+        const uint64_t n = r.u64();
+        if (n > 16) throw std::runtime_error("verifying key: too many degree bounds");
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t b = r.u64();
+            k.shift_powers.emplace_back(b, g1_deserialize(r.take(48)));
+        }
+    }
+    k.max_degree = r.u64();
+    k.supported_degree = r.u64();
+    if (!r.done()) throw std::runtime_error("trailing bytes in the verifying key");
+    // consistency of the claimed sizes (AHPForR1CS::max_degree with zk_bound = 1; supported degree <= SRS degree)
+    const uint64_t h = next_pow2(k.num_constraints), kk = next_pow2(k.num_non_zero);
+    const uint64_t need = std::max(3 * h - 1, 3 * kk - 3);
+    if (k.supported_degree > k.max_degree || k.supported_degree < need) throw std::runtime_error("verifying key: degree bounds of the SRS do not fit the index");
+    const uint64_t x = k.num_instance;
+    if (x < 2 || (x & (x - 1)) || x > h) throw std::runtime_error("verifying key: bad public-input domain");
+    return k;
+}
+// ark-ff ToBytes of IndexVerifierKey (what enters the Fiat-Shamir seed): index_info as 3 x u64, then the 12 commitments
+std::vector<uint8_t> vk_transcript_bytes(const VerifyingKey& k) {
+    std::vector<uint8_t> out;
+    put_u64(out, k.num_variables);
+    put_u64(out, k.num_constraints);
+    put_u64(out, k.num_non_zero);
+    for (int i = 0; i < 12; ++i) {
+        Commitment c;
+        c.comm = k.index_comms[i];
+        comm_to_bytes(c, out);
+    }
+    return out;
+}
+
+// ---- proof: ark-serialize 0.3.0 CanonicalDeserialize of ark_marlin::Proof, one STRICT reader shared by verify_encryption and
+// zkaes_proof_deserialize.  Refused: bool / Option tags other than 0 / 1, G1 encodings ark rejects (both flags, x >= q, not on the
+// curve, outside the subgroup) or never emits (infinity with x != 0), field elements >= r, round sizes and degree-bound
+// placement other than this protocol's, trailing bytes.  Prover messages: ark-marlin 0.3.0 absorbs them into the transcript
+// with the round's commitments (to_bytes![comms, msg]); this AHP sends three empty ones, and anything else is refused here
+// so that a proof has exactly one accepted encoding.
+struct ParsedProof {
+    Commitment comms[9];  // w z_a z_b mask | t g_1 h_1 | g_2 h_2
+    Fr ev[7];             // a_denom b_denom c_denom g_1 g_2 t z_b
+    uint8_t ev_bytes[7 * 32];
+    Aff W[2];
+    bool has_rv[2];
+    Fr rv[2];
+    uint8_t rv_bytes[2][32];
+};
+ParsedProof proof_parse(const uint8_t* bytes, size_t len) {
+    static const uint64_t sizes[3] = {4, 3, 2};
+    static const bool bounded[9] = {false, false, false, false, false, true, false, true, false};  // g_1 and g_2
+    Reader pr(bytes, len);
+    ParsedProof p;
+    if (pr.u64() != 3) throw std::runtime_error("proof: expected three rounds of commitments");
+    int k = 0;
+    for (int r = 0; r < 3; ++r) {
+        if (pr.u64() != sizes[r]) throw std::runtime_error("proof: unexpected number of commitments in a round");
+        for (uint64_t i = 0; i < sizes[r]; ++i, ++k) {
+            p.comms[k].comm = g1_deserialize(pr.take(48));
+            p.comms[k].has_shifted = pr.boolean();
+            p.comms[k].shifted = p.comms[k].has_shifted ? g1_deserialize(pr.take(48)) : Aff::inf();
+            if (p.comms[k].has_shifted != bounded[k]) throw std::runtime_error("proof: degree-bound commitment where the protocol has none (or missing)");
+        }
+    }
+    if (pr.u64() != 7) throw std::runtime_error("proof: expected seven evaluations");
+    bool ok = true;
+    memcpy(p.ev_bytes, pr.take(7 * 32), 7 * 32);
+    for (int i = 0; i < 7; ++i) p.ev[i] = fr_from_canonical(p.ev_bytes + 32 * i, &ok);
+    if (pr.u64() != 3) throw std::runtime_error("proof: expected three prover messages");
+    for (int i = 0; i < 3; ++i)
+        if (pr.boolean()) throw std::runtime_error("proof: non-empty prover message");
+    if (pr.u64() != 2) throw std::runtime_error("proof: expected two opening proofs");
+    for (int i = 0; i < 2; ++i) {
+        p.W[i] = g1_deserialize(pr.take(48));
+        p.has_rv[i] = pr.boolean();
+        memset(p.rv_bytes[i], 0, 32);
+        if (p.has_rv[i]) memcpy(p.rv_bytes[i], pr.take(32), 32);
+        p.rv[i] = p.has_rv[i] ? fr_from_canonical(p.rv_bytes[i], &ok) : Fr::zero();
+    }
+    if (pr.boolean()) throw std::runtime_error("proof: unexpected BatchLCProof evaluations");
+    if (!pr.done()) throw std::runtime_error("proof: trailing bytes");
+    if (!ok) throw std::runtime_error("proof: field element out of range");
+    return p;
+}
+}  // namespace
+
+std::vector<uint8_t> build_verifying_key(uint64_t num_variables, uint64_t num_constraints, uint64_t num_non_zero, uint64_t x_padded,
+                                         const Affine<G1_377Params>* index_comms, uint64_t max_degree, const Fp<Fr377Params>& tau,
+                                         const Fp<Fr377Params>& gamma, std::vector<uint64_t> degree_bounds) {
+    VerifyingKey k;
+    k.num_variables = num_variables;
+    k.num_constraints = num_constraints;
+    k.num_non_zero = num_non_zero;
+    k.num_instance = x_padded;
+    for (int i = 0; i < 12; ++i) k.index_comms[i] = index_comms[i];
+    k.g = Aff::generator();
+    k.gamma_g = g1_scale(k.g, gamma);
+    k.h = G2A::generator();
+    Fr tc = tau.from_mont();
+    k.beta_h = pairing::g2_mul(k.h, tc.v, 8);
+    std::sort(degree_bounds.begin(), degree_bounds.end());  // marlin_pc::trim sorts and de-duplicates the enforced bounds
+    degree_bounds.erase(std::unique(degree_bounds.begin(), degree_bounds.end()), degree_bounds.end());
+    for (uint64_t b : degree_bounds) k.shift_powers.emplace_back(b, g1_scale(k.g, fr_pow_u64(tau, max_degree - b)));
+    k.max_degree = max_degree;
+    k.supported_degree = max_degree;
+    std::vector<uint8_t> out;
+    vk_serialize(k, out);
     return out;
 }
 
@@ -262,85 +497,47 @@ int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t
     *accepted = 0;
     try {
         // ---- verifying key ------------------------------------------------------------------------------------------------
-        Reader vk(vk_bytes, vk_len);
-        if (memcmp(vk.take(8), VK_MAGIC, 8) != 0) throw std::runtime_error("not a zkaes verifying key");
-        const uint64_t x = vk.u64(), D = vk.u64(), ivk_len = vk.u64();
-        const uint8_t* ivk = vk.take(ivk_len);
-        if (ivk_len != 24 + 12 * 195) throw std::runtime_error("index verifying key has the wrong size");
-        Reader ir(ivk, ivk_len);
-        ir.u64();  // number of variables
-        const uint64_t ncons = ir.u64(), nnz = ir.u64();
+        const VerifyingKey key = vk_parse(vk_bytes, vk_len);
+        const std::vector<uint8_t> ivk_vec = vk_transcript_bytes(key);
+        const uint8_t* ivk = ivk_vec.data();
+        const size_t ivk_len = ivk_vec.size();
+        const uint64_t x = key.num_instance;
         Aff comm[N_POLYS], shifted[N_POLYS];
         long bound[N_POLYS];
         for (int i = 0; i < N_POLYS; ++i) bound[i] = -1;
-        for (int i = 0; i < 12; ++i) {
-            comm[i] = g1_from_bytes(ir.take(97));
-            ir.take(98);
-        }
-        const Aff G = g1_from_bytes(vk.take(97)), gamma_G = g1_from_bytes(vk.take(97));
-        const G2A H = g2_from_bytes(vk.take(192)), beta_H = g2_from_bytes(vk.take(192));
-        const uint64_t nb = vk.u64();
-        std::vector<std::pair<uint64_t, Aff>> shift_powers;
-        for (uint64_t i = 0; i < nb; ++i) {
-            uint64_t b = vk.u64();
-            shift_powers.emplace_back(b, g1_from_bytes(vk.take(97)));
-        }
-        if (!vk.done()) throw std::runtime_error("trailing bytes in the verifying key");
-        const uint64_t h = next_pow2(ncons), k = next_pow2(nnz);
-        if (x < 2 || (x & (x - 1)) || x > h) throw std::runtime_error("bad public-input domain");
+        for (int i = 0; i < 12; ++i) comm[i] = key.index_comms[i];
+        const Aff G = key.g, gamma_G = key.gamma_g;
+        const G2A H = key.h, beta_H = key.beta_h;
+        const uint64_t h = next_pow2(key.num_constraints), k = next_pow2(key.num_non_zero);
         auto shift_power = [&](uint64_t b) -> const Aff& {
-            for (auto& sp : shift_powers)
+            for (auto& sp : key.shift_powers)
                 if (sp.first == b) return sp.second;
             throw std::runtime_error("verifying key lacks a shift power");
         };
 
-        // ---- proof (ark-serialize 0.3.0 CanonicalDeserialize of ark_marlin::Proof) -------------------------------------------
-        Reader pr(proof_bytes, proof_len);
-        static const int round_sizes[3] = {4, 3, 2};
-        static const int round_poly[3][4] = {{P_W, P_ZA, P_ZB, P_MASK}, {P_T, P_G1, P_H1, -1}, {P_G2, P_H2, -1, -1}};
+        // ---- proof ---------------------------------------------------------------------------------------------------------------
+        const ParsedProof pp = proof_parse(proof_bytes, proof_len);
+        static const int poly_of[9] = {P_W, P_ZA, P_ZB, P_MASK, P_T, P_G1, P_H1, P_G2, P_H2};
+        static const int round_of[9] = {0, 0, 0, 0, 1, 1, 1, 2, 2};
         bound[P_G1] = (long)(h - 2);
         bound[P_G2] = (long)(k - 2);
         std::vector<uint8_t> round_bytes[3];
-        if (pr.u64() != 3) return 0;
-        for (int r = 0; r < 3; ++r) {
-            if (pr.u64() != (uint64_t)round_sizes[r]) return 0;
-            for (int i = 0; i < round_sizes[r]; ++i) {
-                Commitment c;
-                c.comm = g1_deserialize(pr.take(48));
-                c.has_shifted = pr.u8() != 0;
-                if (c.has_shifted) c.shifted = g1_deserialize(pr.take(48));
-                const int id = round_poly[r][i];
-                if (c.has_shifted != (bound[id] >= 0)) return 0;  // degree bounds exactly where the protocol puts them
-                comm[id] = c.comm;
-                shifted[id] = c.shifted;
-                comm_to_bytes(c, round_bytes[r]);
-            }
+        for (int i = 0; i < 9; ++i) {
+            comm[poly_of[i]] = pp.comms[i].comm;
+            shifted[poly_of[i]] = pp.comms[i].shifted;
+            comm_to_bytes(pp.comms[i], round_bytes[round_of[i]]);
         }
-        bool ok = true;
-        if (pr.u64() != 7) return 0;
-        Fr ev[7];  // a_denom b_denom c_denom g_1 g_2 t z_b
-        const uint8_t* evp = pr.take(7 * 32);
-        const std::vector<uint8_t> ev_bytes(evp, evp + 7 * 32);
-        for (int i = 0; i < 7; ++i) ev[i] = fr_from_canonical(evp + 32 * i, &ok);
-        const uint64_t nmsg = pr.u64();
-        for (uint64_t i = 0; i < nmsg; ++i)
-            if (pr.u8()) {
-                uint64_t cnt = pr.u64();
-                pr.take(32 * cnt);
-            }
-        if (pr.u64() != 2) return 0;
-        Aff W[2];
-        bool has_rv[2];
-        Fr rv[2];
-        for (int i = 0; i < 2; ++i) {
-            W[i] = g1_deserialize(pr.take(48));
-            has_rv[i] = pr.u8() != 0;
-            rv[i] = has_rv[i] ? fr_from_canonical(pr.take(32), &ok) : Fr::zero();
-        }
-        if (pr.u8() != 0 || !pr.done() || !ok) return 0;
+        const Fr* ev = pp.ev;
+        const std::vector<uint8_t> ev_bytes(pp.ev_bytes, pp.ev_bytes + 7 * 32);
+        const Aff* W = pp.W;
+        const bool* has_rv = pp.has_rv;
+        const Fr* rv = pp.rv;
 
+        // The statement's length: ark-marlin 0.3.0 takes domain_x from public_input.len() + 1 and zero-pads the input to
+        // |X| - 1 itself, so a ciphertext is a statement of THIS key only if its bit count selects the key's domain
+        // (a length from another power-of-two bracket is a different statement: rejected, not an error).
+        if (8 * (uint64_t)ct_len + 1 > x || next_pow2(8 * (uint64_t)ct_len + 1) != x) return 0;
         // ---- public input: 8 bits per ciphertext byte, LSB first (src/helpers/mod.rs:84-93), zero-padded to |X| - 1 ----------
-        if (8 * (uint64_t)ct_len > x - 1) return 0;
         std::vector<uint8_t> seed;
         seed.insert(seed.end(), {'M', 'A', 'R', 'L', 'I', 'N', '-', '2', '0', '1', '9'});
         seed.insert(seed.end(), ivk, ivk + ivk_len);
@@ -466,7 +663,6 @@ int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t
             comb.madd(g1_scale(W[g], points[g]));
             if (!pairing::pairing_product_is_one(comb.to_affine(), H, W[g].neg(), beta_H)) return 0;
         }
-        (void)D;
         *accepted = 1;
         return 0;
     } catch (const std::exception& e) {
@@ -495,64 +691,29 @@ Aff g1_from_xy96(const uint8_t b[96]) {
     if (!p.on_curve()) throw std::runtime_error("G1 point not on the curve");
     return p;
 }
-// ark-serialize 0.3.0 compressed GroupAffine: x canonical LE, bit 7 of the last byte = "y > -y", bit 6 = infinity
-void g1_serialize(const Aff& p, std::vector<uint8_t>& out) {
-    uint8_t b[48];
-    if (p.is_inf()) {
-        memset(b, 0, 48);
-        b[47] |= 1 << 6;
-    } else {
-        Fq x = p.x.from_mont(), y = p.y.from_mont(), ny = p.y.neg().from_mont();
-        memcpy(b, x.v, 48);
-        if (y.canonical_gt(ny)) b[47] |= 1 << 7;
-    }
-    out.insert(out.end(), b, b + 48);
-}
 }  // namespace
 
 int proof_deserialize_host(const uint8_t* proof, size_t len, zkaes_proof_fields* out, std::string* err) {
     try {
         memset(out, 0, sizeof(*out));
-        Reader pr(proof, len);
-        static const uint32_t sizes[3] = {4, 3, 2};
-        if (pr.u64() != 3) throw std::runtime_error("proof: expected three rounds of commitments");
+        const ParsedProof p = proof_parse(proof, len);
         out->n_rounds = 3;
-        int k = 0;
-        for (int r = 0; r < 3; ++r) {
-            if (pr.u64() != sizes[r]) throw std::runtime_error("proof: unexpected number of commitments in a round");
-            out->round_sizes[r] = sizes[r];
-            for (uint32_t i = 0; i < sizes[r]; ++i, ++k) {
-                g1_to_xy96(g1_deserialize(pr.take(48)), out->commitments[k].comm);
-                out->commitments[k].has_shifted = pr.u8() != 0;
-                if (out->commitments[k].has_shifted) g1_to_xy96(g1_deserialize(pr.take(48)), out->commitments[k].shifted);
-            }
+        out->round_sizes[0] = 4;
+        out->round_sizes[1] = 3;
+        out->round_sizes[2] = 2;
+        for (int k = 0; k < 9; ++k) {
+            g1_to_xy96(p.comms[k].comm, out->commitments[k].comm);
+            out->commitments[k].has_shifted = p.comms[k].has_shifted ? 1 : 0;
+            if (p.comms[k].has_shifted) g1_to_xy96(p.comms[k].shifted, out->commitments[k].shifted);
         }
-        if (pr.u64() != 7) throw std::runtime_error("proof: expected seven evaluations");
         out->n_evaluations = 7;
-        bool ok = true;
-        for (int i = 0; i < 7; ++i) {
-            const uint8_t* e = pr.take(32);
-            fr_from_canonical(e, &ok);
-            memcpy(out->evaluations[i], e, 32);
-        }
-        const uint64_t nmsg = pr.u64();
-        for (uint64_t i = 0; i < nmsg; ++i)
-            if (pr.u8()) throw std::runtime_error("proof: non-empty prover message");  // this AHP sends none
-        if (nmsg != 3) throw std::runtime_error("proof: expected three prover messages");
-        if (pr.u64() != 2) throw std::runtime_error("proof: expected two opening proofs");
+        memcpy(out->evaluations, p.ev_bytes, 7 * 32);
         out->n_openings = 2;
         for (int i = 0; i < 2; ++i) {
-            g1_to_xy96(g1_deserialize(pr.take(48)), out->openings[i].w);
-            out->openings[i].has_random_v = pr.u8() != 0;
-            if (out->openings[i].has_random_v) {
-                const uint8_t* e = pr.take(32);
-                fr_from_canonical(e, &ok);
-                memcpy(out->openings[i].random_v, e, 32);
-            }
+            g1_to_xy96(p.W[i], out->openings[i].w);
+            out->openings[i].has_random_v = p.has_rv[i] ? 1 : 0;
+            memcpy(out->openings[i].random_v, p.rv_bytes[i], 32);
         }
-        if (pr.u8() != 0) throw std::runtime_error("proof: unexpected BatchLCProof evaluations");
-        if (!pr.done()) throw std::runtime_error("proof: trailing bytes");
-        if (!ok) throw std::runtime_error("proof: field element out of range");
         return 0;
     } catch (const std::exception& e) {
         if (err) *err = e.what();

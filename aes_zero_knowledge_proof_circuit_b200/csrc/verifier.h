@@ -4,20 +4,20 @@
 #include <string>
 #include <vector>
 
-#include "ff.cuh"
+#include "ec.cuh"
 
 struct zkaes_proof_fields;
 
 namespace zk {
 
-// Verifying key = everything `verify_encryption` (reference src/lib.rs:116-136) needs, as one byte string:
-//   "ZKAESVK1" | |X| u64 | SRS max degree u64 | len u64 | IndexVerifierKey ToBytes (index info + 12 commitments) |
-//   g, gamma_g (G1, ark-ff ToBytes, 97 B each) | h, beta_h (G2: x.c0 x.c1 y.c0 y.c1 canonical LE, 192 B each) |
-//   count u64 | (degree bound u64, shift power tau^(D - bound) G, 97 B) ...
-// i.e. ark-marlin's IndexVerifierKey {index_info, index_comms, verifier_key} with ark-poly-commit's marlin_pc::VerifierKey
-// {vk: {g, gamma_g, h, beta_h}, degree_bounds_and_shift_powers}.  tau, gamma: the test SRS trapdoors (Montgomery form).
-std::vector<uint8_t> build_verifying_key(const std::vector<uint8_t>& index_vk, uint64_t x_padded, uint64_t max_degree, const Fp<Fr377Params>& tau,
-                                         const Fp<Fr377Params>& gamma, const std::vector<uint64_t>& degree_bounds);
+// Verifying key = the VerifyingKey half of `synthesize_keys` (reference src/lib.rs:138,173): the ark-serialize 0.3.0
+// CanonicalSerialize bytes of ark_marlin::IndexVerifierKey<Fr, MarlinKZG10<Bls12_377, DensePolynomial<Fr>>> -- index_info (four u64),
+// the 12 index commitments (compressed G1 + an empty shifted_comm), marlin_pc::VerifierKey {kzg10 vk: g, gamma_g (G1), h, beta_h
+// (compressed G2), degree_bounds_and_shift_powers, max_degree, supported_degree}.  Layout in verifier.cpp.
+// tau, gamma: the test-SRS trapdoors (Montgomery form); index_comms: 12 points.
+std::vector<uint8_t> build_verifying_key(uint64_t num_variables, uint64_t num_constraints, uint64_t num_non_zero, uint64_t x_padded,
+                                         const Affine<G1_377Params>* index_comms, uint64_t max_degree, const Fp<Fr377Params>& tau,
+                                         const Fp<Fr377Params>& gamma, std::vector<uint64_t> degree_bounds);
 
 // Returns 0 and sets *accepted to 0/1, or -1 (with *err) when the key or the proof cannot be parsed.
 int verify_encryption_host(const uint8_t* vk, size_t vk_len, const uint8_t* proof, size_t proof_len, const uint8_t* ciphertext, size_t ct_len,

@@ -916,21 +916,42 @@ def index_from_vk_bytes(vk: bytes, num_instance_padded: int) -> Index:
     return idx
 
 
+def g2_serialize_compressed(pt) -> bytes:
+    """ark-serialize 0.3.0 CanonicalSerialize for a G2 GroupAffine over Fq2: x.c0 || x.c1 canonical LE (96 B), SWFlags in the top two
+    bits of the last byte; "positive" means y > -y in ark-ff's order of quadratic extensions (c1 compared first, then c0)."""
+    if pt is None:
+        b = bytearray(96)
+        b[95] |= 1 << 6
+        return bytes(b)
+    (x0, x1), (y0, y1) = pt
+    b = bytearray(x0.to_bytes(48, "little") + x1.to_bytes(48, "little"))
+    n0, n1 = (Q - y0) % Q, (Q - y1) % Q
+    if (y1, y0) > (n1, n0):
+        b[95] |= 1 << 7
+    return bytes(b)
+
+
 def verifying_key_bytes(index_vk: bytes, x_padded: int, max_degree: int, h: int, k: int, tau_seed: bytes, gamma_seed: bytes) -> bytes:
-    """The verifying key `verify_encryption` takes, in the product's self-describing layout (csrc/verifier.h): index vk,
-    KZG verifier key (g, gamma_g in G1; h, beta_h = tau h in G2) and the shift powers tau^(D - bound) G of the two degree
-    bounds.  Built independently of the product (oracle G1 arithmetic, big-integer G2 from oracle/pairing_ref.py)."""
+    """The VerifyingKey `verify_encryption` takes: ark-serialize 0.3.0 CanonicalSerialize of ark_marlin::IndexVerifierKey --
+    index_info {num_variables, num_constraints, num_non_zero, num_instance_variables} (4 x u64), Vec of 12 marlin_pc::Commitment
+    {comm: compressed G1, shifted_comm: None}, marlin_pc::VerifierKey {kzg10 vk {g, gamma_g: G1; h, beta_h = tau h: compressed G2},
+    degree_bounds_and_shift_powers: Some([(bound, tau^(D - bound) G)]) ascending, max_degree, supported_degree}.
+    `index_vk` is IndexVerifierKey's ToBytes form (Index.vk_bytes()).  Built independently of the product (oracle G1 arithmetic,
+    big-integer G2 from oracle/pairing_ref.py)."""
     from . import pairing_ref as pr
 
     tau, gamma = seed_to_scalar(tau_seed), seed_to_scalar(gamma_seed)
-    g1 = lambda s: g1_to_bytes_uncompressed(orc().g1_mul_gen(CURVE, ints_to_limbs([s % P], 4))[0])
-    g2 = lambda pt: b"".join(c.to_bytes(48, "little") for c in (pt[0][0], pt[0][1], pt[1][0], pt[1][1]))
-    out = b"ZKAESVK1" + struct.pack("<QQQ", x_padded, max_degree, len(index_vk)) + index_vk
-    out += g1(1) + g1(gamma) + g2(pr.G2) + g2(pr.e2mul(pr.G2, tau))
-    bounds = [h - 2, k - 2]
-    out += struct.pack("<Q", len(bounds))
+    g1 = lambda s: g1_serialize_compressed(orc().g1_mul_gen(CURVE, ints_to_limbs([s % P], 4))[0])
+    nvar, ncons, nnz = struct.unpack_from("<QQQ", index_vk, 0)
+    out = struct.pack("<QQQQ", nvar, ncons, nnz, x_padded) + struct.pack("<Q", 12)
+    for i in range(12):
+        out += g1_serialize_compressed(g1_from_bytes_uncompressed(index_vk[24 + 195 * i: 24 + 195 * i + 97])) + b"\x00"
+    out += g1(1) + g1(gamma) + g2_serialize_compressed(pr.G2) + g2_serialize_compressed(pr.e2mul(pr.G2, tau))
+    bounds = sorted({h - 2, k - 2})
+    out += b"\x01" + struct.pack("<Q", len(bounds))
     for b in bounds:
         out += struct.pack("<Q", b) + g1(pow(tau, max_degree - b, P))
+    out += struct.pack("<QQ", max_degree, max_degree)
     return out
 
 

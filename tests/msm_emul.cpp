@@ -23,8 +23,11 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
             uint32_t s[8];
             memcpy(s, scalars + 8 * (base + i), 32);
             uint32_t flip = msm_fold_scalar<FrP>(s);
+            std::vector<uint32_t> dig(p.W);
+            msm_digits_all(s, flip, p, dig.data(), 1);  // the kernels' one-walk digits must equal the per-window definition
             for (int w = 0; w < p.W; ++w) {
                 uint32_t neg, d = msm_digit_of_window(s, flip, p, w, &neg);
+                if ((d ? ((d - 1) | (neg << 31)) : MSM_DIGIT_NONE) != dig[w]) return -1;
                 if (d) counts[(uint32_t)w * p.nbw + d - 1]++;
             }
         }

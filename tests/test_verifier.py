@@ -42,6 +42,21 @@ def test_accepts_golden_proof_and_rejects_wrong_ciphertext(golden):
     assert zk.verify_encryption(vk, proof, ct[:15]) is False                         # a shorter statement is a different statement
 
 
+def test_statement_length_follows_ark_marlins_domain_rule(golden):
+    """ark-marlin 0.3.0 takes domain_x from public_input.len() + 1 and zero-pads the input to |X| - 1 itself (verify()), so the
+    statement is bound to the key through the power-of-two bracket of its bit count, exactly as in the reference: lengths from
+    another bracket are rejected whatever their bytes, also when the dropped / added bytes are zero."""
+    vk, proof, ct = bytes.fromhex(golden["verifying_key"]), bytes.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
+    assert zk.verify_encryption(vk, proof, ct + bytes(16)) is False                  # 257 inputs: domain 512, not this key's 256
+    assert zk.verify_encryption(vk, proof, bytes(15)) is False and zk.verify_encryption(vk, proof, b"") is False
+    zero_tail = ct[:15] + b"\x00"
+    assert zk.verify_encryption(vk, proof, zero_tail[:15]) is False                  # truncation below the bracket is rejected even
+    assert zk.verify_encryption(vk, proof, zero_tail) is (zero_tail == ct)           # ... when the dropped byte is zero
+    # inside the bracket the reference itself pads with zeros: ct || 00 is the same padded statement for ark-marlin (and here)
+    assert zk.verify_encryption(vk, proof, ct + b"\x00") is True
+    assert zk.verify_encryption(vk, proof, ct + b"\x01") is False
+
+
 def test_rejects_tampered_proofs(golden):
     vk, proof, ct = bytes.fromhex(golden["verifying_key"]), bytearray.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
     # one evaluation changed (offset: 3 rounds of commitments = 8 + (8 + 4*49) + (8 + 3*49 + 48) + (8 + 2*49 + 48), then the count)
@@ -75,6 +90,59 @@ def test_malformed_inputs_are_errors(golden):
     t = bytearray(proof)
     t[16:16 + 48], t[16 + 49:16 + 49 + 48] = proof[16 + 49:16 + 49 + 48], proof[16:16 + 48]
     assert zk.verify_encryption(vk, bytes(t), ct) is False
+
+
+def _proof_offsets(proof):
+    """byte offsets inside the golden proof: first commitment, its has_shifted byte, prover-message count, first opening"""
+    msgs = 8 + (8 + 4 * 49) + (8 + 3 * 49 + 48) + (8 + 2 * 49 + 48) + 8 + 7 * 32
+    return {"comm0": 16, "shifted0": 16 + 48, "msg_count": msgs, "msg0": msgs + 8, "open_count": msgs + 8 + 3}
+
+
+def test_non_canonical_encodings_are_refused(golden):
+    """the verifier and zkaes_proof_deserialize share ONE strict reader -- a proof has exactly one accepted encoding"""
+    vk, proof, ct = bytes.fromhex(golden["verifying_key"]), bytes.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
+    o = _proof_offsets(proof)
+    assert int.from_bytes(proof[o["msg_count"]:o["msg_count"] + 8], "little") == 3 and proof[o["msg0"]:o["msg0"] + 3] == b"\0\0\0"
+    cases = {}
+    # (a) an empty prover message replaced by FieldElements([42])
+    cases["message with elements"] = proof[:o["msg0"]] + b"\x01" + (1).to_bytes(8, "little") + (42).to_bytes(32, "little") + proof[o["msg0"] + 1:]
+    # (a') ... or by FieldElements([]): absorbs nothing, ark-marlin would accept it as a second encoding of the same proof
+    cases["message with empty vector"] = proof[:o["msg0"]] + b"\x01" + (0).to_bytes(8, "little") + proof[o["msg0"] + 1:]
+    # (b) five prover messages
+    cases["five messages"] = proof[:o["msg_count"]] + (5).to_bytes(8, "little") + b"\0" * 5 + proof[o["msg0"] + 3:]
+    # (c) Option / bool tags other than 0 / 1
+    t = bytearray(proof); t[o["shifted0"]] = 2; cases["has_shifted = 2"] = bytes(t)
+    t = bytearray(proof); t[o["msg0"]] = 2; cases["message tag = 2"] = bytes(t)
+    t = bytearray(proof); t[-1] = 2; cases["BatchLCProof tag = 2"] = bytes(t)
+    # (d) point encodings ark rejects or never emits
+    t = bytearray(proof); t[o["comm0"] + 47] |= 0xC0; cases["infinity and sign flags"] = bytes(t)
+    t = bytearray(proof); t[o["comm0"] + 47] = (t[o["comm0"] + 47] & 0x3F) | 0x40; cases["infinity with non-zero x"] = bytes(t)
+    # (e) a point of the curve outside the prime-order subgroup (BLS12-377 G1 has a cofactor): smallest x with x^3 + 1 a square
+    from tests.oracle_lib import FQ
+    q = FQ[377]
+    x = next(x for x in range(2, 100) if pow(x ** 3 + 1, (q - 1) // 2, q) == 1)
+    t = bytearray(proof); t[o["comm0"]:o["comm0"] + 48] = x.to_bytes(48, "little"); cases["outside the subgroup"] = bytes(t)
+    for what, data in cases.items():
+        with pytest.raises(zk.ZkAesError):
+            zk.verify_encryption(vk, data, ct)
+        with pytest.raises(zk.ZkAesError):
+            zk.deserialize_proof(data)
+    assert zk.verify_encryption(vk, proof, ct) is True
+
+
+def test_implausible_verifying_keys_are_errors_not_hangs(golden):
+    vk, proof, ct = bytearray.fromhex(golden["verifying_key"]), bytes.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
+    for off, val in ((8, (1 << 63) + 1), (16, (1 << 63) + 1), (24, 1 << 62), (8, 0)):   # num_constraints, num_non_zero, |X|
+        t = bytearray(vk)
+        t[off:off + 8] = val.to_bytes(8, "little")
+        with pytest.raises(zk.ZkAesError):
+            zk.verify_encryption(bytes(t), proof, ct)
+    t = bytearray(vk)
+    t[-16:-8] = (7).to_bytes(8, "little")                                              # SRS degree too small for the index
+    with pytest.raises(zk.ZkAesError):
+        zk.verify_encryption(bytes(t), proof, ct)
+    with pytest.raises(zk.ZkAesError):
+        zk.verify_encryption(bytes(vk) + b"\0", proof, ct)
 
 
 def test_second_golden_proof_and_cross_statements(golden):

@@ -51,7 +51,7 @@ def generate(name, MSG, KEY, ZK_SEED):
         "message": MSG.hex(), "key": KEY.hex(), "ciphertext": ct.hex(),
         "tau_seed": TAU_SEED.hex(), "gamma_seed": GAMMA_SEED.hex(), "zk_seed": ZK_SEED.hex(),
         "h": idx.domain_h.size, "k": idx.domain_k.size, "x": idx.domain_x.size, "max_degree": idx.max_degree,
-        "vk_sha256": hashlib.sha256(idx.vk_bytes()).hexdigest(), "vk_len": len(idx.vk_bytes()),
+        "vk_sha256": hashlib.sha256(idx.vk_bytes()).hexdigest(), "vk_len": len(idx.vk_bytes()), "index_vk": idx.vk_bytes().hex(),
         "verifying_key": mo.verifying_key_bytes(idx.vk_bytes(), idx.domain_x.size, idx.max_degree, idx.domain_h.size, idx.domain_k.size,
                                                 TAU_SEED, GAMMA_SEED).hex(),
         "proof": pb.hex(),
