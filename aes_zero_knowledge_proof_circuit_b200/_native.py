@@ -33,6 +33,9 @@ def _load():
     sigs = {
         "zkaes_ctx_create": (c_int, [c_int, POINTER(vp)]),
         "zkaes_ctx_destroy": (None, [vp]),
+        "zkaes_coset_plan": (c_int, [c_int, c_int, c_int, ctypes.c_double, vp, vp]),
+        "zkaes_ctx_create_multi": (c_int, [vp, c_int, POINTER(vp)]),
+        "zkaes_ctx_devices": (c_int, [vp]),
         "zkaes_last_error": (c_char_p, [vp]),
         "zkaes_ctx_stream": (vp, [vp]),
         "zkaes_ctx_launches": (c_uint64, [vp]),
@@ -68,6 +71,8 @@ def _load():
         "zkaes_witness_aes128_ecb": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp]),
         "zkaes_synthesize_keys": (c_int, [vp, c_size_t, vp, vp, POINTER(vp)]),
         "zkaes_pk_free": (None, [vp]),
+        "zkaes_pk_save": (c_int, [vp, vp, ctypes.c_char_p, c_int]),
+        "zkaes_pk_load": (c_int, [vp, ctypes.c_char_p, POINTER(vp)]),
         "zkaes_pk_info": (c_int, [vp, vp]),
         "zkaes_pk_vk_bytes": (c_int, [vp, vp, POINTER(c_size_t)]),
         "zkaes_encrypt": (c_int, [vp, vp, vp, c_size_t, vp, vp, vp, vp, POINTER(c_size_t)]),
@@ -127,15 +132,36 @@ def shard_range(n: int, rank: int, nranks: int):
     return s.value, c.value
 
 
-class Context:
-    """One prover context bound to one CUDA device (one per process / rank)."""
+def coset_plan(nranks: int, ncoset: int, ntask: int, own_extra: float):
+    """-> (owner[ncoset], exec[ncoset][ntask]): zkaes_coset_plan, the work split of the prover's coset evaluations over the ranks"""
+    owner = np.zeros(ncoset, dtype=np.int32)
+    ex = np.zeros(ncoset * ntask, dtype=np.int32)
+    if lib().zkaes_coset_plan(nranks, ncoset, ntask, float(own_extra), _ptr(owner), _ptr(ex)) != 0:
+        raise ZkAesError("zkaes_coset_plan: bad arguments")
+    return owner.tolist(), ex.reshape(ncoset, ntask).tolist()
 
-    def __init__(self, device: int = 0):
+
+class Context:
+    """One prover context: one CUDA device (`Context(0)`, one per process / rank), or several devices driven by this one process
+    (`Context([0, 1, 2, 3])`, zkaes_ctx_create_multi: worker threads + an in-process NCCL communicator)."""
+
+    def __init__(self, device=0):
         self._h = c_void_p()
-        rc = lib().zkaes_ctx_create(device, ctypes.byref(self._h))
+        if isinstance(device, (list, tuple)):
+            ids = (c_int * len(device))(*device)
+            rc = lib().zkaes_ctx_create_multi(ctypes.cast(ids, c_void_p), len(device), ctypes.byref(self._h))
+            what = f"zkaes_ctx_create_multi(devices={list(device)})"
+            self.device = device[0] if device else None
+        else:
+            rc = lib().zkaes_ctx_create(device, ctypes.byref(self._h))
+            what = f"zkaes_ctx_create(device={device})"
+            self.device = device
         if rc != 0:
-            raise ZkAesError(f"zkaes_ctx_create(device={device}) failed with {rc}: a B200 (sm_100) GPU is required; there is no CPU path")
-        self.device = device
+            raise ZkAesError(f"{what} failed with {rc}: B200 (sm_100) GPUs are required; there is no CPU path")
+
+    @property
+    def n_devices(self) -> int:
+        return int(lib().zkaes_ctx_devices(self._h))
 
     def close(self):
         if self._h:
@@ -288,7 +314,7 @@ class Circuit:
         if rc != 0:
             raise ZkAesError(f"zkaes_circuit_build({msg_len}) failed with {rc}: message length must be a non-zero multiple of 16")
         info = np.zeros(len(CIRCUIT_INFO_FIELDS), dtype=np.uint64)
-        assert lib().zkaes_circuit_info(self._h, _ptr(info)) == 0
+        _ok(lib().zkaes_circuit_info(self._h, _ptr(info)), "zkaes_circuit_info")
         self.info = {k: int(v) for k, v in zip(CIRCUIT_INFO_FIELDS, info)}
 
     def matrix(self, which: int):
@@ -297,7 +323,7 @@ class Circuit:
         row_ptr = np.zeros(self.info["num_constraints"] + 1, dtype=np.uint32)
         col = np.zeros(nnz, dtype=np.uint32)
         coeff = np.zeros(nnz, dtype=np.int8)
-        assert lib().zkaes_circuit_matrix(self._h, which, _ptr(row_ptr), _ptr(col), _ptr(coeff)) == 0
+        _ok(lib().zkaes_circuit_matrix(self._h, which, _ptr(row_ptr), _ptr(col), _ptr(coeff)), "zkaes_circuit_matrix")
         return row_ptr, col, coeff
 
     def close(self):
@@ -315,6 +341,12 @@ class Circuit:
 PK_INFO_FIELDS = ("msg_len", "num_constraints", "num_variables", "nnz_a", "nnz_b", "nnz_c", "h", "k", "x", "max_degree", "num_instance_used")
 
 
+def _ok(rc, what):
+    """ABI calls without a context to ask for the message: a non-zero return code is an error, never an `assert`"""
+    if rc != 0:
+        raise ZkAesError(f"libzkaes_b200: {what} returned {rc}")
+
+
 class ProvingKey:
     """Device-resident proving key (SRS powers, matrices, index polynomials) for one plaintext length."""
 
@@ -322,23 +354,26 @@ class ProvingKey:
         self._ctx = ctx
         self._h = handle
         info = np.zeros(len(PK_INFO_FIELDS), dtype=np.uint64)
-        assert lib().zkaes_pk_info(self._h, _ptr(info)) == 0
+        _ok(lib().zkaes_pk_info(self._h, _ptr(info)), "zkaes_pk_info")
         self.info = {k: int(v) for k, v in zip(PK_INFO_FIELDS, info)}
 
-    def vk_bytes(self) -> bytes:
+    def _bytes_of(self, fn, what) -> bytes:
         n = c_size_t(0)
-        assert lib().zkaes_pk_vk_bytes(self._h, None, ctypes.byref(n)) == 0
+        _ok(fn(self._h, None, ctypes.byref(n)), what)
         buf = np.zeros(n.value, dtype=np.uint8)
-        assert lib().zkaes_pk_vk_bytes(self._h, _ptr(buf), ctypes.byref(n)) == 0
+        _ok(fn(self._h, _ptr(buf), ctypes.byref(n)), what)
         return buf.tobytes()
 
+    def vk_bytes(self) -> bytes:
+        return self._bytes_of(lib().zkaes_pk_vk_bytes, "zkaes_pk_vk_bytes")
+
     def verifying_key(self) -> bytes:
-        """The VerifyingKey half of synthesize_keys' result (src/lib.rs:138): what verify_encryption takes."""
-        n = c_size_t(0)
-        assert lib().zkaes_pk_verifying_key(self._h, None, ctypes.byref(n)) == 0
-        buf = np.zeros(n.value, dtype=np.uint8)
-        assert lib().zkaes_pk_verifying_key(self._h, _ptr(buf), ctypes.byref(n)) == 0
-        return buf.tobytes()
+        """The VerifyingKey half of synthesize_keys' result (src/lib.rs:138): what verify_encryption takes (ark-serialize bytes)."""
+        return self._bytes_of(lib().zkaes_pk_verifying_key, "zkaes_pk_verifying_key")
+
+    def save(self, path: str, srs: bool = True, index_polys: bool = True):
+        """zkaes_pk_save: this rank's key file; without the two bulk sections it is ~3 KB and load recomputes them."""
+        self._ctx._check(lib().zkaes_pk_save(self._ctx._h, self._h, os.fsencode(path), (1 if srs else 0) | (2 if index_polys else 0)))
 
     def close(self):
         if self._h:
@@ -360,6 +395,13 @@ def _seed(b):
 def _synthesize_keys(self, plaintext_length: int, tau_seed: bytes, gamma_seed: bytes) -> ProvingKey:
     h = c_void_p()
     self._check(lib().zkaes_synthesize_keys(self._h, plaintext_length, _ptr(_seed(tau_seed)), _ptr(_seed(gamma_seed)), ctypes.byref(h)))
+    return ProvingKey(self, h)
+
+
+def _load_keys(self, path: str) -> ProvingKey:
+    """zkaes_pk_load: a key saved by ProvingKey.save(), rebuilt on this context's device without the commitment MSMs"""
+    h = c_void_p()
+    self._check(lib().zkaes_pk_load(self._h, os.fsencode(path), ctypes.byref(h)))
     return ProvingKey(self, h)
 
 
@@ -433,9 +475,10 @@ def pairing_selftest(a: int, b: int) -> bytes:
     out = np.zeros(576, dtype=np.uint8)
     ab = np.frombuffer(int(a).to_bytes(32, "little"), dtype=np.uint8)
     bb = np.frombuffer(int(b).to_bytes(32, "little"), dtype=np.uint8)
-    assert lib().zkaes_selftest_pairing(_ptr(ab), _ptr(bb), _ptr(out)) == 0
+    _ok(lib().zkaes_selftest_pairing(_ptr(ab), _ptr(bb), _ptr(out)), "zkaes_selftest_pairing")
     return out.tobytes()
 
 
 Context.synthesize_keys = _synthesize_keys
+Context.load_keys = _load_keys
 Context.encrypt = _encrypt

@@ -10,6 +10,7 @@
 #include "prover.cuh"
 #include "comm.cuh"
 #include "verifier.h"
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -68,6 +69,64 @@ static int msm_host_impl(zkaes_ctx* ctx, const void* bases, const void* scalars,
     return msm_device_impl<C>(ctx, db.p, ds.p, n, 0, out96);
 }
 
+// ---- single-process multi-GPU (zkaes_ctx_create_multi) ------------------------------------------------------------------------
+// The opaque key handle: the leader's key plus, for a multi-GPU context, one key per peer rank (each holds its rank's SRS share).
+struct zkaes_pk {
+    zk::zkaes_pk_impl* impl = nullptr;
+    std::vector<zk::zkaes_pk_impl*> peer_impls;
+};
+
+static void worker_loop(ZkWorker* w, int device) {
+    cudaSetDevice(device);
+    std::unique_lock<std::mutex> lk(w->m);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+        if (w->quit) return;
+        std::function<int()> job = std::move(w->job);
+        w->has_job = false;
+        lk.unlock();
+        int rc;
+        try {
+            rc = job();
+        } catch (const std::exception&) {
+            rc = ZK_ERR_STATE;
+        }
+        lk.lock();
+        w->rc = rc;
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+// fn(context of rank i, i) on every rank at once: peers on their worker threads, rank 0 on the calling thread.  Returns the first
+// failure (the failing rank's message is copied into the leader's last_error).
+static int run_on_all(zkaes_ctx* ctx, const std::function<int(zkaes_ctx*, int)>& fn) {
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < ctx->peers.size(); ++i) {
+        ZkWorker* w = ctx->workers[i].get();
+        zkaes_ctx* pc = ctx->peers[i];
+        std::lock_guard<std::mutex> g(w->m);
+        w->job = [&fn, pc, i] { return fn(pc, (int)i + 1); };
+        w->has_job = true;
+        w->done = false;
+        w->cv.notify_all();
+    }
+    int rc;
+    try {
+        rc = fn(ctx, 0);
+    } catch (const std::exception& e) {
+        rc = fail(ctx, ZK_ERR_STATE, e.what());
+    }
+    for (size_t i = 0; i < ctx->peers.size(); ++i) {
+        ZkWorker* w = ctx->workers[i].get();
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != ZK_OK && rc == ZK_OK) rc = fail(ctx, w->rc, "rank " + std::to_string(i + 1) + ": " + ctx->peers[i]->err);
+    }
+    return rc;
+}
+static std::string rank_path(const zkaes_ctx* ctx, const char* path, int rank) {
+    return ctx->peers.empty() ? std::string(path) : std::string(path) + ".r" + std::to_string(rank);
+}
 
 extern "C" {
 
@@ -87,6 +146,10 @@ int zkaes_ctx_create(int device_id, zkaes_ctx** out) {
         delete c;
         return ZK_ERR_CUDA;
     }
+    if (const char* e = getenv("ZKAES_MSM_WINDOW_MAX")) {  // experiments: cap of the automatic MSM window choice (same as the tuning knob)
+        const int v = atoi(e);
+        if (v >= 3 && v <= 24) c->msm_window_max = v;
+    }
     // keep freed stream-ordered scratch cached in the pool instead of returning it to the driver every call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -96,8 +159,89 @@ int zkaes_ctx_create(int device_id, zkaes_ctx** out) {
     *out = c;
     return ZK_OK;
 }
+int zkaes_ctx_create_multi(const int* device_ids, int n_devices, zkaes_ctx** out) {
+    if (!out) return ZK_ERR_ARG;
+    *out = nullptr;
+    if (!device_ids || n_devices < 1 || n_devices > 64) return ZK_ERR_ARG;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return ZK_ERR_ARG;
+    zkaes_ctx* leader = nullptr;
+    int rc = zkaes_ctx_create(device_ids[0], &leader);
+    if (rc != ZK_OK) return rc;
+    if (n_devices == 1) {
+        *out = leader;
+        return ZK_OK;
+    }
+    // peers are created ON their worker threads, so each thread's current device is its rank's
+    for (int i = 1; i < n_devices && rc == ZK_OK; ++i) {
+        leader->workers.emplace_back(new ZkWorker());
+        leader->peers.push_back(nullptr);
+        ZkWorker* w = leader->workers.back().get();
+        w->th = std::thread(worker_loop, w, device_ids[i]);
+    }
+    uint8_t uid[128];
+    std::string err;
+    rc = zk::comm_unique_id(uid, err);
+    if (rc != ZK_OK) fail(leader, rc, err);
+    if (rc == ZK_OK) {
+        std::vector<int> devs(device_ids, device_ids + n_devices);
+        // create the peer contexts and join the communicator: ncclCommInitRank blocks until every rank has called it
+        std::vector<zkaes_ctx*>& peers = leader->peers;
+        for (size_t i = 0; i < peers.size(); ++i) {
+            ZkWorker* w = leader->workers[i].get();
+            std::lock_guard<std::mutex> g(w->m);
+            w->job = [&peers, &devs, &uid, i, n_devices] {
+                int r = zkaes_ctx_create(devs[i + 1], &peers[i]);
+                if (r != ZK_OK) return r;
+                return zk::comm_init(peers[i], (int)i + 1, n_devices, uid);
+            };
+            w->has_job = true;
+            w->done = false;
+            w->cv.notify_all();
+        }
+        cudaSetDevice(leader->device);
+        rc = zk::comm_init(leader, 0, n_devices, uid);
+        for (size_t i = 0; i < peers.size(); ++i) {
+            ZkWorker* w = leader->workers[i].get();
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [&] { return w->done; });
+            if (w->rc != ZK_OK && rc == ZK_OK) rc = w->rc;
+        }
+    }
+    if (rc != ZK_OK) {
+        zkaes_ctx_destroy(leader);
+        return rc;
+    }
+    *out = leader;
+    return ZK_OK;
+}
+int zkaes_ctx_devices(const zkaes_ctx* ctx) { return ctx ? ctx->nranks : 0; }
 void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     if (!ctx) return;
+    for (size_t i = 0; i < ctx->workers.size(); ++i) {  // peers first, each on its own thread
+        ZkWorker* w = ctx->workers[i].get();
+        zkaes_ctx* pc = ctx->peers[i];
+        {
+            std::lock_guard<std::mutex> g(w->m);
+            w->job = [pc] {
+                if (pc) zkaes_ctx_destroy(pc);
+                return ZK_OK;
+            };
+            w->has_job = true;
+            w->done = false;
+            w->cv.notify_all();
+        }
+        {
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [&] { return w->done; });
+            w->quit = true;
+            w->cv.notify_all();
+        }
+        if (w->th.joinable()) w->th.join();
+    }
+    ctx->workers.clear();
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     zk::comm_destroy(ctx);
@@ -108,7 +252,12 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
 }
 const char* zkaes_last_error(const zkaes_ctx* ctx) { return ctx ? ctx->err.c_str() : g_host_err.empty() ? "null context" : g_host_err.c_str(); }
 void* zkaes_ctx_stream(zkaes_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t zkaes_ctx_launches(const zkaes_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const zkaes_ctx* p : ctx->peers) n += p ? p->launches : 0;
+    return n;
+}
 int zkaes_ctx_sync(zkaes_ctx* ctx) {
     NEED_CTX(ctx);
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -127,6 +276,13 @@ int zkaes_ctx_comm_init(zkaes_ctx* ctx, int rank, int nranks, const uint8_t uniq
 int zkaes_shard_range(size_t n, int rank, int nranks, size_t* start, size_t* count) {
     if (!start || !count || nranks < 1 || rank < 0 || rank >= nranks) return ZK_ERR_ARG;
     zk::shard_range(n, rank, nranks, start, count);
+    return ZK_OK;
+}
+int zkaes_coset_plan(int nranks, int ncoset, int ntask, double own_extra, int* owner_out, int* exec_out) {
+    if (nranks < 1 || ncoset < 1 || ntask < 1 || ncoset > 64 || ntask > 64 || !owner_out || !exec_out) return ZK_ERR_ARG;
+    const zk::CosetPlan pl = zk::coset_plan(nranks, ncoset, ntask, own_extra);
+    for (int j = 0; j < ncoset; ++j) owner_out[j] = pl.owner[j];
+    for (int i = 0; i < ncoset * ntask; ++i) exec_out[i] = pl.exec[i];
     return ZK_OK;
 }
 int zkaes_ctx_profile(zkaes_ctx* ctx, int enable) {
@@ -174,12 +330,16 @@ int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
     } else {
         return fail(ctx, ZK_ERR_ARG, "tuning: unknown key " + k);
     }
+    for (zkaes_ctx* p : ctx->peers)  // every rank must derive the same window plan
+        if (p) zkaes_ctx_set_tuning(p, key, value);
     return ZK_OK;
 }
 int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits) {
     NEED_CTX(ctx);
     if (window_bits < 0 || window_bits > 24 || window_bits == 1 || window_bits == 2) return fail(ctx, ZK_ERR_ARG, "window bits must be 0 or 3..24");
     ctx->msm_window_bits = window_bits;
+    for (zkaes_ctx* p : ctx->peers)
+        if (p) p->msm_window_bits = window_bits;
     return ZK_OK;
 }
 
@@ -431,30 +591,73 @@ int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* h, const uint8
 }
 
 // ---- keys + encrypt ------------------------------------------------------------------------------------------------
+static void pk_handle_free(zkaes_pk* pk) {
+    if (!pk) return;
+    zk::pk_free(pk->impl);  // cudaFree finds the owning device through the pointer; no device switch needed
+    for (zk::zkaes_pk_impl* p : pk->peer_impls) zk::pk_free(p);
+    delete pk;
+}
 int zkaes_synthesize_keys(zkaes_ctx* ctx, size_t plaintext_len, const uint8_t tau_seed32[32], const uint8_t gamma_seed32[32], zkaes_pk** out) {
     NEED_CTX(ctx);
     if (!tau_seed32 || !gamma_seed32 || !out) return fail(ctx, ZK_ERR_ARG, "synthesize_keys: null pointer");
     *out = nullptr;
-    zk::zkaes_pk_impl* p = nullptr;
-    int rc;
-    try {
-        rc = zk::pk_synthesize(ctx, plaintext_len, tau_seed32, gamma_seed32, &p);
-    } catch (const std::exception& e) {
-        return fail(ctx, ZK_ERR_STATE, std::string("synthesize_keys: ") + e.what());
+    zkaes_pk* pk = new zkaes_pk();
+    pk->peer_impls.assign(ctx->peers.size(), nullptr);
+    int rc = run_on_all(ctx, [&](zkaes_ctx* c, int r) {
+        try {
+            return zk::pk_synthesize(c, plaintext_len, tau_seed32, gamma_seed32, r == 0 ? &pk->impl : &pk->peer_impls[r - 1]);
+        } catch (const std::exception& e) {
+            return fail(c, ZK_ERR_STATE, std::string("synthesize_keys: ") + e.what());
+        }
+    });
+    if (rc != ZK_OK) {
+        pk_handle_free(pk);
+        return rc;
     }
-    if (rc != ZK_OK) return rc;
-    *out = reinterpret_cast<zkaes_pk*>(p);
+    *out = pk;
     return ZK_OK;
 }
-void zkaes_pk_free(zkaes_pk* pk) { zk::pk_free(reinterpret_cast<zk::zkaes_pk_impl*>(pk)); }
+void zkaes_pk_free(zkaes_pk* pk) { pk_handle_free(pk); }
+int zkaes_pk_save(zkaes_ctx* ctx, const zkaes_pk* pk, const char* path, int flags) {
+    NEED_CTX(ctx);
+    if (!pk || !path) return fail(ctx, ZK_ERR_ARG, "pk_save: null pointer");
+    if (pk->peer_impls.size() != ctx->peers.size()) return fail(ctx, ZK_ERR_STATE, "pk_save: key belongs to another context");
+    return run_on_all(ctx, [&](zkaes_ctx* c, int r) {
+        try {
+            return zk::pk_save(c, r == 0 ? pk->impl : pk->peer_impls[r - 1], rank_path(ctx, path, r).c_str(), flags);
+        } catch (const std::exception& e) {
+            return fail(c, ZK_ERR_STATE, std::string("pk_save: ") + e.what());
+        }
+    });
+}
+int zkaes_pk_load(zkaes_ctx* ctx, const char* path, zkaes_pk** out) {
+    NEED_CTX(ctx);
+    if (!path || !out) return fail(ctx, ZK_ERR_ARG, "pk_load: null pointer");
+    *out = nullptr;
+    zkaes_pk* pk = new zkaes_pk();
+    pk->peer_impls.assign(ctx->peers.size(), nullptr);
+    int rc = run_on_all(ctx, [&](zkaes_ctx* c, int r) {
+        try {
+            return zk::pk_load(c, rank_path(ctx, path, r).c_str(), r == 0 ? &pk->impl : &pk->peer_impls[r - 1]);
+        } catch (const std::exception& e) {
+            return fail(c, ZK_ERR_STATE, std::string("pk_load: ") + e.what());
+        }
+    });
+    if (rc != ZK_OK) {
+        pk_handle_free(pk);
+        return rc;
+    }
+    *out = pk;
+    return ZK_OK;
+}
 int zkaes_pk_info(const zkaes_pk* pk, uint64_t info[ZKAES_PK_INFO_WORDS]) {
     if (!pk || !info) return ZK_ERR_ARG;
-    zk::pk_info(reinterpret_cast<const zk::zkaes_pk_impl*>(pk), info);
+    zk::pk_info(pk->impl, info);
     return ZK_OK;
 }
 int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len) {
     if (!pk || !len) return ZK_ERR_ARG;
-    const std::vector<uint8_t>& v = zk::pk_vk_bytes(reinterpret_cast<const zk::zkaes_pk_impl*>(pk));
+    const std::vector<uint8_t>& v = zk::pk_vk_bytes(pk->impl);
     if (out) {
         if (*len < v.size()) return ZK_ERR_ARG;
         memcpy(out, v.data(), v.size());
@@ -464,7 +667,7 @@ int zkaes_pk_vk_bytes(const zkaes_pk* pk, uint8_t* out, size_t* len) {
 }
 int zkaes_pk_verifying_key(const zkaes_pk* pk, uint8_t* out, size_t* len) {
     if (!pk || !len) return ZK_ERR_ARG;
-    const std::vector<uint8_t>& v = zk::pk_verifying_key(reinterpret_cast<const zk::zkaes_pk_impl*>(pk));
+    const std::vector<uint8_t>& v = zk::pk_verifying_key(pk->impl);
     if (out) {
         if (*len < v.size()) return ZK_ERR_ARG;
         memcpy(out, v.data(), v.size());
@@ -524,14 +727,23 @@ int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t
         return ZK_OK;
     }
     if (*proof_len < need) return fail(ctx, ZK_ERR_ARG, "encrypt: proof buffer too small");
-    std::vector<uint8_t> proof;
-    int rc;
-    try {
-        rc = zk::pk_encrypt(ctx, reinterpret_cast<const zk::zkaes_pk_impl*>(pk), msg, msg_len, key, zk_seed32, ct_out, proof);
-    } catch (const std::exception& e) {
-        return fail(ctx, ZK_ERR_STATE, std::string("encrypt: ") + e.what());
-    }
+    if (pk->peer_impls.size() != ctx->peers.size()) return fail(ctx, ZK_ERR_STATE, "encrypt: key belongs to another context");
+    // every rank runs the prover in lock step (their transcripts are identical; the MSMs meet in the NCCL all-gather); rank 0's
+    // outputs go to the caller, the peers' are compared with them
+    const size_t nr = ctx->peers.size() + 1;
+    std::vector<std::vector<uint8_t>> proofs(nr), cts(nr);
+    int rc = run_on_all(ctx, [&](zkaes_ctx* c, int r) {
+        try {
+            cts[r].resize(msg_len ? msg_len : 1);
+            return zk::pk_encrypt(c, r == 0 ? pk->impl : pk->peer_impls[r - 1], msg, msg_len, key, zk_seed32, r == 0 ? ct_out : cts[r].data(), proofs[r]);
+        } catch (const std::exception& e) {
+            return fail(c, ZK_ERR_STATE, std::string("encrypt: ") + e.what());
+        }
+    });
     if (rc != ZK_OK) return rc;
+    for (size_t r = 1; r < nr; ++r)
+        if (proofs[r] != proofs[0] || memcmp(cts[r].data(), ct_out, msg_len) != 0) return fail(ctx, ZK_ERR_STATE, "encrypt: rank " + std::to_string(r) + " diverged from rank 0");
+    std::vector<uint8_t>& proof = proofs[0];
     if (proof.size() > *proof_len) return fail(ctx, ZK_ERR_STATE, "encrypt: proof larger than its bound");
     memcpy(proof_out, proof.data(), proof.size());
     *proof_len = proof.size();

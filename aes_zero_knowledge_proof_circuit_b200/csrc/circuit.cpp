@@ -195,7 +195,21 @@ struct Builder {
         record(WOP_AND, r, ref_of(a), ref_of(b), 0);
         return Bool{1, 0, r};
     }
-    Bool bor(Bool a, Bool b) { return b_not(band(b_not(a), b_not(b))); }
+    // ark-r1cs-std 0.3.1 Boolean::or: constants fold; (Is, Is) is AllocatedBool::or -- a fresh witness r = a | b with
+    // (1 - a) * (1 - b) = (1 - r), result Is(r); every other combination is NOT(AND(NOT a, NOT b)).
+    Bool bor(Bool a, Bool b) {
+        if (a.is_false()) return b;
+        if (b.is_false()) return a;
+        if (a.is_true() || b.is_true()) return B_TRUE;
+        if (a.kind == 1 && b.kind == 1) {
+            Var r = new_witness();
+            Term ta[2] = {{1, VAR_ONE}, {-1, a.var}}, tb[2] = {{1, VAR_ONE}, {-1, b.var}}, tc[2] = {{1, VAR_ONE}, {-1, r}};
+            enforce(ta, 2, tb, 2, tc, 2);
+            record(WOP_SEL, r, ref_of(a), REF_CONST | 1u, ref_of(b));  // a ? 1 : b
+            return Bool{1, 0, r};
+        }
+        return b_not(band(b_not(a), b_not(b)));
+    }
     Bool select(Bool cond, Bool t, Bool f) {
         if (cond.is_true()) return t;
         if (cond.is_false()) return f;

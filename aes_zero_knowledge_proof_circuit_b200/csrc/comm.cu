@@ -18,6 +18,10 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
@@ -37,9 +41,14 @@ static bool load_nccl(std::string& err) {
     g_nccl.CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Broadcast || !g_nccl.CommDestroy) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Broadcast || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd ||
+        !g_nccl.CommDestroy) {
         err = "libnccl.so.2 lacks a required symbol";
         return false;
     }
@@ -100,6 +109,30 @@ int comm_broadcast(zkaes_ctx* ctx, void* buf, size_t bytes, int root) {
     if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_STATE, "broadcast: communicator not initialised");
     int rc = g_nccl.Broadcast(buf, buf, bytes, /*ncclInt8*/ 0, root, (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (rc != 0) return fail(ctx, ZK_ERR_STATE, "ncclBroadcast: " + nccl_err(rc));
+    return ZK_OK;
+}
+
+int comm_group_start(zkaes_ctx* ctx) {
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_STATE, "group: communicator not initialised");
+    int rc = g_nccl.GroupStart();
+    if (rc != 0) return fail(ctx, ZK_ERR_STATE, "ncclGroupStart: " + nccl_err(rc));
+    return ZK_OK;
+}
+int comm_group_end(zkaes_ctx* ctx) {
+    int rc = g_nccl.GroupEnd();
+    if (rc != 0) return fail(ctx, ZK_ERR_STATE, "ncclGroupEnd: " + nccl_err(rc));
+    return ZK_OK;
+}
+int comm_send(zkaes_ctx* ctx, const void* buf, size_t bytes, int peer) {
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_STATE, "send: communicator not initialised");
+    int rc = g_nccl.Send(buf, bytes, /*ncclInt8*/ 0, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, ZK_ERR_STATE, "ncclSend: " + nccl_err(rc));
+    return ZK_OK;
+}
+int comm_recv(zkaes_ctx* ctx, void* buf, size_t bytes, int peer) {
+    if (!ctx->nccl_comm) return fail(ctx, ZK_ERR_STATE, "recv: communicator not initialised");
+    int rc = g_nccl.Recv(buf, bytes, /*ncclInt8*/ 0, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, ZK_ERR_STATE, "ncclRecv: " + nccl_err(rc));
     return ZK_OK;
 }
 

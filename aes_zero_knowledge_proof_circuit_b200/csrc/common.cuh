@@ -5,7 +5,12 @@
 #include <iterator>
 #include <cstdint>
 #include <cstdio>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -70,6 +75,17 @@ struct DevArena {
     }
 };
 
+// Worker of a single-process multi-GPU context (zkaes_ctx_create_multi): one host thread per peer rank, bound to that rank's
+// device, executing the jobs the leader posts (key synthesis, encrypt(), key files) in lock step with the leader's own call.
+struct ZkWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = 0;
+};
+
 struct zkaes_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -84,9 +100,12 @@ struct zkaes_ctx {
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
     int msm_madd_call = 1;   // 1: the mixed addition issues its ten products through one out-of-line multiplier (XYZZ::madd_call)
     int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
-    // multi-GPU: this process' rank among the contexts that share one sharded MSM (comm.cu)
+    // multi-GPU: this context's rank among the contexts that share one sharded MSM (comm.cu) -- one process per GPU
+    // (zkaes_ctx_comm_init), or one process driving all GPUs (zkaes_ctx_create_multi: the leader, rank 0, owns the peers)
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
+    std::vector<zkaes_ctx*> peers;                  // leader only: ranks 1..nranks-1
+    std::vector<std::unique_ptr<ZkWorker>> workers;  // leader only: workers[i] drives peers[i]
     // optional per-kernel timing of the dominant kernel (bench.py's roofline): CUDA events around every bucket
     // accumulation launch, resolved by zkaes_ctx_profile_read
     bool prof = false;

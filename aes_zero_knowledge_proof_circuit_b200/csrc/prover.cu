@@ -299,6 +299,7 @@ struct zkaes_pk_impl {
     size_t srs_count = 0;
     Aff gamma_g[3];         // gamma tau^i G (host)
     Aff index_comms[12];
+    uint8_t tau_seed[32] = {}, gamma_seed[32] = {};  // the test SRS's trapdoor seeds (a key file can regenerate the SRS from them)
     std::vector<uint8_t> vk_bytes;   // IndexVerifierKey ToBytes (enters the Fiat-Shamir seed)
     std::vector<uint8_t> vk_full;    // the verifying key verify_encryption takes (verifier.h)
     WitnessDev wit;
@@ -378,12 +379,13 @@ int pc_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t 
 }  // namespace
 
 // ======================================================================================================================
-// synthesize_keys
+// synthesize_keys, in stages that zkaes_pk_load re-uses: shape (circuit, matrices, witness program), SRS share, index
+// polynomials (+ their 12 commitments), verifying key
 // ======================================================================================================================
-int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], const uint8_t gamma_seed[32], zkaes_pk_impl** out) {
-    *out = nullptr;
-    std::unique_ptr<zkaes_pk_impl> pkp(new zkaes_pk_impl());
-    zkaes_pk_impl& pk = *pkp;
+namespace {
+
+// circuit shape -> sizes, CSR / CSC / K-domain index arrays and the witness program in HBM, table of omega_H powers
+int pk_build_shape(zkaes_ctx* ctx, zkaes_pk_impl& pk, size_t msg_len) {
     try {
         build_aes_circuit(msg_len, pk.circ);
     } catch (const std::exception& e) {
@@ -404,20 +406,9 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     // AHPForR1CS::max_degree with zk_bound = 1
     pk.D = std::max(std::max(2 * pk.h - 1, 3 * pk.h - 1), std::max(pk.h, 3 * pk.k - 3));
     const size_t h = pk.h, k = pk.k, x = pk.x;
-
-    // ---- SRS: tau^i G on the device, gamma tau^i G (i < 3) on the host -----------------------------------------------
     {
         const size_t N = (size_t)ctx->nranks, r = (size_t)ctx->rank;
         pk.srs_count = pk.D + 1 > r ? (pk.D + 1 - r + N - 1) / N : 0;  // points i = r (mod N), i <= D
-        ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * std::max<size_t>(pk.srs_count, 1)));
-        ZK_TRY(srs_powers_device<C>(ctx, tau_seed, pk.srs_count, pk.srs, /*start=*/r, /*stride=*/N));
-    }
-    ZK_TRY(msm_bases_to_internal<C>(ctx, pk.srs, pk.srs, pk.srs_count));  // resident bases live in the MSM kernels' internal form
-    Fr tau = fr_from_seed(tau_seed), gamma = fr_from_seed(gamma_seed);
-    Fr gt = gamma;
-    for (int i = 0; i < 3; ++i) {
-        pk.gamma_g[i] = g1_mul(Aff::generator(), gt);
-        gt = gt * tau;
     }
 
     // ---- matrices: CSR, CSC (for t), K-domain arithmetisation indices -------------------------------------------------
@@ -475,14 +466,33 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         ZK_CUDA(ctx, cudaStreamSynchronize(st));
     }
     ZK_TRY(witness_upload(ctx, c, pk.wit));
-
-    // ---- index polynomials (ahp/indexer.rs arithmetize_matrix) and their commitments ---------------------------------
     ZK_CUDA(ctx, cudaMalloc((void**)&pk.elems_h, sizeof(Fr) * h));
     ZK_TRY(po_powers(ctx, pk.elems_h, h, domain_gen(pk.log_h), Fr::one()));
+    return ZK_OK;
+}
+
+// SRS: this rank's share of tau^i G on the device; gamma tau^i G (i < 3) on the host
+int pk_build_srs(zkaes_ctx* ctx, zkaes_pk_impl& pk, bool generate_points) {
+    ZK_CUDA(ctx, cudaMalloc((void**)&pk.srs, sizeof(Aff) * std::max<size_t>(pk.srs_count, 1)));
+    if (generate_points)
+        ZK_TRY(srs_powers_device<C>(ctx, pk.tau_seed, pk.srs_count, pk.srs, /*start=*/(size_t)ctx->rank, /*stride=*/(size_t)ctx->nranks));
+    Fr tau = fr_from_seed(pk.tau_seed), gamma = fr_from_seed(pk.gamma_seed);
+    Fr gt = gamma;
+    for (int i = 0; i < 3; ++i) {
+        pk.gamma_g[i] = g1_mul(Aff::generator(), gt);
+        gt = gt * tau;
+    }
+    return ZK_OK;
+}
+
+// index polynomials (ahp/indexer.rs arithmetize_matrix) and, unless they come from a key file, their 12 commitments
+int pk_build_index_polys(zkaes_ctx* ctx, zkaes_pk_impl& pk, bool compute, bool commit) {
+    const size_t h = pk.h, k = pk.k;
     Fr hinv = Fr::from_u64(h).inverse();
     for (int m = 0; m < 3; ++m) {
         Fr** P = &pk.idx_poly[4 * m];
         for (int j = 0; j < 4; ++j) ZK_CUDA(ctx, cudaMalloc((void**)&P[j], sizeof(Fr) * k));
+        if (!compute) continue;
         ZK_TRY(po_gather(ctx, P[0], pk.elems_h, pk.krow[m], k));
         ZK_TRY(po_gather(ctx, P[1], pk.elems_h, pk.kcol[m], k));
         // val = M / u_H(row, row), u_H(y, y) = |H| y^(|H|-1) = |H| / y
@@ -490,10 +500,17 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         ZK_TRY(po_vec(ctx, 2, P[3], P[0], P[1], k));
         for (int j = 0; j < 4; ++j) {
             ZK_TRY(ntt(ctx, P[j], pk.log_k, true, false));
-            ZK_TRY(msm_commit(ctx, pk, P[j], k, 0, &pk.index_comms[4 * m + j]));
+            if (commit) ZK_TRY(msm_commit(ctx, pk, P[j], k, 0, &pk.index_comms[4 * m + j]));
         }
     }
-    // IndexVerifierKey ToBytes: index_info (3 x u64) || 12 commitments
+    return ZK_OK;
+}
+
+// IndexVerifierKey ToBytes (index_info (3 x u64) || 12 commitments) and the VerifyingKey half of synthesize_keys' result
+void pk_build_vk(zkaes_pk_impl& pk) {
+    const AesCircuit& c = pk.circ;
+    const size_t nvar = (size_t)c.num_instance + c.num_witness;
+    const size_t nnz_max = std::max(pk.nnz[0], std::max(pk.nnz[1], pk.nnz[2]));
     pk.vk_bytes.clear();
     put_u64(pk.vk_bytes, nvar);
     put_u64(pk.vk_bytes, c.num_constraints);
@@ -503,10 +520,135 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
         cm.comm = pk.index_comms[i];
         comm_to_bytes(cm, pk.vk_bytes);
     }
-    // the VerifyingKey half of synthesize_keys' result (src/lib.rs:138): index vk + KZG verifier key + the two shift powers
-    pk.vk_full = build_verifying_key(nvar, c.num_constraints, nnz_max, x, pk.index_comms, pk.D, tau, gamma, {h - 2, k - 2});
-    PhaseTrace(st).mark("synthesize_keys (end)");
-    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    pk.vk_full = build_verifying_key(nvar, c.num_constraints, nnz_max, pk.x, pk.index_comms, pk.D, fr_from_seed(pk.tau_seed), fr_from_seed(pk.gamma_seed),
+                                     {pk.h - 2, pk.k - 2});
+}
+
+}  // namespace
+
+int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], const uint8_t gamma_seed[32], zkaes_pk_impl** out) {
+    *out = nullptr;
+    std::unique_ptr<zkaes_pk_impl> pkp(new zkaes_pk_impl());
+    zkaes_pk_impl& pk = *pkp;
+    memcpy(pk.tau_seed, tau_seed, 32);
+    memcpy(pk.gamma_seed, gamma_seed, 32);
+    PhaseTrace tr(ctx->stream);
+    ZK_TRY(pk_build_shape(ctx, pk, msg_len));
+    tr.mark("keys: circuit + matrices");
+    ZK_TRY(pk_build_srs(ctx, pk, true));
+    tr.mark("keys: SRS share");
+    ZK_TRY(pk_build_index_polys(ctx, pk, true, true));
+    tr.mark("keys: index polys + 12 commitments");
+    pk_build_vk(pk);
+    tr.mark("keys: verifying key");
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = pkp.release();
+    return ZK_OK;
+}
+
+// ======================================================================================================================
+// key files (the reference regenerates SRS and keys in every process, src/lib.rs:138-174)
+// ======================================================================================================================
+// Layout (little-endian): "ZKAESPK1" | version u64 | msg_len | nranks | rank | flags | D | srs_count | |K| | tau_seed[32] | gamma_seed[32]
+//   | 12 index commitments (96 B affine, arkworks Montgomery limbs) | vk_full length u64 | vk_full (ark-serialize VerifyingKey)
+//   | [flags & 1: this rank's SRS share, srs_count x 96 B] | [flags & 2: 12 index polynomials, |K| x 32 B each]
+// What is absent is recomputed by zkaes_pk_load: the circuit shape and matrices always (deterministic in msg_len), the SRS from the
+// seeds (test SRS), the index polynomials from the matrices.  The 12 index commitments -- the expensive part of synthesize_keys,
+// twelve |K|-term MSMs -- are never recomputed.  One file per rank: the SRS share is the rank's.
+namespace {
+constexpr char PK_MAGIC[8] = {'Z', 'K', 'A', 'E', 'S', 'P', 'K', '1'};
+constexpr size_t IO_CHUNK = (size_t)64 << 20;
+struct File {
+    FILE* f = nullptr;
+    ~File() {
+        if (f) fclose(f);
+    }
+};
+int dev_to_file(zkaes_ctx* ctx, FILE* f, const void* dev, size_t bytes) {
+    std::vector<uint8_t> buf(std::min(bytes, IO_CHUNK));
+    for (size_t off = 0; off < bytes; off += IO_CHUNK) {
+        const size_t n = std::min(IO_CHUNK, bytes - off);
+        ZK_CUDA(ctx, cudaMemcpyAsync(buf.data(), (const char*)dev + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (fwrite(buf.data(), 1, n, f) != n) return fail(ctx, ZK_ERR_STATE, "pk_save: short write");
+    }
+    return ZK_OK;
+}
+int file_to_dev(zkaes_ctx* ctx, FILE* f, void* dev, size_t bytes) {
+    std::vector<uint8_t> buf(std::min(bytes, IO_CHUNK));
+    for (size_t off = 0; off < bytes; off += IO_CHUNK) {
+        const size_t n = std::min(IO_CHUNK, bytes - off);
+        if (fread(buf.data(), 1, n, f) != n) return fail(ctx, ZK_ERR_ARG, "pk_load: truncated key file");
+        ZK_CUDA(ctx, cudaMemcpyAsync((char*)dev + off, buf.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+        ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return ZK_OK;
+}
+}  // namespace
+
+int pk_save(zkaes_ctx* ctx, const zkaes_pk_impl* pk, const char* path, int flags) {
+    if ((flags & ~3) != 0) return fail(ctx, ZK_ERR_ARG, "pk_save: unknown flags");
+    File file;
+    file.f = fopen(path, "wb");
+    if (!file.f) return fail(ctx, ZK_ERR_ARG, std::string("pk_save: cannot open ") + path);
+    std::vector<uint8_t> hd(PK_MAGIC, PK_MAGIC + 8);
+    for (uint64_t v : {(uint64_t)1, (uint64_t)pk->circ.msg_len, (uint64_t)ctx->nranks, (uint64_t)ctx->rank, (uint64_t)flags, (uint64_t)pk->D,
+                       (uint64_t)pk->srs_count, (uint64_t)pk->k})
+        put_u64(hd, v);
+    hd.insert(hd.end(), pk->tau_seed, pk->tau_seed + 32);
+    hd.insert(hd.end(), pk->gamma_seed, pk->gamma_seed + 32);
+    const uint8_t* comms = reinterpret_cast<const uint8_t*>(pk->index_comms);
+    hd.insert(hd.end(), comms, comms + sizeof(pk->index_comms));
+    put_u64(hd, pk->vk_full.size());
+    hd.insert(hd.end(), pk->vk_full.begin(), pk->vk_full.end());
+    if (fwrite(hd.data(), 1, hd.size(), file.f) != hd.size()) return fail(ctx, ZK_ERR_STATE, "pk_save: short write");
+    if (flags & 1) ZK_TRY(dev_to_file(ctx, file.f, pk->srs, sizeof(Aff) * pk->srs_count));
+    if (flags & 2)
+        for (int i = 0; i < 12; ++i) ZK_TRY(dev_to_file(ctx, file.f, pk->idx_poly[i], sizeof(Fr) * pk->k));
+    if (fflush(file.f) != 0) return fail(ctx, ZK_ERR_STATE, "pk_save: flush failed");
+    return ZK_OK;
+}
+
+int pk_load(zkaes_ctx* ctx, const char* path, zkaes_pk_impl** out) {
+    *out = nullptr;
+    File file;
+    file.f = fopen(path, "rb");
+    if (!file.f) return fail(ctx, ZK_ERR_ARG, std::string("pk_load: cannot open ") + path);
+    uint8_t fixed[8 + 8 * 8 + 64];
+    if (fread(fixed, 1, sizeof(fixed), file.f) != sizeof(fixed) || memcmp(fixed, PK_MAGIC, 8) != 0) return fail(ctx, ZK_ERR_ARG, "pk_load: not a zkaes key file");
+    uint64_t v[8];
+    memcpy(v, fixed + 8, sizeof(v));
+    const uint64_t version = v[0], msg_len = v[1], nranks = v[2], rank = v[3], flags = v[4], D = v[5], srs_count = v[6], kk = v[7];
+    if (version != 1 || (flags & ~(uint64_t)3)) return fail(ctx, ZK_ERR_ARG, "pk_load: unsupported key file version / flags");
+    if (nranks != (uint64_t)ctx->nranks || rank != (uint64_t)ctx->rank)
+        return fail(ctx, ZK_ERR_STATE, "pk_load: the key file holds the SRS share of another rank layout (rank " + std::to_string(rank) + " of " +
+                                           std::to_string(nranks) + ")");
+    std::unique_ptr<zkaes_pk_impl> pkp(new zkaes_pk_impl());
+    zkaes_pk_impl& pk = *pkp;
+    memcpy(pk.tau_seed, fixed + 8 + 64, 32);
+    memcpy(pk.gamma_seed, fixed + 8 + 64 + 32, 32);
+    PhaseTrace tr(ctx->stream);
+    ZK_TRY(pk_build_shape(ctx, pk, (size_t)msg_len));
+    if (pk.D != D || pk.srs_count != srs_count || pk.k != kk) return fail(ctx, ZK_ERR_ARG, "pk_load: key file does not match the circuit of its message length");
+    tr.mark("load: circuit + matrices");
+    if (fread(pk.index_comms, 1, sizeof(pk.index_comms), file.f) != sizeof(pk.index_comms)) return fail(ctx, ZK_ERR_ARG, "pk_load: truncated key file");
+    for (int i = 0; i < 12; ++i)
+        if (!pk.index_comms[i].on_curve()) return fail(ctx, ZK_ERR_ARG, "pk_load: index commitment not on the curve");
+    uint64_t vk_len = 0;
+    if (fread(&vk_len, 1, 8, file.f) != 8 || vk_len > ((uint64_t)1 << 20)) return fail(ctx, ZK_ERR_ARG, "pk_load: truncated key file");
+    std::vector<uint8_t> vk_file(vk_len);
+    if (fread(vk_file.data(), 1, vk_len, file.f) != vk_len) return fail(ctx, ZK_ERR_ARG, "pk_load: truncated key file");
+    ZK_TRY(pk_build_srs(ctx, pk, !(flags & 1)));
+    if (flags & 1) ZK_TRY(file_to_dev(ctx, file.f, pk.srs, sizeof(Aff) * pk.srs_count));
+    tr.mark((flags & 1) ? "load: SRS share from the file" : "load: SRS share from the seeds");
+    ZK_TRY(pk_build_index_polys(ctx, pk, !(flags & 2), false));
+    if (flags & 2)
+        for (int i = 0; i < 12; ++i) ZK_TRY(file_to_dev(ctx, file.f, pk.idx_poly[i], sizeof(Fr) * pk.k));
+    tr.mark((flags & 2) ? "load: index polynomials from the file" : "load: index polynomials recomputed");
+    if (fgetc(file.f) != EOF) return fail(ctx, ZK_ERR_ARG, "pk_load: trailing bytes in the key file");
+    pk_build_vk(pk);
+    if (pk.vk_full != vk_file) return fail(ctx, ZK_ERR_ARG, "pk_load: the verifying key in the file differs from the one its commitments and seeds give");
+    ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = pkp.release();
     return ZK_OK;
 }
@@ -519,6 +661,61 @@ void pk_info(const zkaes_pk_impl* pk, uint64_t info[ZK_PK_INFO_WORDS]) {
     uint64_t v[ZK_PK_INFO_WORDS] = {c.msg_len, c.num_constraints, (uint64_t)c.num_instance + c.num_witness, pk->nnz[0], pk->nnz[1], pk->nnz[2],
                                     pk->h, pk->k, pk->x, pk->D, c.num_instance_used};
     memcpy(info, v, sizeof(v));
+}
+
+// Multi-GPU evaluation of `ncoset` independent cosets (rounds 2 and 3).  Coset j needs `ntask` forward transforms (task(dst, j, p)
+// writes transform p of coset j into dst, `elems` field elements) which its owner folds into the coset's result (fold(j, T): T[p] =
+// transform p) -- the inverse transform and the pointwise products stay with the owner.  Cosets are processed in waves of at most
+// nranks cosets with distinct owners; inside a wave the forward transforms are spread over ALL ranks by coset_plan (comm.cuh):
+//   1. every rank computes the transforms assigned to it (its own coset's into T, the others' into helper buffers),
+//   2. one NCCL group of sends / receives moves the helpers' transforms to the owners over NVLink,
+//   3. the owners fold.
+// The results are then broadcast by the caller.  Field arithmetic is exact, so who computes a transform does not change a bit.
+template <class Task, class Fold>
+int run_coset_waves(zkaes_ctx* ctx, int ncoset, int ntask, double own_extra, size_t elems, Task task, Fold fold) {
+    cudaStream_t st = ctx->stream;
+    const int N = ctx->nranks, me = ctx->rank;
+    const size_t bytes = sizeof(Fr) * elems;
+    for (int j0 = 0; j0 < ncoset; j0 += N) {
+        const int nw = std::min(N, ncoset - j0);
+        const CosetPlan plan = coset_plan(N, nw, ntask, own_extra);
+        const bool owner = me < nw;  // owner of coset j0 + me
+        int n_help = 0;
+        for (int jj = 0; jj < nw; ++jj)
+            for (int p = 0; p < ntask; ++p) n_help += (plan.executor(jj, p) == me && plan.owner[jj] != me);
+        const int n_own = owner ? ntask : 0;
+        std::unique_ptr<DevBuf[]> T(new DevBuf[n_own ? n_own : 1]), H(new DevBuf[n_help ? n_help : 1]);  // DevBuf is neither copyable nor movable
+        std::vector<Fr*> Tp(ntask, nullptr);
+        for (int p = 0; p < n_own; ++p) {
+            ZK_CUDA(ctx, T[p].alloc(bytes, st));
+            Tp[p] = T[p].as<Fr>();
+        }
+        for (int i = 0; i < n_help; ++i) ZK_CUDA(ctx, H[i].alloc(bytes, st));
+        // 1. compute
+        int hi = 0;
+        for (int jj = 0; jj < nw; ++jj)
+            for (int p = 0; p < ntask; ++p)
+                if (plan.executor(jj, p) == me) ZK_TRY(task(plan.owner[jj] == me ? Tp[p] : H[hi++].as<Fr>(), j0 + jj, p));
+        // 2. exchange (helpers -> owners)
+        if (N > 1) {
+            ZK_TRY(comm_group_start(ctx));
+            hi = 0;
+            int rc = ZK_OK;
+            for (int jj = 0; jj < nw && rc == ZK_OK; ++jj)
+                for (int p = 0; p < ntask && rc == ZK_OK; ++p) {
+                    const int e = plan.executor(jj, p), o = plan.owner[jj];
+                    if (e == o) continue;
+                    if (me == e) rc = comm_send(ctx, H[hi++].p, bytes, o);
+                    if (me == o) rc = comm_recv(ctx, Tp[p], bytes, e);
+                }
+            const int rc_end = comm_group_end(ctx);
+            if (rc != ZK_OK) return rc;
+            ZK_TRY(rc_end);
+        }
+        // 3. fold
+        if (owner) ZK_TRY(fold(j0 + me, Tp));
+    }
+    return ZK_OK;
 }
 
 // ======================================================================================================================
@@ -654,22 +851,42 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             ZK_TRY(po_scale_powers(ctx, dst, dst, s, h));
             return ntt(ctx, dst, pk.log_h, false, false);
         };
-        Fr sj = Fr::one(), sjh = Fr::one();
-        // Multi-GPU: like the round-3 cosets below, coset j is evaluated by rank (j mod N) and broadcast (2.1 GB at 4 KiB)
-        for (int j = 0; j < 4; ++j, sj = sj * w4h, sjh = sjh * i4) {
-            if (j % ctx->nranks != ctx->rank) continue;
-            Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
-            ZK_TRY(to_coset_h(k_ra.as<Fr>(), ra.as<Fr>(), h, sj, sjh));
-            ZK_TRY(to_coset_h(k_za.as<Fr>(), za.as<Fr>(), h + 1, sj, sjh));
-            ZK_TRY(to_coset_h(k_zb.as<Fr>(), zb.as<Fr>(), h + 1, sj, sjh));
-            ZK_TRY(to_coset_h(k_t.as<Fr>(), tpoly.as<Fr>(), h, sj, sjh));
-            ZK_TRY(to_coset_h(k_z.as<Fr>(), zpoly.as<Fr>(), h + 1, sj, sjh));
-            ZK_TRY(po_round2(ctx, Rj, k_ra.as<Fr>(), k_za.as<Fr>(), k_zb.as<Fr>(), k_t.as<Fr>(), k_z.as<Fr>(), eta, h));
-            ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
-            ZK_TRY(po_scale_powers(ctx, Rj, Rj, sj.inverse(), h));
+        // s_j and s_j^|H| of the four cosets
+        Fr s4[4], s4h[4];
+        s4[0] = Fr::one();
+        s4h[0] = Fr::one();
+        for (int j = 1; j < 4; ++j) {
+            s4[j] = s4[j - 1] * w4h;
+            s4h[j] = s4h[j - 1] * i4;
         }
-        if (ctx->nranks > 1)
+        if (ctx->nranks == 1) {
+            for (int j = 0; j < 4; ++j) {
+                Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
+                ZK_TRY(to_coset_h(k_ra.as<Fr>(), ra.as<Fr>(), h, s4[j], s4h[j]));
+                ZK_TRY(to_coset_h(k_za.as<Fr>(), za.as<Fr>(), h + 1, s4[j], s4h[j]));
+                ZK_TRY(to_coset_h(k_zb.as<Fr>(), zb.as<Fr>(), h + 1, s4[j], s4h[j]));
+                ZK_TRY(to_coset_h(k_t.as<Fr>(), tpoly.as<Fr>(), h, s4[j], s4h[j]));
+                ZK_TRY(to_coset_h(k_z.as<Fr>(), zpoly.as<Fr>(), h + 1, s4[j], s4h[j]));
+                ZK_TRY(po_round2(ctx, Rj, k_ra.as<Fr>(), k_za.as<Fr>(), k_zb.as<Fr>(), k_t.as<Fr>(), k_z.as<Fr>(), eta, h));
+                ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
+                ZK_TRY(po_scale_powers(ctx, Rj, Rj, s4[j].inverse(), h));
+            }
+        } else {
+            // Multi-GPU: coset j is assembled by rank (j mod N) and broadcast (2.1 GB at 4 KiB); its five forward transforms are
+            // spread over all ranks (run_coset_waves)
+            for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) bfr->release();
+            const Fr* src[5] = {ra.as<Fr>(), za.as<Fr>(), zb.as<Fr>(), tpoly.as<Fr>(), zpoly.as<Fr>()};
+            const size_t len[5] = {h, h + 1, h + 1, h, h + 1};
+            ZK_TRY(run_coset_waves(
+                ctx, 4, 5, 1.5, h, [&](Fr* dst, int j, int p) -> int { return to_coset_h(dst, src[p], len[p], s4[j], s4h[j]); },
+                [&](int j, const std::vector<Fr*>& T) -> int {
+                    Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
+                    ZK_TRY(po_round2(ctx, Rj, T[0], T[1], T[2], T[3], T[4], eta, h));
+                    ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
+                    return po_scale_powers(ctx, Rj, Rj, s4[j].inverse(), h);
+                }));
             for (int j = 0; j < 4; ++j) ZK_TRY(comm_broadcast(ctx, e_ra.as<Fr>() + (size_t)j * h, sizeof(Fr) * h, j % ctx->nranks));
+        }
         ZK_TRY(po_coset4_combine(ctx, e_ra.as<Fr>(), h, i4.inverse()));  // rhs coefficients (degree <= 3|H| + 1)
     }
     for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) bfr->release();
@@ -735,45 +952,65 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const int log4k = pk.log_k + 2;
     const Fr ab = alpha * beta;
     const Fr g = coset_gen(), w4k = domain_gen(log4k);
-    DevBuf V, dden[3], tA;
+    DevBuf V;
     ZK_CUDA(ctx, V.alloc(sizeof(Fr) * 3 * k, st));
-    for (int m = 0; m < 3; ++m) ZK_CUDA(ctx, dden[m].alloc(sizeof(Fr) * k, st));
-    ZK_CUDA(ctx, tA.alloc(sizeof(Fr) * k, st));
     auto to_coset = [&](Fr* dst, const Fr* poly, const Fr& shift) -> int {  // dst[i] = poly(shift * w_K^i)
         ZK_TRY(po_scale_powers(ctx, dst, poly, shift, k));
         return ntt(ctx, dst, pk.log_k, false, false);
     };
-    // Multi-GPU: the cosets are independent -- rank (j mod N) evaluates coset j and broadcasts its |K| values
-    // (NVLink; 4.3 GB per coset at 4 KiB), instead of every rank repeating all of them.
     constexpr int NCOSET = 3;
-    Fr sj = g, uj[NCOSET];
-    for (int j = 0; j < NCOSET; ++j, sj = sj * w4k) {
-        uj[j] = fr_pow_u64(sj, k);
-        if (j % ctx->nranks != ctx->rank) continue;
-        for (int m = 0; m < 3; ++m) {
-            // the denominator is linear in (row, col, row_col): combine the coefficient vectors first, one NTT instead of three
-            Fr* const* P = &pk.idx_poly[4 * m];
-            ZK_TRY(po_lincomb_den(ctx, dden[m].as<Fr>(), P[0], P[1], P[3], alpha.neg(), beta.neg(), ab, k));
-            ZK_TRY(to_coset(dden[m].as<Fr>(), dden[m].as<Fr>(), sj));
+    Fr s3[NCOSET], uj[NCOSET];
+    s3[0] = g;
+    for (int j = 1; j < NCOSET; ++j) s3[j] = s3[j - 1] * w4k;
+    for (int j = 0; j < NCOSET; ++j) uj[j] = fr_pow_u64(s3[j], k);
+    // forward transform p of coset j: 0..2 the denominators of A, B, C (linear in (row, col, row_col): the coefficient vectors are
+    // combined first, one NTT instead of three), 3 = f, 4..6 = val of A, B, C
+    auto r3_task = [&](Fr* dst, int j, int p) -> int {
+        if (p < 3) {
+            Fr* const* P = &pk.idx_poly[4 * p];
+            ZK_TRY(po_lincomb_den(ctx, dst, P[0], P[1], P[3], alpha.neg(), beta.neg(), ab, k));
+            return to_coset(dst, dst, s3[j]);
         }
+        return to_coset(dst, p == 3 ? fpoly.as<Fr>() : pk.idx_poly[4 * (p - 4) + 2], s3[j]);
+    };
+    // V_j <- (a - b f) / v_K on coset j from the seven transforms, then back to the coefficients of the degree-<|K| interpolant
+    auto r3_finish = [&](int j) -> int {
         Fr* Vj = V.as<Fr>() + (size_t)j * k;
-        ZK_TRY(to_coset(tA.as<Fr>(), fpoly.as<Fr>(), sj));
-        ZK_TRY(po_mul3(ctx, Vj, dden[0].as<Fr>(), dden[1].as<Fr>(), dden[2].as<Fr>(), Fr::one().neg(), k));
-        ZK_TRY(po_vec(ctx, 2, Vj, Vj, tA.as<Fr>(), k));  // - b * f
-        for (int m = 0; m < 3; ++m) {
-            ZK_TRY(to_coset(tA.as<Fr>(), pk.idx_poly[4 * m + 2], sj));
-            ZK_TRY(po_fma3(ctx, Vj, tA.as<Fr>(), dden[(m + 1) % 3].as<Fr>(), dden[(m + 2) % 3].as<Fr>(), vv * eta[m], k));  // + a
-        }
         const Fr vk_inv = (uj[j] - Fr::one()).inverse();
         ZK_TRY(po_scale(ctx, Vj, Vj, vk_inv, k));
-        // back to the coefficients of the degree-<|K| interpolant on this coset, with the shift undone
         ZK_TRY(ntt(ctx, Vj, pk.log_k, true, false));
-        ZK_TRY(po_scale_powers(ctx, Vj, Vj, sj.inverse(), k));
-    }
-    if (ctx->nranks > 1)
+        return po_scale_powers(ctx, Vj, Vj, s3[j].inverse(), k);  // the shift undone
+    };
+    if (ctx->nranks == 1) {
+        // one GPU: four |K|-sized work buffers, transforms consumed as they are produced
+        DevBuf dden[3], tA;
+        for (int m = 0; m < 3; ++m) ZK_CUDA(ctx, dden[m].alloc(sizeof(Fr) * k, st));
+        ZK_CUDA(ctx, tA.alloc(sizeof(Fr) * k, st));
+        for (int j = 0; j < NCOSET; ++j) {
+            Fr* Vj = V.as<Fr>() + (size_t)j * k;
+            for (int m = 0; m < 3; ++m) ZK_TRY(r3_task(dden[m].as<Fr>(), j, m));
+            ZK_TRY(r3_task(tA.as<Fr>(), j, 3));
+            ZK_TRY(po_mul3(ctx, Vj, dden[0].as<Fr>(), dden[1].as<Fr>(), dden[2].as<Fr>(), Fr::one().neg(), k));
+            ZK_TRY(po_vec(ctx, 2, Vj, Vj, tA.as<Fr>(), k));  // - b * f
+            for (int m = 0; m < 3; ++m) {
+                ZK_TRY(r3_task(tA.as<Fr>(), j, 4 + m));
+                ZK_TRY(po_fma3(ctx, Vj, tA.as<Fr>(), dden[(m + 1) % 3].as<Fr>(), dden[(m + 2) % 3].as<Fr>(), vv * eta[m], k));  // + a
+            }
+            ZK_TRY(r3_finish(j));
+        }
+    } else {
+        // Multi-GPU: coset j is assembled by rank (j mod N) and broadcast (NVLink; 4.3 GB per coset at 4 KiB); its seven forward
+        // transforms are spread over all ranks (run_coset_waves) instead of leaving N - 3 ranks idle
+        ZK_TRY(run_coset_waves(
+            ctx, NCOSET, 7, 1.5, k, r3_task, [&](int j, const std::vector<Fr*>& T) -> int {
+                Fr* Vj = V.as<Fr>() + (size_t)j * k;
+                ZK_TRY(po_mul3(ctx, Vj, T[0], T[1], T[2], Fr::one().neg(), k));
+                ZK_TRY(po_vec(ctx, 2, Vj, Vj, T[3], k));
+                for (int m = 0; m < 3; ++m) ZK_TRY(po_fma3(ctx, Vj, T[4 + m], T[(m + 1) % 3], T[(m + 2) % 3], vv * eta[m], k));
+                return r3_finish(j);
+            }));
         for (int j = 0; j < NCOSET; ++j) ZK_TRY(comm_broadcast(ctx, V.as<Fr>() + (size_t)j * k, sizeof(Fr) * k, j % ctx->nranks));
-    for (int m = 0; m < 3; ++m) dden[m].release();
-    tA.release();
+    }
     ZK_TRY(po_coset3_combine(ctx, V.as<Fr>(), k, uj));
     Fr* h2 = V.as<Fr>();  // 3|K| - 3 coefficients
     const size_t len_h2 = 3 * k - 3;

@@ -8,9 +8,10 @@
  * Conventions: return 0 on success, negative on error (never aborts, never throws across the boundary);
  * zkaes_last_error(ctx) gives the message.  All pointers are caller-owned except opaque handles, which are
  * released by their matching *_free / *_destroy.  "host" pointers may be pageable.  Calls are blocking
- * (internally asynchronous on the context's stream).  A context is bound to ONE CUDA device and is not
- * re-entrant; multi-GPU runs use one process (one context) per GPU and exchange the small MSM partials with
- * an all-gather (torch.distributed / NCCL) between zkaes_msm_g1_windows and zkaes_msm_g1_fold.
+ * (internally asynchronous on the context's stream).  A context is not re-entrant.  Multi-GPU: either one process drives
+ * all GPUs through zkaes_ctx_create_multi, or one process (one context) per GPU joins a communicator with
+ * zkaes_ctx_comm_init; the stand-alone MSM entry points exchange their small partials with an all-gather between
+ * zkaes_msm_g1_windows and zkaes_msm_g1_fold.
  *
  * Wire formats (identical to arkworks 0.3.0 in-memory layouts, little-endian):
  *   Fr element : 32 B, 4 x u64 limbs, Montgomery form (R = 2^256)             [ark-ff Fp256]
@@ -41,6 +42,16 @@ typedef struct zkaes_ctx zkaes_ctx;
 /* ---- context ------------------------------------------------------------------------------------------ */
 /* Creates a context on CUDA device `device_id` (fails loudly if there is no usable GPU: there is no CPU path). */
 int zkaes_ctx_create(int device_id, zkaes_ctx** out);
+/* One context, several GPUs, ONE process (`zkaes_ctx_create(const int* device_ids, int n_devices, ..)`): the
+ * returned context is rank 0 on device_ids[0] and owns one peer context per further device, each driven by its own host thread,
+ * plus an in-process NCCL communicator.  zkaes_synthesize_keys / zkaes_encrypt / zkaes_pk_save / zkaes_pk_load on such a context
+ * run on every rank at once (MSMs sharded by point, as described below) and return rank 0's result after checking that every
+ * rank produced the same bytes -- so the reference's single-call `encrypt()` (src/lib.rs:60-64) drives all GPUs of the box.
+ * Key files of a multi-GPU context are written per rank as `path.r<rank>`.  n_devices = 1 is zkaes_ctx_create(device_ids[0]).
+ * The MSM / NTT / witness entry points act on rank 0's device only. */
+int zkaes_ctx_create_multi(const int* device_ids, int n_devices, zkaes_ctx** out);
+/* number of GPUs (ranks) behind the context */
+int zkaes_ctx_devices(const zkaes_ctx* ctx);
 void zkaes_ctx_destroy(zkaes_ctx* ctx);
 const char* zkaes_last_error(const zkaes_ctx* ctx);
 /* The CUDA stream the context launches on (a cudaStream_t), so callers can record events on it. */
@@ -61,6 +72,11 @@ int zkaes_ctx_sync(zkaes_ctx* ctx);
 int zkaes_comm_unique_id(uint8_t out128[128]);
 int zkaes_ctx_comm_init(zkaes_ctx* ctx, int rank, int nranks, const uint8_t unique_id128[128]);
 int zkaes_shard_range(size_t n, int rank, int nranks, size_t* start, size_t* count);
+/* How the prover splits the coset evaluations of rounds 2 and 3 over the ranks (host only; exposed for tests and for reading the
+ * phase traces): ncoset cosets of ntask forward transforms each plus own_extra transforms' worth of owner-only work.
+ * owner_out[ncoset]: the rank that assembles coset j; exec_out[ncoset * ntask]: the rank that computes transform p of coset j
+ * (it sends the result to the owner when it is not the owner).  Ranks that hand work out never take work in. */
+int zkaes_coset_plan(int nranks, int ncoset, int ntask, double own_extra, int* owner_out, int* exec_out);
 
 /* Per-kernel timing of the dominant kernel (the MSM bucket accumulation) for bench.py's roofline: when enabled, every
  * launch is bracketed by CUDA events on the context's stream.  profile_read synchronises and returns
@@ -96,9 +112,8 @@ int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases_host, const voi
 #define ZKAES_MSM_BASES_PREPARED 2
 int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n,
                         int flags, void* out_affine96_host);
-/* Rewrites n device-resident bases IN PLACE from the arkworks form into the kernels' internal form (same 96 bytes per
- * point: radix-2^29 Montgomery representative, R' = 2^377 / 2^406, packed little-endian).  Bases that are reused across
- * many MSMs (an SRS) should be prepared once; unprepared bases are converted into scratch on every call. */
+/* Kept for ABI stability: the kernels read the arkworks form directly (12 x u32 Montgomery limbs per coordinate), so
+ * "preparing" bases is the identity and ZKAES_MSM_BASES_PREPARED changes nothing. */
 int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, size_t n);
 /* multi-GPU split: (1) per-rank window sums of this rank's point range, written to a device buffer of
  * zkaes_msm_g1_windows_bytes(n_total) bytes; the window plan is derived from n_total so all ranks agree.
@@ -123,7 +138,8 @@ int zkaes_ntt_fr_device(zkaes_ctx* ctx, int curve_id, void* data_dev, uint32_t l
 int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[32], size_t n, void* out_bases_dev);
 
 /* ---- on-device self test of the field / curve arithmetic (used by tests/, not by the product path) -------
- * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul.  variant: 0 = generated PTX multiplier, 1 = portable CIOS.
+ * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul.  variant: 0 = generated PTX multiplier (inlined), 1 = portable CIOS,
+ * 2 = the out-of-line copy of the PTX multiplier that the MSM inner loop and the curve formulas call.
  * a, b, out are host arrays of `count` elements (32 B or 48 B each). */
 int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int variant, const void* a_host, const void* b_host,
                          void* out_host, size_t count);
@@ -177,6 +193,18 @@ typedef struct zkaes_pk zkaes_pk;
 #define ZKAES_PK_INFO_WORDS 11
 int zkaes_synthesize_keys(zkaes_ctx* ctx, size_t plaintext_len, const uint8_t tau_seed32[32], const uint8_t gamma_seed32[32], zkaes_pk** out);
 void zkaes_pk_free(zkaes_pk* pk);
+/* Key files (the reference regenerates SRS and keys in every process, src/lib.rs:138-174, and its
+ * ProvingKey never leaves the process).  zkaes_pk_save writes the key of THIS rank to `path`; flags: bit 0 (ZKAES_PK_FILE_SRS) =
+ * include the rank's SRS share, bit 1 (ZKAES_PK_FILE_INDEX_POLYS) = include the 12 index polynomials.  With neither the file is
+ * ~3 KB (seeds of the test SRS, sizes, the 12 index commitments, the verifying key).  zkaes_pk_load rebuilds the key on the
+ * context's device: the circuit shape and matrices from the message length, whatever the file lacks by recomputation (SRS
+ * from its seeds, index polynomials from the matrices) -- the twelve |K|-term commitment MSMs of synthesize_keys are never
+ * repeated -- and checks the file's verifying key against the one its contents give.  Multi-GPU: one file per rank; a file
+ * only loads on a context with the rank / world size it was saved from. */
+#define ZKAES_PK_FILE_SRS 1
+#define ZKAES_PK_FILE_INDEX_POLYS 2
+int zkaes_pk_save(zkaes_ctx* ctx, const zkaes_pk* pk, const char* path, int flags);
+int zkaes_pk_load(zkaes_ctx* ctx, const char* path, zkaes_pk** out);
 int zkaes_pk_info(const zkaes_pk* pk, uint64_t info[ZKAES_PK_INFO_WORDS]);
 /* Verifying-key bytes as they enter the Fiat-Shamir transcript: index info (3 x u64 LE) || 12 index commitments
  * (ark-ff ToBytes of marlin_pc::Commitment, 195 bytes each).  out may be NULL to query the size. */
@@ -185,10 +213,14 @@ int zkaes_encrypt(zkaes_ctx* ctx, const zkaes_pk* pk, const uint8_t* msg, size_t
                   uint8_t* ct_out, uint8_t* proof_out, size_t* proof_len);
 
 /* ---- S1 seam: verify_encryption ------------------------------------------------------------------------------------
- * zkaes_pk_verifying_key exports the VerifyingKey half of `synthesize_keys`' result (src/lib.rs:138,173): ark-marlin's
- * IndexVerifierKey (index info, 12 index commitments) with ark-poly-commit's marlin_pc::VerifierKey (g, gamma_g, h,
- * beta_h and the shift powers of the two degree bounds) as one self-describing byte string (layout: csrc/verifier.h).
+ * zkaes_pk_verifying_key exports the VerifyingKey half of `synthesize_keys`' result (src/lib.rs:138,173) as the ark-serialize
+ * 0.3.0 CanonicalSerialize bytes of ark_marlin::IndexVerifierKey<Fr, MarlinKZG10<Bls12_377, DensePolynomial<Fr>>>: index_info
+ * (4 x u64), the 12 index commitments (compressed G1, no shifted part), marlin_pc::VerifierKey {kzg10 vk: g, gamma_g (compressed
+ * G1), h, beta_h (compressed G2); degree bounds and shift powers; max_degree; supported_degree} -- layout in csrc/verifier.cpp.
  * out may be NULL to query the size.
+ * Statement length: like ark-marlin 0.3.0 (which derives the input domain from public_input.len() + 1 and zero-pads the input
+ * itself), a ciphertext is a statement of the key iff next_pow2(8 * ct_len + 1) equals the key's input-domain size; callers that
+ * know the key's message length should compare lengths themselves, as the reference's callers must.
  * zkaes_verify_encryption stands in for `verify_encryption(verifying_key, proof, ciphertext)` (src/lib.rs:116-136): the
  * ciphertext becomes 8 public-input bits per byte (src/helpers/mod.rs:84-93), the Marlin verifier replays the
  * transcript and checks the two KZG openings with a BLS12-377 pairing.  HOST ONLY -- no context, no device (the

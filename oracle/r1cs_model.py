@@ -10,7 +10,7 @@ Reference code followed (in tree):
     src/aes_circuit.rs:214-266  add_round_key / substitute_byte(s)   :268-334 shift_rows   :336-427 mix_columns / gmix_column
     src/helpers/mod.rs:11-64    add (ripple carry) / multiply (by a constant-valued multiplier)
 Third-party behaviour restated from the pinned versions' published sources (NOT in /root/reference):
-    ark-r1cs-std 0.3.1  Boolean::{xor,and,or,not,conditionally_select,conditional_enforce_equal}, AllocatedBool,
+    ark-r1cs-std 0.3.1  Boolean::{xor,and,or,not,conditionally_select,conditional_enforce_equal}, AllocatedBool (incl. AllocatedBool::or),
                         UInt8::{new_witness,new_input,xor,conditionally_select,enforce_equal},
                         CondSelectGadget::conditionally_select_power_of_two_vector
     ark-relations 0.3.0 ConstraintSystem: variable numbering, LinearCombination (sorted, deduplicated), to_matrices
@@ -186,6 +186,19 @@ def AND(cs, a, b):
 
 
 def OR(cs, a, b):
+    # Boolean::or: constants fold; (Is, Is) -> AllocatedBool::or: fresh witness r with (1 - a)(1 - b) = (1 - r), result Is(r);
+    # every other combination is NOT((NOT a) AND (NOT b))
+    if a == F:
+        return b
+    if b == F:
+        return a
+    if a == T or b == T:
+        return T
+    if a[0] == "I" and b[0] == "I":
+        val = a[2] or b[2]
+        r = cs.new_witness(val)
+        cs.enforce([(1, ONE), (-1, a[1])], [(1, ONE), (-1, b[1])], [(1, ONE), (-1, r)])
+        return ("I", r, val)
     return NOT(AND(cs, NOT(a), NOT(b)))
 
 

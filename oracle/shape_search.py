@@ -28,22 +28,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import r1cs_model as m  # noqa: E402
 
 TARGET_CONSTRAINTS, TARGET_INSTANCE, TARGET_NNZ = 866_944, 513, 4_062_064
-NOR_OR = m.OR
+ALLOC_OR = m.OR
 BaseCS = m.CS
 
 
-def or_allocated(cs, a, b):  # ark-r1cs-std 0.3.1 Boolean::or: (Is, Is) -> AllocatedBool::or
-    if a == m.F:
-        return b
-    if b == m.F:
-        return a
-    if a == m.T or b == m.T:
-        return m.T
-    if a[0] == "I" and b[0] == "I":
-        val = a[2] or b[2]
-        r = cs.new_witness(val)
-        cs.enforce([(1, m.ONE), (-1, a[1])], [(1, m.ONE), (-1, b[1])], [(1, m.ONE), (-1, r)])
-        return ("I", r, val)
+def or_nor(cs, a, b):  # the lowering round 1 used for every combination: NOT((NOT a) AND (NOT b))
     return m.NOT(m.AND(cs, m.NOT(a), m.NOT(b)))
 
 
@@ -118,7 +107,7 @@ def install(cs, sl, sr, rot, orv):
     m.shift_left = lambda b, k: fl(cs, b, k, True)
     m.shift_right = lambda b, k: fr(cs, b, k, False)
     m.rot_bytes = lambda arr, k: rt(cs, arr, k)
-    m.OR = or_allocated if orv == "or" else NOR_OR
+    m.OR = ALLOC_OR if orv == "or" else or_nor
 
 
 def fresh_byte(cs):

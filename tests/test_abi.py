@@ -105,3 +105,22 @@ def test_header_is_plain_c_and_verifier_links_from_c(tmp_path):
     ok, bad = run("ct"), run("ct_bad")
     assert (ok.returncode, ok.stdout.strip()) == (0, "accepted"), ok.stderr
     assert (bad.returncode, bad.stdout.strip()) == (1, "rejected"), bad.stderr
+
+
+def test_rust_sys_crate_declares_exactly_the_header_exports():
+    """rust/zk-aes-b200-sys/src/lib.rs (the -sys shim a Rust caller binds) declares one `pub fn` per export of include/zkaes_b200.h, no
+    more and no fewer, and the shared library exports every one of them.  (No Rust toolchain in this image: the crate is source only.)"""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "zkaes_b200.h")).read()
+    exported = set(re.findall(r"^(?:int|void|size_t|uint64_t|const char\*|void\*) ?\*? ?(zkaes_[a-z0-9_]+)\(", hdr, re.M))
+    rust = open(os.path.join(ROOT, "rust", "zk-aes-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (zkaes_[a-z0-9_]+)\(", rust))
+    assert declared == exported, (sorted(declared - exported), sorted(exported - declared))
+    assert exported == set(zk.lib()._zk_symbols), (sorted(exported - set(zk.lib()._zk_symbols)), sorted(set(zk.lib()._zk_symbols) - exported))
+    # the facade keeps the reference's three signatures (src/lib.rs:60-64, 116-120, 138)
+    facade = open(os.path.join(ROOT, "rust", "zk-aes-b200", "src", "lib.rs")).read()
+    for sig in ("pub fn synthesize_keys(plaintext_length: usize) -> Result<(ProvingKey, VerifyingKey)>",
+                "pub fn encrypt(message: &[u8], secret_key: &[u8; 16], proving_key: ProvingKey) -> Result<MarlinProof>",
+                "pub fn verify_encryption(verifying_key: VerifyingKey, proof: &MarlinProof, ciphertext: &[u8]) -> Result<bool>"):
+        assert sig in facade, sig

@@ -112,6 +112,32 @@ def test_full_size_4kib_proof_verifies(ctx):
         pk.close()
 
 
+@pytest.mark.parametrize("srs,polys", [(True, True), (False, False), (True, False)])
+def test_key_file_round_trip_proves_the_golden_bytes(ctx, pk16, golden, tmp_path, srs, polys):
+    """zkaes_pk_save / zkaes_pk_load: a key rebuilt from its file -- with the bulk sections stored, or recomputed from the seeds
+    and matrices -- has the same verifying key and produces the golden proof bytes; corrupt files are errors"""
+    path = str(tmp_path / "key16.zkpk")
+    pk16.save(path, srs=srs, index_polys=polys)
+    size = os.path.getsize(path)
+    assert (size < 8192) == (not srs and not polys)
+    pk2 = ctx.load_keys(path)
+    try:
+        assert pk2.info == pk16.info and pk2.vk_bytes() == pk16.vk_bytes() and pk2.verifying_key() == pk16.verifying_key()
+        ct, proof = ctx.encrypt(pk2, bytes.fromhex(golden["message"]), bytes.fromhex(golden["key"]), bytes.fromhex(golden["zk_seed"]))
+        assert ct.hex() == golden["ciphertext"] and proof.hex() == golden["proof"]
+    finally:
+        pk2.close()
+    raw = bytearray(open(path, "rb").read())
+    for what, data in (("truncated", raw[:-5]), ("trailing", raw + b"\0"), ("magic", b"X" + raw[1:]),
+                       ("commitment", raw[:8 + 64 + 64 + 5] + bytes([raw[8 + 64 + 64 + 5] ^ 1]) + raw[8 + 64 + 64 + 6:])):
+        bad = str(tmp_path / f"bad_{what}.zkpk")
+        open(bad, "wb").write(bytes(data))
+        with pytest.raises(zk.ZkAesError):
+            ctx.load_keys(bad).close()
+    with pytest.raises(zk.ZkAesError):
+        ctx.load_keys(str(tmp_path / "does_not_exist.zkpk"))
+
+
 def test_wrong_length_rejected(ctx, pk16):
     with pytest.raises(zk.ZkAesError):
         ctx.encrypt(pk16, b"\x00" * 32, b"\x00" * 16, bytes(32))

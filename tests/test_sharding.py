@@ -65,3 +65,33 @@ def test_point_ranges_single_process(world):
         assert pos == n
     with pytest.raises(zk.ZkAesError):
         zk.shard_range(10, world, world)
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 5, 8, 16])
+@pytest.mark.parametrize("ncoset,ntask", [(3, 7), (4, 5), (1, 7), (2, 5)])
+def test_coset_plan_is_acyclic_and_balanced(nranks, ncoset, ntask):
+    """zkaes_coset_plan (the split of the prover's round-2 / round-3 coset transforms over the ranks; the prover calls it per wave of at most
+    `nranks` cosets): owners are j mod N, every transform has exactly one executor, a rank that hands work out never takes work in (so the
+    stream-ordered NCCL sends and receives cannot deadlock), and handing work out never makes the busiest rank busier."""
+    nw = min(ncoset, nranks)  # one wave
+    owner, ex = zk.coset_plan(nranks, nw, ntask, 1.5)
+    assert owner == [j % nranks for j in range(nw)] and len(ex) == nw and all(len(r) == ntask for r in ex)
+    assert all(0 <= e < nranks for row in ex for e in row)
+    gives = {owner[j] for j in range(nw) for p in range(ntask) if ex[j][p] != owner[j]}
+    takes = {ex[j][p] for j in range(nw) for p in range(ntask) if ex[j][p] != owner[j]}
+    assert not (gives & takes)
+    load = [0.0] * nranks
+    for j in range(nw):
+        load[owner[j]] += 1.5
+        for p in range(ntask):
+            load[ex[j][p]] += 1.0 + (0.15 if ex[j][p] != owner[j] else 0.0)
+    assert max(load) <= ntask + 1.5 + 1e-9            # never worse than everything at the owner
+    if nranks >= 2 * nw:
+        assert max(load) < 0.7 * (ntask + 1.5)        # with idle ranks around, the critical path really shrinks
+    # handed-out transforms are the last-needed ones of their coset (the owner starts with what it needs first)
+    for j in range(nw):
+        local = [p for p in range(ntask) if ex[j][p] == owner[j]]
+        assert local == list(range(len(local)))
+    assert (owner, ex) == zk.coset_plan(nranks, nw, ntask, 1.5)
+    with pytest.raises(zk.ZkAesError):
+        zk.coset_plan(0, 3, 7, 1.5)
