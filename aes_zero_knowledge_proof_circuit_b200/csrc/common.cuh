@@ -99,7 +99,7 @@ struct zkaes_ctx {
                              // Off by default: one round measured break-even (profiles/r1_launches_msm_2p26_pair_round.txt)
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
     int msm_madd_call = 1;   // 1: the mixed addition issues its ten products through one out-of-line multiplier (XYZZ::madd_call)
-    int msm_window_max = 22;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B)
+    int msm_window_max = 23;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B: 8.9 GB at c = 23, W = 11)
     // multi-GPU: this context's rank among the contexts that share one sharded MSM (comm.cu) -- one process per GPU
     // (zkaes_ctx_comm_init), or one process driving all GPUs (zkaes_ctx_create_multi: the leader, rank 0, owns the peers)
     int rank = 0, nranks = 1;

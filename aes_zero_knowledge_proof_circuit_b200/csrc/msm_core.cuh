@@ -444,12 +444,14 @@ ZK_HD XYZZ<C> msm_reduce_segment(const XYZZ<C>* B, uint32_t nbw, uint32_t seg, u
 }
 
 // ---- plan ---------------------------------------------------------------------------------------------------------------
-// Window size: minimise  W * (1.15 n_local + 4 * 2^(c-1))  -- per window n_local mixed additions in the accumulation plus
+// Window size: minimise  W * (1.15 n_local + 5 * 2^(c-1))  -- per window n_local mixed additions in the accumulation plus
 // the sort passes (~0.15 of a mixed addition per entry), and two full additions per bucket in the reduction (measured
-// ~4 mixed-addition times per bucket, profiles/r1_launches_msm_2p26_slices.txt) -- over c <= c_max.  c_max bounds the bucket
-// array (2^(c-1) W XYZZ points: 4.8 GB at c = 22).  n_local = points per rank (the plan is a function of the global
+// 4-5 mixed-addition times per bucket, profiles/r1_launches_msm_2p26_slices.txt, r2_launches_bench_4k.txt) -- over c <= c_max.
+// c_max bounds the bucket array (2^(c-1) W XYZZ points: 4.8 GB at c = 22, 8.9 GB at c = 23).  253 = 11 x 23: from ~2^27 terms on
+// the plan is 11 windows of 23 bits instead of 12 of 22 -- the 4 KiB proof went 14.94 -> 14.60 s with the cap raised from 22 to 23
+// (same proof bytes; gpurun_out/j3_bench_c2{2,3}.json).  n_local = points per rank (the plan is a function of the global
 // (n, nranks) so that every rank derives the same windows).
-inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1, int c_max = 22) {
+inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1, int c_max = 23) {
     MsmPlan p;
     int c = forced_c;
     if (c <= 0) {
@@ -457,7 +459,7 @@ inline MsmPlan msm_make_plan(size_t n, int fr_bits, int forced_c, int nranks = 1
         double best = 0;
         for (int cc = 3; cc <= c_max; ++cc) {
             const int W = (fr_bits + cc - 1) / cc;
-            const double cost = W * (1.15 * n_local + 4.0 * (double)((size_t)1 << (cc - 1)));
+            const double cost = W * (1.15 * n_local + 5.0 * (double)((size_t)1 << (cc - 1)));
             if (c <= 0 || cost < best) {
                 best = cost;
                 c = cc;

@@ -7,7 +7,7 @@ from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 pytestmark = pytest.mark.gpu
 CURVES = [377, 381]
-TUNING_DEFAULTS = {"msm_acc_blocks": 3, "msm_window_max": 22, "msm_pair_round": 0, "msm_madd_call": 1}  # csrc/common.cuh zkaes_ctx
+TUNING_DEFAULTS = {"msm_acc_blocks": 3, "msm_window_max": 23, "msm_pair_round": 0, "msm_madd_call": 1}  # csrc/common.cuh zkaes_ctx
 
 
 def rand_fq(rng, curve, n):
@@ -151,7 +151,7 @@ def test_msm_window_sizes(ctx, oracle, window):
         ctx.set_msm_window(0)
 
 
-@pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 23, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
+@pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 22, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
                                     {"msm_pair_round": 1, "msm_window_max": 10}, {"msm_pair_round": 2, "msm_window_max": 10},
                                     {"msm_pair_round": 3, "msm_window_max": 9}, {"msm_madd_call": 0}, {"msm_madd_call": 1},
                                     {"msm_madd_call": 1, "msm_acc_blocks": 4}, {"msm_madd_call": 0, "msm_acc_blocks": 4}])
