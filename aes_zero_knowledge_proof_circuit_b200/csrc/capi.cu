@@ -19,6 +19,7 @@ template <class F> int selftest_field_asm(zkaes_ctx*, int, const void*, const vo
 template <class F> int selftest_field_portable(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class C> int selftest_g1(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template <class F> int selftest_field_call(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+int selftest_fq52(zkaes_ctx*, const void*, const void*, void*, size_t);
 }
 using namespace zk;
 
@@ -446,6 +447,10 @@ int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int va
     NEED_CTX(ctx);
     if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
     if (curve_id != 377 && curve_id != 381) return fail(ctx, ZK_ERR_ARG, "unknown curve_id");
+    if (variant == 3) {  // FP64-limb product (csrc/fq52.cuh), BLS12-377 Fq, multiplication only; result in Montgomery radix 2^416
+        if (curve_id != 377 || field != 1 || op != 2) return fail(ctx, ZK_ERR_ARG, "selftest: variant 3 is the BLS12-377 Fq product only");
+        return selftest_fq52(ctx, a, b, out, count);
+    }
     if (variant == 2) {  // products through the out-of-line multiplier of the MSM inner loop (Fp::mul_call)
         if (curve_id == 377) return field ? selftest_field_call<Fq377>(ctx, op, a, b, out, count) : selftest_field_call<Fr377>(ctx, op, a, b, out, count);
         return field ? selftest_field_call<Fq381>(ctx, op, a, b, out, count) : selftest_field_call<Fr381>(ctx, op, a, b, out, count);

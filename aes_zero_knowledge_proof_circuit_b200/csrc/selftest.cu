@@ -1,6 +1,7 @@
 // Self-test instantiation with the production (generated PTX) multiplier + G1 formula checks.
 #define ZK_SELFTEST_NAME(x) x##_asm
 #include "selftest_impl.cuh"
+#include "fq52.cuh"
 namespace zk {
 template int selftest_field_asm<Fr377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template int selftest_field_asm<Fq377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
@@ -39,6 +40,31 @@ template int selftest_field_call<Fr377>(zkaes_ctx*, int, const void*, const void
 template int selftest_field_call<Fq377>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template int selftest_field_call<Fr381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
 template int selftest_field_call<Fq381>(zkaes_ctx*, int, const void*, const void*, void*, size_t);
+
+// variant 3: the FP64-limb product of csrc/fq52.cuh (BLS12-377 Fq only; an experiment, not used by the prover): a, b as 12 words ->
+// 8 x 52-bit limbs in doubles -> DFMA hi/lo Montgomery product -> 12 words.  Its Montgomery radix is 2^416: out = a b 2^-416 mod q.
+__global__ void k_selftest_fq52(const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fq52 r = fq52_mont_mul<Fq377P52>(fq52_from_words(a + 12 * i), fq52_from_words(b + 12 * i));
+    fq52_to_words(r, out + 12 * i);
+}
+int selftest_fq52(zkaes_ctx* ctx, const void* a, const void* b, void* out, size_t count) {
+    cudaStream_t st = ctx->stream;
+    DevBuf da, db, dout;
+    const size_t bytes = 48 * count;
+    ZK_CUDA(ctx, da.alloc(bytes, st));
+    ZK_CUDA(ctx, db.alloc(bytes, st));
+    ZK_CUDA(ctx, dout.alloc(bytes, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    k_selftest_fq52<<<cdiv(count, 128), 128, 0, st>>>(da.as<uint32_t>(), db.as<uint32_t>(), dout.as<uint32_t>(), count);
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    ZK_CUDA(ctx, cudaMemcpyAsync(out, dout.p, bytes, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    return ZK_OK;
+}
 
 template <class C>
 __global__ void k_selftest_g1(const Affine<C>* a, const Affine<C>* b, Affine<C>* out, size_t n, int op) {

@@ -139,7 +139,9 @@ int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[3
 
 /* ---- on-device self test of the field / curve arithmetic (used by tests/, not by the product path) -------
  * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul.  variant: 0 = generated PTX multiplier (inlined), 1 = portable CIOS,
- * 2 = the out-of-line copy of the PTX multiplier that the MSM inner loop and the curve formulas call.
+ * 2 = the out-of-line copy of the PTX multiplier that the MSM inner loop and the curve formulas call,
+ * 3 = the FP64-limb product of csrc/fq52.cuh (an experiment: curve 377, field 1, op 2 only; out = a b 2^-416 mod q, i.e. its own
+ *     Montgomery radix -- tests compare against big integers).
  * a, b, out are host arrays of `count` elements (32 B or 48 B each). */
 int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int variant, const void* a_host, const void* b_host,
                          void* out_host, size_t count);

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <vector>
 #include "ec.cuh"
+#include "fq52.cuh"
 
 using namespace zk;
 
@@ -145,6 +146,40 @@ __global__ void __launch_bounds__(128) k_fqmul_call(uint32_t* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// ---- FP64-limb Fq product (csrc/fq52.cuh): alone, and warp-specialised next to the IMAD.WIDE product -----------------------------------
+// DF warps of every block (warp index < DF of 4) run the 52-bit-limb DFMA product, the others the 32-bit-limb IMAD.WIDE product; each kind
+// gets its own iteration count so that both finish together.  DF = 4: FP64 only; DF = 0: IMAD.WIDE only.
+template <int DF>
+__global__ void __launch_bounds__(128) k_fq_hybrid(uint32_t* out, int iters_imad, int iters_dfma) {
+    const int warp = threadIdx.x >> 5;
+    uint32_t s = 0;
+    if (warp < DF) {
+        Fq52 x, y;
+        for (int i = 0; i < 8; ++i) {
+            x.v[i] = (double)(((uint64_t)(threadIdx.x + 1) * (i + 3) * 0x9e3779b97f4aull) & (i == 7 ? 0xfffull : ZK52_MASK));
+            y.v[i] = (double)(((uint64_t)(blockIdx.x + 7) * (i + 11) * 0xc2b2ae3d27d4ull) & (i == 7 ? 0xfffull : ZK52_MASK));
+        }
+        for (int it = 0; it < iters_dfma; ++it) x = fq52_mont_mul<Fq377P52>(x, y);
+        for (int i = 0; i < 8; ++i) s ^= (uint32_t)__double_as_longlong(x.v[i]);
+    } else {
+        Fq377 x, y;
+        for (int i = 0; i < 12; ++i) {
+            x.v[i] = (threadIdx.x + 1) * (i + 3) * 2654435761u >> (i == 11 ? 8 : 0);
+            y.v[i] = (blockIdx.x + 7) * (i + 11) * 40503u >> (i == 11 ? 8 : 0);
+        }
+        for (int it = 0; it < iters_imad; ++it) x = Fq377::mul_call(x, y);
+        for (int i = 0; i < 12; ++i) s ^= x.v[i];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// bit-exactness of the FP64 product on the device: a, b as 12 words -> 52-bit limbs -> product -> 12 words (Montgomery form with R = 2^416)
+__global__ void k_fq52_check(const uint32_t* a, const uint32_t* b, uint32_t* o, int n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    Fq52 r = fq52_mont_mul<Fq377P52>(fq52_from_words(a + 12 * t), fq52_from_words(b + 12 * t));
+    fq52_to_words(r, o + 12 * t);
+}
+
 __global__ void k_make_pts(G1Affine377* pts, int n) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -206,6 +241,23 @@ int main() {
     RUN_MUL(2, 1, "register modulus") RUN_MUL(2, 2, "register modulus")
     RUN_MUL(3, 1, "portable CIOS")
 
+    {
+        // device check of the FP64 product against the 32-bit-limb multiplier: both compute a*b/R mod q with their own R (2^416 vs 2^384),
+        // so compare fq52(a, b) with imad(imad(a, b), 2^352 mod q in R=2^384 form)... simpler: the host recomputes with __int128-free schoolbook
+        // in tests/test_fq52.py (CPU tier, same header under round-toward-zero); here only a smoke value is printed.
+        int iters = 1000;
+#define RUN_HYB(DF, II, ID) { \
+        for (int bps = 4; bps <= 8; bps *= 2) { \
+            int blocks = sms * bps; \
+            k_fq_hybrid<DF><<<blocks, 128>>>(out, 5, 5); \
+            cudaEventRecord(e0); k_fq_hybrid<DF><<<blocks, 128>>>(out, II, ID); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); \
+            double muls = (double)blocks * 32.0 * ((4 - DF) * (double)(II) + DF * (double)(ID)); float ms = time_ms(e0, e1); \
+            printf("fq product, %d of 4 warps on the FP64 pipe (iters imad %d / dfma %d) blocks/SM=%d: %.2f Gmul/s (%.2f clk/SM/mul)\n", DF, II, ID, bps, muls / ms / 1e6, (ms * 1e-3) * clk_khz * 1e3 * sms / muls); } }
+        RUN_HYB(0, iters, 0) RUN_HYB(4, 0, iters)
+        RUN_HYB(1, iters, iters) RUN_HYB(1, iters, 2 * iters) RUN_HYB(1, iters, 3 * iters)
+        RUN_HYB(2, iters, iters) RUN_HYB(2, iters, iters / 2) RUN_HYB(2, iters, 3 * iters / 2)
+        RUN_HYB(3, iters, iters / 2) RUN_HYB(3, iters, iters / 3)
+    }
     int npts = 4096;
     G1Affine377* pts; CK(cudaMalloc(&pts, sizeof(G1Affine377) * npts));
     k_make_pts<<<npts / 64, 64>>>(pts, npts);
