@@ -39,12 +39,12 @@ static thread_local std::string g_host_err;
 template <class C>
 static int msm_windows_impl(zkaes_ctx* ctx, const void* bases, const void* scalars, size_t n_local, size_t n_total, int mont,
                             void* windows_dev) {
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, 1, ctx->msm_window_max);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, ctx->msm_plan_ranks, ctx->msm_window_max);
     return msm_window_sums<C>(ctx, bases, scalars, n_local, mont & 1, p, windows_dev, (mont >> 1) & 1);
 }
 template <class C>
 static int msm_fold_impl(zkaes_ctx* ctx, const void* gathered, int n_ranks, size_t n_total, void* out96) {
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, 1, ctx->msm_window_max);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, C::FrP::BITS, ctx->msm_window_bits, ctx->msm_plan_ranks, ctx->msm_window_max);
     std::vector<XYZZ<C>> h((size_t)n_ranks * p.W);
     ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), gathered, sizeof(XYZZ<C>) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -325,6 +325,12 @@ int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
     } else if (k == "msm_acc_blocks") {
         if (value != 3 && value != 4) return fail(ctx, ZK_ERR_ARG, "msm_acc_blocks must be 3 or 4");
         ctx->msm_acc_blocks = value;
+    } else if (k == "msm_plan_ranks") {
+        if (value < 1 || value > 1024) return fail(ctx, ZK_ERR_ARG, "msm_plan_ranks must be in 1..1024");
+        ctx->msm_plan_ranks = value;
+    } else if (k == "msm_prefetch") {
+        if (value < 0 || value > 2) return fail(ctx, ZK_ERR_ARG, "msm_prefetch must be 0, 1 or 2");
+        ctx->msm_prefetch = value;
     } else if (k == "msm_madd_call") {
         if (value != 0 && value != 1) return fail(ctx, ZK_ERR_ARG, "msm_madd_call must be 0 or 1");
         ctx->msm_madd_call = value;
@@ -394,7 +400,7 @@ int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, si
 size_t zkaes_msm_g1_windows_bytes(zkaes_ctx* ctx, int curve_id, size_t n_total) {
     if (!ctx) return 0;
     int bits = curve_id == 377 ? Fr377Params::BITS : Fr381Params::BITS;
-    MsmPlan p = msm_make_plan(n_total ? n_total : 1, bits, ctx->msm_window_bits, 1, ctx->msm_window_max);
+    MsmPlan p = msm_make_plan(n_total ? n_total : 1, bits, ctx->msm_window_bits, ctx->msm_plan_ranks, ctx->msm_window_max);
     return (size_t)p.W * 192;
 }
 int zkaes_msm_g1_windows(zkaes_ctx* ctx, int curve_id, const void* bases, const void* scalars, size_t n_local, size_t n_total,
@@ -445,7 +451,7 @@ int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[3
 int zkaes_selftest_field(zkaes_ctx* ctx, int curve_id, int field, int op, int variant, const void* a, const void* b, void* out,
                          size_t count) {
     NEED_CTX(ctx);
-    if (!a || !b || !out || op < 0 || op > 2) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
+    if (!a || !b || !out || op < 0 || op > 3) return fail(ctx, ZK_ERR_ARG, "selftest: bad arguments");
     if (curve_id != 377 && curve_id != 381) return fail(ctx, ZK_ERR_ARG, "unknown curve_id");
     if (variant == 3) {  // FP64-limb product (csrc/fq52.cuh), BLS12-377 Fq, multiplication only; result in Montgomery radix 2^416
         if (curve_id != 377 || field != 1 || op != 2) return fail(ctx, ZK_ERR_ARG, "selftest: variant 3 is the BLS12-377 Fq product only");

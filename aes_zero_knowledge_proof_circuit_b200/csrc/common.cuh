@@ -98,6 +98,8 @@ struct zkaes_ctx {
     int msm_pair_round = 0;  // R = number of batched-affine pair rounds before the XYZZ accumulation (msm_core.cuh); 0 = plain accumulation.
                              // Off by default: one round measured break-even (profiles/r1_launches_msm_2p26_pair_round.txt)
     int msm_acc_blocks = 3;  // resident blocks per SM of the bucket accumulation kernel (3 or 4)
+    int msm_plan_ranks = 1;  // stand-alone sharded MSM entry points (zkaes_msm_g1_windows / _fold): ranks sharing the MSM, so the window plan fits the per-rank share
+    int msm_prefetch = 0;    // 1 / 2: stage the next entry's point in shared memory (cp.async / cp.async.bulk + mbarrier) while the current one is added
     int msm_madd_call = 1;   // 1: the mixed addition issues its ten products through one out-of-line multiplier (XYZZ::madd_call)
     int msm_window_max = 23;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B: 8.9 GB at c = 23, W = 11)
     // multi-GPU: this context's rank among the contexts that share one sharded MSM (comm.cu) -- one process per GPU

@@ -95,12 +95,12 @@ struct XYZZ {
         if (p.is_inf() || p.y.is_zero()) return inf();
         XYZZ r;
         Fq u = p.y.dbl();
-        Fq v = Fq::mul_call(u, u);
+        Fq v = Fq::sqr_call(u);
         Fq w = Fq::mul_call(u, v);
         Fq s = Fq::mul_call(p.x, v);
-        Fq x2 = Fq::mul_call(p.x, p.x);
+        Fq x2 = Fq::sqr_call(p.x);
         Fq m = x2.dbl() + x2;
-        r.x = Fq::mul_call(m, m) - s.dbl();
+        r.x = Fq::sqr_call(m) - s.dbl();
         r.y = Fq::mul_call(m, s - r.x) - Fq::mul_call(w, p.y);
         r.zz = v;
         r.zzz = w;
@@ -112,12 +112,12 @@ struct XYZZ {
         if (is_inf() || y.is_zero()) return inf();
         XYZZ r;
         Fq u = y.dbl();
-        Fq v = Fq::mul_call(u, u);
+        Fq v = Fq::sqr_call(u);
         Fq w = Fq::mul_call(u, v);
         Fq s = Fq::mul_call(x, v);
-        Fq x2 = Fq::mul_call(x, x);
+        Fq x2 = Fq::sqr_call(x);
         Fq m = x2.dbl() + x2;
-        r.x = Fq::mul_call(m, m) - s.dbl();
+        r.x = Fq::sqr_call(m) - s.dbl();
         r.y = Fq::mul_call(m, s - r.x) - Fq::mul_call(w, y);
         r.zz = Fq::mul_call(v, zz);
         r.zzz = Fq::mul_call(w, zzz);
@@ -145,7 +145,7 @@ struct XYZZ {
                 *this = inf();
             return;
         }
-        Fq pp = Fq::mul_after(pp_, pp_, tok);
+        Fq pp = Fq::mul_after(pp_, pp_, tok);  // (the inlined form keeps products only: its ordering tokens chain through mul_after)
         Fq ppp = Fq::mul_after(pp_, pp, tok);
         Fq q = Fq::mul_after(x, pp, tok);
         Fq r2 = Fq::mul_after(r_, r_, tok);
@@ -175,10 +175,10 @@ struct XYZZ {
                 *this = inf();
             return;
         }
-        Fq pp = Fq::mul_call(pp_, pp_);
+        Fq pp = Fq::sqr_call(pp_);
         Fq ppp = Fq::mul_call(pp_, pp);
         Fq q = Fq::mul_call(x, pp);
-        Fq r2 = Fq::mul_call(r_, r_);
+        Fq r2 = Fq::sqr_call(r_);
         Fq x3 = r2 - ppp - q.dbl();
         Fq yp = Fq::mul_call(y, ppp);
         zz = Fq::mul_call(zz, pp);
@@ -207,10 +207,10 @@ struct XYZZ {
                 *this = inf();
             return;
         }
-        Fq pp = Fq::mul_call(pp_, pp_);
+        Fq pp = Fq::sqr_call(pp_);
         Fq ppp = Fq::mul_call(pp_, pp);
         Fq q = Fq::mul_call(u1, pp);
-        Fq x3 = Fq::mul_call(r_, r_) - ppp - q.dbl();
+        Fq x3 = Fq::sqr_call(r_) - ppp - q.dbl();
         y = Fq::mul_call(r_, q - x3) - Fq::mul_call(s1, ppp);
         x = x3;
         zz = Fq::mul_call(Fq::mul_call(zz, o.zz), pp);

@@ -240,7 +240,22 @@ struct Fp {
         r.reduce_once();
         return r;
     }
-    ZK_HD Fp sqr() const { return *this * *this; }
+    // Squaring.  Device, 12 limbs: the generated dedicated squaring (tools/gen_mont_asm.py sqr_rows_for: off-diagonal products once and
+    // doubled, then a separate reduction -- 222 wide multiplies instead of 288).  Everything else: a product.
+    ZK_HD Fp sqr() const {
+#if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
+        if constexpr (N == 12) {
+            Fp r;
+            uint32_t m[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) m[i] = P::MOD(i);
+            mont_sqr_raw_12(r.v, v, m, zk_c_mont_inv[P::FIELD_ID], zk_c_zero);
+            r.reduce_once();
+            return r;
+        }
+#endif
+        return *this * *this;
+    }
 
     // a * b, scheduled after `tok` was produced (device: a false data dependency on b[0]; host: plain product).
     // `tok` is then replaced by a limb of the result so that calls chain.
@@ -262,6 +277,7 @@ struct Fp {
     // The MSM inner loop issues its ten products through this so that the loop body is ~10 KB of SASS instead of the 84 KB of ten
     // inlined copies, which thrashed the 32 KB instruction cache (20 % "no instruction" stalls in the round-1 ncu capture).
     static ZK_HD Fp mul_call(const Fp& a, const Fp& b);
+    static ZK_HD Fp sqr_call(const Fp& a);  // the same for sqr(): one out-of-line copy of the dedicated squaring
 
     // wire-format hooks: the arkworks limbs ARE the working form
     static ZK_HD Fp unpack(const uint32_t* w) {
@@ -346,6 +362,34 @@ __device__ __noinline__ FpWords<P> fp_mul_out_of_line(FpWords<P> a, FpWords<P> b
     return o;
 }
 #endif
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ FpWords<P> fp_sqr_out_of_line(FpWords<P> a) {
+    Fp<P> x;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) x.v[i] = a.v[i];
+    const Fp<P> r = x.sqr();
+    FpWords<P> o;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) o.v[i] = r.v[i];
+    return o;
+}
+#endif
+template <class P>
+ZK_HD Fp<P> Fp<P>::sqr_call(const Fp<P>& a) {
+#if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)
+    FpWords<P> x;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) x.v[i] = a.v[i];
+    const FpWords<P> o = fp_sqr_out_of_line<P>(x);
+    Fp<P> r;
+#pragma unroll
+    for (int i = 0; i < P::N; ++i) r.v[i] = o.v[i];
+    return r;
+#else
+    return a * a;
+#endif
+}
 template <class P>
 ZK_HD Fp<P> Fp<P>::mul_call(const Fp<P>& a, const Fp<P>& b) {
 #if defined(__CUDA_ARCH__) && !defined(ZK_FF_PORTABLE)

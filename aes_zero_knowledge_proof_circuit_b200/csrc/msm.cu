@@ -192,24 +192,32 @@ int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32
 // BLOCKS = resident blocks per SM the register allocation is held to: 3 (166 registers, no spills) or 4 (128 registers,
 // 92 bytes of spills, 16 instead of 12 warps per SM to cover the IMAD dependency waits).
 // CALL: the ten field products of a mixed addition go through one out-of-line multiplier (XYZZ::madd_call) instead of ten
-// inlined copies -- the loop body then fits the instruction cache.
-template <class C, int BLOCKS, bool CALL>
+// inlined copies -- the loop body then fits the instruction cache.  PF: the next entry's point is staged in shared memory while the
+// current one is added (msm_core.cuh: 1 = cp.async, 2 = cp.async.bulk + mbarrier).
+template <class C, int BLOCKS, bool CALL, int PF>
 __global__ void __launch_bounds__(128, BLOCKS) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                                 const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t n_slices, uint32_t L,
                                                                 XYZZ<C>* __restrict__ buckets, XYZZ<C>* __restrict__ head,
                                                                 XYZZ<C>* __restrict__ tail, uint32_t* __restrict__ tail_bucket) {
-    msm_slice_accumulate<C, CALL>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, nb, sorted, bases, buckets, head, tail, tail_bucket);
+    __shared__ __align__(128) uint8_t s_pts[PF ? 128 * 192 : 16];
+    __shared__ __align__(16) uint64_t s_bars[PF == 2 ? 128 * 2 : 2];
+    msm_slice_accumulate<C, CALL, PF>(blockIdx.x * blockDim.x + threadIdx.x, n_slices, L, offsets, nb, sorted, bases, buckets, head, tail, tail_bucket,
+                                      s_pts, s_bars);
 }
 template <class C>
 static void msm_launch_accumulate(zkaes_ctx* ctx, size_t slices, const uint32_t* bases, const uint32_t* sorted, const uint32_t* offsets, uint32_t nb,
                                   uint32_t L, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket) {
     const unsigned grid = cdiv(slices, 128);
     cudaStream_t st = ctx->stream;
-#define ZK_ACC(B, CALLV) k_msm_accumulate<C, B, CALLV><<<grid, 128, 0, st>>>(bases, sorted, offsets, nb, (uint32_t)slices, L, buckets, head, tail, tail_bucket)
-    if (ctx->msm_madd_call) {
-        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, true); else ZK_ACC(3, true);
+#define ZK_ACC(B, CALLV, PFV) k_msm_accumulate<C, B, CALLV, PFV><<<grid, 128, 0, st>>>(bases, sorted, offsets, nb, (uint32_t)slices, L, buckets, head, tail, tail_bucket)
+    if (ctx->msm_prefetch == 1) {
+        ZK_ACC(3, true, 1);
+    } else if (ctx->msm_prefetch == 2) {
+        ZK_ACC(3, true, 2);
+    } else if (ctx->msm_madd_call) {
+        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, true, 0); else ZK_ACC(3, true, 0);
     } else {
-        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, false); else ZK_ACC(3, false);
+        if (ctx->msm_acc_blocks == 4) ZK_ACC(4, false, 0); else ZK_ACC(3, false, 0);
     }
 #undef ZK_ACC
     ctx->launches++;

@@ -137,14 +137,86 @@ ZK_HD void msm_store_xyzz(XYZZ<C>* p, const XYZZ<C>& v) {
 #endif
 }
 
+// ---- asynchronous staging of the NEXT entry's point in shared memory (device only) -----------------------------------------------------
+// north_star sketches "point windows staged into shared memory via TMA".  After the sort a bucket's points are a gather of 96-byte
+// records, so the only thing to stage is the next record of each thread: while the ten products of entry `pos` run, the point of entry
+// pos + 1 travels global -> shared without passing through registers, and the sorted index of entry pos + 2 is already in a register.
+//   PF = 1: six 16-byte cp.async (LDGSTS) per point, cp.async.wait_group per thread
+//   PF = 2: ONE 96-byte bulk copy (cp.async.bulk, the TMA engine) per point, completion on a per-thread mbarrier (tx-count 96)
+// Shared memory per block of 128 threads: 2 stages x 96 B x 128 = 24 KB (+ 2 KB of mbarriers).  Measured: profiles/r2_quick_perf_prefetch.txt.
+#if defined(__CUDA_ARCH__)
+struct MsmStage {
+    uint32_t pts;   // shared-space address of this thread's two 96-byte slots (slot s at pts + s * 96 * blockDim.x ... see msm_stage_slot)
+    uint32_t bars;  // shared-space address of this thread's two mbarriers (PF = 2)
+};
+__device__ __forceinline__ uint32_t msm_stage_slot(const MsmStage& st, int s) { return st.pts + (uint32_t)s * 96u; }
+template <int PF>
+__device__ __forceinline__ void msm_stage_init(MsmStage& st, void* smem_pts, void* smem_bars) {
+    // thread-private slots: [thread][stage][96 B] so that the bulk copy's destination is contiguous
+    st.pts = (uint32_t)__cvta_generic_to_shared(smem_pts) + threadIdx.x * 192u;
+    st.bars = (uint32_t)__cvta_generic_to_shared(smem_bars) + threadIdx.x * 16u;
+    if (PF == 2) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st.bars));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st.bars + 8u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+}
+template <int PF>
+__device__ __forceinline__ void msm_stage_issue(const MsmStage& st, int s, const uint32_t* bases, uint32_t idx) {
+    const uint32_t dst = msm_stage_slot(st, s);
+    const void* src = bases + (size_t)idx * 24;
+    if (PF == 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"((const char*)src + 16 * k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        const uint32_t bar = st.bars + 8u * s;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's earlier generic-proxy reads of the slot before the async-proxy write
+        asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], 96; }" ::"r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 96, [%2];" ::"r"(dst), "l"(src), "r"(bar) : "memory");
+    }
+}
+// waits for the copy into slot s (`pending` = copies issued after it that may still be in flight: 0 or 1), then reads the point
+template <class C, int PF>
+__device__ __forceinline__ Affine<C> msm_stage_take(const MsmStage& st, int s, uint32_t parity, int pending) {
+    if (PF == 1) {
+        if (pending)
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        const uint32_t bar = st.bars + 8u * s;
+        asm volatile(
+            "{ .reg .pred p;\n"
+            "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@!p bra W; }" ::"r"(bar), "r"(parity) : "memory");
+    }
+    using Fq = typename Affine<C>::Fq;
+    uint32_t w[24];
+    const uint32_t src = msm_stage_slot(st, s);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * k]), "=r"(w[4 * k + 1]), "=r"(w[4 * k + 2]), "=r"(w[4 * k + 3]) : "r"(src + 16u * k) : "memory");
+    Affine<C> r;
+    r.x = Fq::unpack(w);
+    r.y = Fq::unpack(w + 12);
+    return r;
+}
+#endif
+
 // ---- accumulate: thread t owns sorted[t L, min((t+1) L, E)) ------------------------------------------------------------
 // offsets has nb + 1 entries (offsets[nb] = E = number of sorted entries).  buckets must hold valid points (zeroed =
 // infinity before the first chunk).  head / tail / tail_bucket have one slot per slice; tail_bucket[t] names the bucket
 // whose partial sits in tail[t] (MSM_NO_BUCKET if none), which is all the merge pass needs.
 static constexpr uint32_t MSM_NO_BUCKET = 0xffffffffu;
-template <class C, bool CALL = false>
+template <class C, bool CALL = false, int PF = 0>
 ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const uint32_t* offsets, uint32_t nb, const uint32_t* sorted,
-                                const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket) {
+                                const uint32_t* bases, XYZZ<C>* buckets, XYZZ<C>* head, XYZZ<C>* tail, uint32_t* tail_bucket,
+                                void* smem_pts = nullptr, void* smem_bars = nullptr) {
+    (void)smem_pts;
+    (void)smem_bars;
     if (t >= n_slices) return;
     const uint32_t E = offsets[nb];
     const uint64_t lo64 = (uint64_t)t * L;
@@ -162,7 +234,32 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
     uint32_t seg_end = offsets[b + 1];
     bool open_head = offsets[b] < lo;  // the bucket began in an earlier slice
     XYZZ<C> acc = open_head ? XYZZ<C>::inf() : msm_load_xyzz<C>(buckets + b);
+#if defined(__CUDA_ARCH__)
+    // software pipeline of the staged variants: e_cur = entry pos (its point is in flight to slot (pos - lo) & 1), e_next = entry pos + 1
+    MsmStage stage;
+    uint32_t e_cur = 0, e_next = 0;
+    if (PF) {
+        msm_stage_init<PF>(stage, smem_pts, smem_bars);
+        e_cur = sorted ? sorted[lo] : lo;
+        msm_stage_issue<PF>(stage, 0, bases, e_cur & 0x7fffffffu);
+        if (lo + 1 < hi) e_next = sorted ? sorted[lo + 1] : lo + 1;
+    }
+#endif
     for (uint32_t pos = lo; pos < hi; ++pos) {
+#if defined(__CUDA_ARCH__)
+        Affine<C> staged;
+        uint32_t e_staged = 0;
+        if (PF) {
+            const int slot = (int)((pos - lo) & 1u);
+            const bool more = pos + 1 < hi;
+            if (more) msm_stage_issue<PF>(stage, slot ^ 1, bases, e_next & 0x7fffffffu);  // slot ^ 1 was consumed in the previous iteration
+            const uint32_t e_next2 = pos + 2 < hi ? (sorted ? sorted[pos + 2] : pos + 2) : 0u;
+            staged = msm_stage_take<C, PF>(stage, slot, ((pos - lo) >> 1) & 1u, more ? 1 : 0);
+            e_staged = e_cur;
+            e_cur = e_next;
+            e_next = e_next2;
+        }
+#endif
         if (pos == seg_end) {  // bucket b is complete: flush, move to the next non-empty bucket
             if (open_head) {
                 msm_store_xyzz<C>(head + t, acc);
@@ -189,8 +286,13 @@ ZK_HD void msm_slice_accumulate(uint32_t t, uint32_t n_slices, uint32_t L, const
             }
             acc = msm_load_xyzz<C>(buckets + b);
         }
+#if defined(__CUDA_ARCH__)
+        const uint32_t e = PF ? e_staged : (sorted ? sorted[pos] : pos);
+        Affine<C> pt = PF ? staged : msm_load_affine<C>(bases, e & 0x7fffffffu);
+#else
         const uint32_t e = sorted ? sorted[pos] : pos;  // no index array: the points themselves are in bucket order (pair round output)
         Affine<C> pt = msm_load_affine<C>(bases, e & 0x7fffffffu);
+#endif
         if (e >> 31) pt.y = pt.y.neg();
         if (CALL)
             acc.madd_call(pt);

@@ -16,6 +16,7 @@ __global__ void k_selftest_field_call(const F* a, const F* b, F* out, size_t n, 
     F x = a[i], y = b[i], r;
     if (op == 0) r = x + y;
     else if (op == 1) r = x - y;
+    else if (op == 3) r = F::sqr_call(x);
     else r = F::mul_call(x, y);
     out[i] = r;
 }

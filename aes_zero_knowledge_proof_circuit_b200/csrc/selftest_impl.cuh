@@ -12,6 +12,7 @@ __global__ void ZK_SELFTEST_NAME(k_selftest_field)(const F* a, const F* b, F* ou
     F x = a[i], y = b[i], r;
     if (op == 0) r = x + y;
     else if (op == 1) r = x - y;
+    else if (op == 3) r = x.sqr();
     else r = x * y;
     out[i] = r;
 }

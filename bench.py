@@ -55,10 +55,11 @@ def emit(line: dict):
 SEED_TAU, SEED_GAMMA, SEED_ZK = bytes(range(32)), bytes(range(1, 33)), bytes([7] * 32)
 AES_KEY = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")  # FIPS-197 (SURVEY.md 8(d) synthetic inputs)
 # Integer-pipe peak of one B200, tools/ubench.cu (profiles/ubench_r2.txt): 9.05e12 IMAD.WIDE/s (31.1 /clk/SM x 148 SMs x 1965 MHz; every
-# 32x32->64 multiply-add runs at half the IMAD rate on sm_100).  A mixed addition is 10 Fq products x 288 IMAD.WIDE (12 x 12 partial
-# products + 12 x 12 reduction), so the pipe allows 9.05e12 / 2880 = 3.14 G mixed additions/s; that is the denominator of alu.frac.
+# 32x32->64 multiply-add runs at half the IMAD rate on sm_100).  A mixed addition is 8 Fq products x 288 IMAD.WIDE (12 x 12 partial
+# products + 12 x 12 reduction) + 2 dedicated squarings x 222 (78 + 144) = 2748, so the pipe allows 9.05e12 / 2748 = 3.29 G mixed
+# additions/s; that is the denominator of alu.frac.
 IMAD_WIDE_PEAK_PER_S = 9.05e12
-IMAD_WIDE_PER_MADD = 10 * 288
+IMAD_WIDE_PER_MADD = 8 * 288 + 2 * 222
 MADD_PEAK_PER_S = IMAD_WIDE_PEAK_PER_S / IMAD_WIDE_PER_MADD
 MADD_UBENCH_PER_S = 2.46e9  # the same addition formula in a register-resident microbenchmark loop (tools/ubench.cu k_madd)
 
@@ -309,7 +310,7 @@ def bench_prove(args, rank, world, local_rank):
                      "alu": {"madds_per_s": madds_per_s, "imad_wide_per_s": madds_per_s * IMAD_WIDE_PER_MADD, "imad_wide_peak_per_s": IMAD_WIDE_PEAK_PER_S,
                              "frac": madds_per_s / MADD_PEAK_PER_S, "madd_peak_per_s": MADD_PEAK_PER_S,
                              "frac_of_microbenchmark": madds_per_s / MADD_UBENCH_PER_S,
-                             "note": "the kernel is integer-multiplier bound (10 Fq products = 2880 IMAD.WIDE per mixed addition): frac = IMAD.WIDE issued per "
+                             "note": "the kernel is integer-multiplier bound (8 Fq products + 2 squarings = 2748 IMAD.WIDE per mixed addition): frac = IMAD.WIDE issued per "
                                      "second / the measured IMAD.WIDE pipe peak; the HBM fraction above is reported as the contract asks"}},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "constraints/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": msg_len + 16 + 32,
                 "d2h_bytes_per_step": msg_len + len(proof)},
@@ -353,6 +354,7 @@ def bench_msm(args, rank, world, local_rank):
     import aes_zero_knowledge_proof_circuit_b200 as zk
     curve = args.curve
     ctx = zk.Context(local_rank)
+    ctx.set_tuning("msm_plan_ranks", world)  # the window plan of the stand-alone entry points should fit the per-rank share
     log_n = args.log_n
     n_total = 1 << log_n
     n_local = n_total // world

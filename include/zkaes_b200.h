@@ -89,6 +89,10 @@ int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
  * is 2^(c-1) * ceil(253/c) points of 192 B), "msm_acc_blocks" (resident blocks per SM of the bucket accumulation: 3 or 4),
  * "msm_pair_round" (R = 0..4: add the entries of every bucket in pairs as affine points with a shared inversion, R times
  * over, before the XYZZ accumulation; 0 = plain accumulation). */
+/* Further keys: "msm_madd_call" (0 / 1: ten inlined products per mixed addition / ten calls of one out-of-line multiplier, the default),
+ * "msm_prefetch" (0 / 1 / 2: stage the next entry's point in shared memory with cp.async / cp.async.bulk + mbarrier; measured no gain,
+ * default 0), "msm_plan_ranks" (the number of ranks that share a zkaes_msm_g1_windows / zkaes_msm_g1_fold MSM, so that the window plan
+ * fits the per-rank share; every rank must set the same value; default 1). */
 int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value);
 
 /* ---- device memory (thin wrappers so non-CUDA hosts can keep inputs resident in HBM) -------------------- */
@@ -138,7 +142,7 @@ int zkaes_ntt_fr_device(zkaes_ctx* ctx, int curve_id, void* data_dev, uint32_t l
 int zkaes_srs_powers_device(zkaes_ctx* ctx, int curve_id, const uint8_t seed32[32], size_t n, void* out_bases_dev);
 
 /* ---- on-device self test of the field / curve arithmetic (used by tests/, not by the product path) -------
- * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul.  variant: 0 = generated PTX multiplier (inlined), 1 = portable CIOS,
+ * field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 square of a (Fq on the device: the generated dedicated squaring).  variant: 0 = generated PTX multiplier (inlined), 1 = portable CIOS,
  * 2 = the out-of-line copy of the PTX multiplier that the MSM inner loop and the curve formulas call,
  * 3 = the FP64-limb product of csrc/fq52.cuh (an experiment: curve 377, field 1, op 2 only; out = a b 2^-416 mod q, i.e. its own
  *     Montgomery radix -- tests compare against big integers).
@@ -183,7 +187,9 @@ int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* c, const uint8
  * zkaes_synthesize_keys stands in for `synthesize_keys(plaintext_length)` (src/lib.rs:138-174): test SRS from the two
  * seeds (tau, gamma: INSECURE, like the reference's -- README.md:26), circuit shape, Marlin index, all left resident in
  * HBM behind the opaque handle.  Unlike the reference's hard-coded bounds (src/lib.rs:141) the SRS is sized for the
- * requested length.
+ * requested length.  Limits of this build: |K| = next_pow2(max nnz) <= 2^28 (messages up to 8 KiB; larger lengths return
+ * ZKAES_ERR_UNSUPPORTED), and the circuit must have nnz(A) < nnz(B) (ark-marlin's balance_matrices is then the identity; true for
+ * every length of this circuit, checked at key synthesis).
  * zkaes_encrypt stands in for `encrypt(message, secret_key, proving_key)` (src/lib.rs:60-114): witness generation and
  * the Marlin proof.  `zk_seed32` seeds the prover's zero-knowledge randomness (the reference draws it from
  * simpleworks::marlin::generate_rand(); an explicit seed makes runs reproducible).  ct_out receives msg_len bytes.

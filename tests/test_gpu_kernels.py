@@ -7,7 +7,7 @@ from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 pytestmark = pytest.mark.gpu
 CURVES = [377, 381]
-TUNING_DEFAULTS = {"msm_acc_blocks": 3, "msm_window_max": 23, "msm_pair_round": 0, "msm_madd_call": 1}  # csrc/common.cuh zkaes_ctx
+TUNING_DEFAULTS = {"msm_acc_blocks": 3, "msm_window_max": 23, "msm_pair_round": 0, "msm_madd_call": 1, "msm_prefetch": 0}  # csrc/common.cuh zkaes_ctx
 
 
 def rand_fq(rng, curve, n):
@@ -33,9 +33,9 @@ def test_device_field_ops(ctx, oracle, curve, field, variant):
     b[: len(edge)] = edge[::-1]
     a[len(edge): 2 * len(edge)] = edge
     b[len(edge): 2 * len(edge)] = edge
-    for op in (0, 1, 2):
+    for op in (0, 1, 2, 3):  # 3 = square of a (Fq: the dedicated squaring of tools/gen_mont_asm.py) against the oracle's product a * a
         got = ctx.selftest_field(curve, field, op, variant, a, b)
-        exp = oracle.field_op(curve, field, op, a, b)
+        exp = oracle.field_op(curve, field, 2 if op == 3 else op, a, a if op == 3 else b)
         bad = np.nonzero((got != exp).any(axis=1))[0]
         assert bad.size == 0, f"curve {curve} field {field} op {op} variant {variant}: {bad.size} mismatches, first at {bad[:4]}"
 
@@ -55,9 +55,9 @@ def test_device_out_of_line_multiplier(ctx, oracle, curve, field):
     b[: len(edge)] = edge[::-1]
     a[len(edge): 2 * len(edge)] = edge
     b[len(edge): 2 * len(edge)] = edge
-    for op in (0, 1, 2):
+    for op in (0, 1, 2, 3):
         got = ctx.selftest_field(curve, field, op, 2, a, b)
-        exp = oracle.field_op(curve, field, op, a, b)
+        exp = oracle.field_op(curve, field, 2 if op == 3 else op, a, a if op == 3 else b)
         bad = np.nonzero((got != exp).any(axis=1))[0]
         assert bad.size == 0, f"curve {curve} field {field} op {op}: {bad.size} mismatches, first at {bad[:4]}"
 
@@ -154,7 +154,8 @@ def test_msm_window_sizes(ctx, oracle, window):
 @pytest.mark.parametrize("tuning", [{"msm_acc_blocks": 4}, {"msm_window_max": 12}, {"msm_window_max": 22, "msm_acc_blocks": 3}, {"msm_pair_round": 0},
                                     {"msm_pair_round": 1, "msm_window_max": 10}, {"msm_pair_round": 2, "msm_window_max": 10},
                                     {"msm_pair_round": 3, "msm_window_max": 9}, {"msm_madd_call": 0}, {"msm_madd_call": 1},
-                                    {"msm_madd_call": 1, "msm_acc_blocks": 4}, {"msm_madd_call": 0, "msm_acc_blocks": 4}])
+                                    {"msm_madd_call": 1, "msm_acc_blocks": 4}, {"msm_madd_call": 0, "msm_acc_blocks": 4},
+                                    {"msm_prefetch": 1}, {"msm_prefetch": 2}, {"msm_prefetch": 1, "msm_window_max": 10}, {"msm_prefetch": 2, "msm_window_max": 10}])
 def test_msm_tuning_knobs_do_not_change_results(ctx, oracle, tuning):
     """70,000 terms: large enough for the batched-affine pair round (on by default) -- checked against the oracle with the
     round on and off, with degenerate pairs in the buckets (equal points, opposite points, infinity, repeated scalars)."""

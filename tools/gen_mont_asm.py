@@ -27,6 +27,12 @@ class Sim:
             if op == "taint":   # d = d | (x & zero): a scheduling fence, value-preserving because zero == 0
                 env[d] = g(d) | (g(x) & g(y))
                 continue
+            if op == "shl1":    # d = x << 1 (mod 2^32)
+                env[d] = (g(x) << 1) & MASK
+                continue
+            if op == "shf1":    # d = funnel shift left by one of (y : x): (y << 1) | (x >> 31)
+                env[d] = ((g(y) << 1) | (g(x) >> 31)) & MASK
+                continue
             if op in ("mul.lo", "mul.hi"):
                 p = g(x) * g(y)
                 env[d] = (p & MASK) if op == "mul.lo" else (p >> 32)
@@ -48,24 +54,29 @@ class Sim:
                 assert s >> 32 == 0 or op in ("add", "addc", "mad.lo", "madc.hi", "madc.lo"), op
                 env["_ovf"] = env.get("_ovf", 0) | (s >> 32)
 
-def rows_for(n):
+def rows_for(n, square=False):
     """Return the list of rows (each a list of instrs) for an n-limb Montgomery product.
-    Symbols: a0..a{n-1}, b0.., p0.., m, inv, X0..X{n-1}/Y0.. accumulators, r0.. result."""
+    Symbols: a0..a{n-1}, b0.., p0.., m, inv, X0..X{n-1}/Y0.. accumulators, r0.. result.
+    square=True: the rows of sqr_rows_for (multiplier a_i, multiplicand vector with skipped / doubled columns)."""
     assert n % 2 == 0
     rows = []
     E, O = "X", "Y"
+    def cand(i, j):  # multiplicand of column j in row i (None = skipped)
+        if not square:
+            return f"a{j}"
+        return None if j < i else f"a{j}" if j == i else f"e{j}" if j == i + 1 else f"d{j}"
     for i in range(n):
-        bi = f"b{i}"
+        bi = f"a{i}" if square else f"b{i}"
         if i == 0:
             r = []
             for j in range(0, n, 2):
-                r.append(("mul.lo", f"{E}{j}", f"a{j}", bi, None))
-                r.append(("mul.hi", f"{E}{j+1}", f"a{j}", bi, None))
+                r.append(("mul.lo", f"{E}{j}", cand(i, j), bi, None))
+                r.append(("mul.hi", f"{E}{j+1}", cand(i, j), bi, None))
             rows.append(r)
             r = []
             for j in range(1, n, 2):
-                r.append(("mul.lo", f"{O}{j-1}", f"a{j}", bi, None))
-                r.append(("mul.hi", f"{O}{j}", f"a{j}", bi, None))
+                r.append(("mul.lo", f"{O}{j-1}", cand(i, j), bi, None))
+                r.append(("mul.hi", f"{O}{j}", cand(i, j), bi, None))
             rows.append(r)
         else:
             # fence: make this row's head depend on the previous row's last carry-out (E[n-1] is where both of the
@@ -78,16 +89,23 @@ def rows_for(n):
                 src_lo = f"{O}{j+1}" if j + 1 < n else 0
                 src_hi = f"{O}{j+2}" if j + 2 < n else 0
                 last = (j == n - 1)
-                r.append(("madc.lo.cc", f"{O}{j-1}", f"a{j}", bi, src_lo))
-                r.append(("madc.hi" if last else "madc.hi.cc", f"{O}{j}", f"a{j}", bi, src_hi))
+                if cand(i, j) is None:  # skipped column: the two limbs still move down (O >> 2 limbs) and pass the carry on
+                    r.append(("addc.cc", f"{O}{j-1}", src_lo, 0, None))
+                    r.append(("addc" if last else "addc.cc", f"{O}{j}", src_hi, 0, None))
+                else:
+                    r.append(("madc.lo.cc", f"{O}{j-1}", cand(i, j), bi, src_lo))
+                    r.append(("madc.hi" if last else "madc.hi.cc", f"{O}{j}", cand(i, j), bi, src_hi))
             rows.append(r)
             # S2: E += a_even*bi ; carry -> O[n-1]
             r = []
             for j in range(0, n, 2):
-                r.append(("mad.lo.cc" if j == 0 else "madc.lo.cc", f"{E}{j}", f"a{j}", bi, f"{E}{j}"))
-                r.append(("madc.hi.cc", f"{E}{j+1}", f"a{j}", bi, f"{E}{j+1}"))
-            r.append(("addc", f"{O}{n-1}", f"{O}{n-1}", 0, None))
-            rows.append(r)
+                if cand(i, j) is None:
+                    continue  # skipped column below the first product: nothing to add, no carry can reach it
+                r.append(("mad.lo.cc" if not r else "madc.lo.cc", f"{E}{j}", cand(i, j), bi, f"{E}{j}"))
+                r.append(("madc.hi.cc", f"{E}{j+1}", cand(i, j), bi, f"{E}{j+1}"))
+            if r:
+                r.append(("addc", f"{O}{n-1}", f"{O}{n-1}", 0, None))
+                rows.append(r)
         rows.append([("mul.lo", "m", f"{E}0", "inv", None)])
         # S3: O += p_odd*m (no carry out)
         r = []
@@ -127,6 +145,31 @@ def simulate(n, a, b, p):
     r = sum(env[f"r{k}"] << (32 * k) for k in range(n))
     return r
 
+def sqr_rows_for(n):
+    """Rows of a dedicated Montgomery SQUARING r = a*a/2^(32n) mod p (result < 2p) in the SAME row structure as the product (fixed even/odd
+    accumulator pairs, so ptxas needs no register re-pairing):  a^2 = sum_i a_i 2^(32i) * (a_i 2^(32i) + 2 U_i 2^(32(i+1))),  U_i = a >> 32(i+1).
+    Row i multiplies a_i with the vector [ -, .., -, a_i, e_(i+1), d_(i+2), .., d_(n-1) ]: columns j < i are SKIPPED (their products were
+    counted, doubled, in earlier rows), e_j = a_j << 1 and d_j = (a_j << 1) | (a_(j-1) >> 31) are the limbs of the doubled upper part
+    (needs 3p < 2^(32n): the doubled multiplicand makes the running sum reach 3p; true for the two 12-limb base fields, NOT for Fr).  A skipped product keeps its place in the carry chain as
+    a plain add.  n(n+1)/2 + n^2 wide multiplies instead of 2 n^2: 222 instead of 288 for n = 12."""
+    pre = []
+    for j in range(1, n):
+        pre.append(("shl1", f"e{j}", f"a{j}", None, None))
+        pre.append(("shf1", f"d{j}", f"a{j-1}", f"a{j}", None))
+    return [pre] + rows_for(n, square=True)
+
+def simulate_sqr(n, a, p):
+    inv = (-pow(p, -1, 1 << 32)) & MASK
+    env = {"inv": inv, "zero": 0}
+    for k in range(n):
+        env[f"a{k}"] = (a >> (32 * k)) & MASK
+        env[f"p{k}"] = (p >> (32 * k)) & MASK
+    sim = Sim()
+    for row in sqr_rows_for(n):
+        sim.run(row, env)
+    assert env.get("_ovf", 0) == 0, "unexpected overflow on a non-.cc op"
+    return sum(env[f"r{k}"] << (32 * k) for k in range(n))
+
 def selftest():
     P377 = 0x1ae3a4617c510eac63b05c06ca1493b1a22d9f300f5138f1ef3622fba094800170b5d44300000008508c00000000001
     R377 = 0x12ab655e9a2ca55660b44d1e5c37b00159aa76fed00000010a11800000000001
@@ -141,16 +184,29 @@ def selftest():
             r = simulate(n, a, b, p)
             assert r < 2 * p, "result not < 2p"
             assert r % p == a * b * Rinv % p, (n, hex(a), hex(b))
-    print("gen_mont_asm: model OK (n=8,12; both curves)")
+        if n != 12:
+            continue  # the dedicated squaring needs 3p < 2^(32n) (doubled multiplicand): true for the two 12-limb base fields, not for Fr
+        allones = (1 << (32 * n)) - 1
+        for a in [0, 1, p - 1, p - 2, p >> 1, allones % p, (allones >> 7) % p, sum(0xffffffff << (64 * k) for k in range(n // 2)) % p] + [x for x, _ in cases[4:]]:
+            r = simulate_sqr(n, a, p)
+            assert r < 2 * p, "square not < 2p"
+            assert r % p == a * a * Rinv % p, (n, hex(a))
+    print("gen_mont_asm: model OK (n=8,12; both curves; products and dedicated squarings)")
 
-def emit(n, name):
+def emit(n, name, square=False):
     """Emit a __device__ function whose body is one asm statement per row."""
     out = []
     out.append(f"// GENERATED by tools/gen_mont_asm.py -- do not edit. n={n} 32-bit limbs.")
-    out.append(f"// r = a*b/2^{32*n} mod p, result in [0, 2p); caller does the final conditional subtract.")
-    out.append(f"__device__ __forceinline__ void {name}(uint32_t* __restrict__ r, const uint32_t* __restrict__ a,")
-    out.append(f"        const uint32_t* __restrict__ b, const uint32_t* __restrict__ p, uint32_t inv, uint32_t zero) {{")
-    out.append(f"    uint32_t X[{n}], Y[{n}], m;")
+    if square:
+        out.append(f"// Dedicated squaring (sqr_rows_for): r = a*a/2^{32*n} mod p, result in [0, 2p); {n*(n+1)//2 + n*n} wide multiplies instead of {2*n*n}.")
+        out.append(f"__device__ __forceinline__ void {name}(uint32_t* __restrict__ r, const uint32_t* __restrict__ a,")
+        out.append(f"        const uint32_t* __restrict__ p, uint32_t inv, uint32_t zero) {{")
+        out.append(f"    uint32_t X[{n}], Y[{n}], e[{n}], d[{n}], m;")
+    else:
+        out.append(f"// r = a*b/2^{32*n} mod p, result in [0, 2p); caller does the final conditional subtract.")
+        out.append(f"__device__ __forceinline__ void {name}(uint32_t* __restrict__ r, const uint32_t* __restrict__ a,")
+        out.append(f"        const uint32_t* __restrict__ b, const uint32_t* __restrict__ p, uint32_t inv, uint32_t zero) {{")
+        out.append(f"    uint32_t X[{n}], Y[{n}], m;")
     def ref(t, ops, kinds):
         # map symbol -> %k placeholder, registering operand
         if not isinstance(t, str):
@@ -158,7 +214,7 @@ def emit(n, name):
         if t not in ops:
             ops[t] = len(ops)
         return None
-    all_rows = rows_for(n)
+    all_rows = sqr_rows_for(n) if square else rows_for(n)
     for row in all_rows[:-1]:
         # collect symbols: written ones first
         written, read = [], []
@@ -178,7 +234,7 @@ def emit(n, name):
             if t == "inv": return "inv"
             if t == "zero": return "zero"
             arr, idx = t[0], int(t[1:])
-            return {"X": "X", "Y": "Y", "a": "a", "b": "b", "p": "p", "r": "r"}[arr] + f"[{idx}]"
+            return {"X": "X", "Y": "Y", "a": "a", "b": "b", "p": "p", "r": "r", "e": "e", "d": "d"}[arr] + f"[{idx}]"
         # first-use analysis for written symbols
         first_is_write = {}
         for op, d, x, y, z in row:
@@ -200,6 +256,10 @@ def emit(n, name):
         for op, d, x, y, z in row:
             if op == "taint":
                 lines.append(f"lop3.b32 {o(d)}, {o(d)}, {o(x)}, {o(y)}, 0xF8;")
+            elif op == "shl1":
+                lines.append(f"shl.b32 {o(d)}, {o(x)}, 1;")
+            elif op == "shf1":
+                lines.append(f"shf.l.wrap.b32 {o(d)}, {o(x)}, {o(y)}, 1;")
             elif op in ("mul.lo", "mul.hi"):
                 lines.append(f"{op}.u32 {o(d)}, {o(x)}, {o(y)};")
             elif op.startswith("mad"):
@@ -226,5 +286,6 @@ if __name__ == "__main__":
         with open(sys.argv[1], "w") as f:
             f.write("// clang-format off\n")
             f.write(emit(8, "mont_mul_raw_8") + "\n\n")
-            f.write(emit(12, "mont_mul_raw_12") + "\n")
+            f.write(emit(12, "mont_mul_raw_12") + "\n\n")
+            f.write(emit(12, "mont_sqr_raw_12", square=True) + "\n")
         print("wrote", sys.argv[1])
