@@ -31,7 +31,7 @@ static thread_local std::string g_host_err;
         g_host_err = "null context";    \
         return ZK_ERR_ARG;              \
     }                                   \
-    (void)0
+    zk::DevBuf::pool() = (ctx)->pool
 #define CURVE_DISPATCH(ctx, curve_id, expr377, expr381)                    \
     ((curve_id) == 377 ? (expr377) : (curve_id) == 381 ? (expr381) : fail((ctx), ZK_ERR_ARG, "unknown curve_id (use 377 or 381)"))
 
@@ -106,12 +106,16 @@ static int run_on_all(zkaes_ctx* ctx, const std::function<int(zkaes_ctx*, int)>&
         ZkWorker* w = ctx->workers[i].get();
         zkaes_ctx* pc = ctx->peers[i];
         std::lock_guard<std::mutex> g(w->m);
-        w->job = [&fn, pc, i] { return fn(pc, (int)i + 1); };
+        w->job = [&fn, pc, i] {
+            zk::DevBuf::pool() = pc->pool;
+            return fn(pc, (int)i + 1);
+        };
         w->has_job = true;
         w->done = false;
         w->cv.notify_all();
     }
     int rc;
+    zk::DevBuf::pool() = ctx->pool;
     try {
         rc = fn(ctx, 0);
     } catch (const std::exception& e) {
@@ -151,11 +155,22 @@ int zkaes_ctx_create(int device_id, zkaes_ctx** out) {
         const int v = atoi(e);
         if (v >= 3 && v <= 24) c->msm_window_max = v;
     }
-    // keep freed stream-ordered scratch cached in the pool instead of returning it to the driver every call
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // a private stream-ordered pool that keeps freed scratch cached instead of returning it to the driver every call (falls back to the
+    // device's default pool, untouched, if the driver refuses to create one)
+    {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device_id;
+        if (cudaMemPoolCreate(&c->pool, &props) == cudaSuccess) {
+            c->pool_owned = true;
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        } else {
+            cudaGetLastError();
+            c->pool = nullptr;
+        }
     }
     *out = c;
     return ZK_OK;
@@ -248,6 +263,7 @@ void zkaes_ctx_destroy(zkaes_ctx* ctx) {
     zk::comm_destroy(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->pool_owned) cudaMemPoolDestroy(ctx->pool);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -89,6 +89,10 @@ struct ZkWorker {
 struct zkaes_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // the context's OWN stream-ordered memory pool: every DevBuf of this context comes from it (release threshold, trimming and the
+    // high-water mark that sizes the scratch arena then concern this context only, not other cudaMallocAsync users of the process)
+    cudaMemPool_t pool = nullptr;
+    bool pool_owned = false;
     std::string err;
     uint64_t launches = 0;  // kernels launched by this library on this context (bench.py's gpu_launches)
     // cached device tables keyed by (curve, kind, log size)
@@ -155,8 +159,13 @@ struct DevBuf {
     // host time spent inside the stream-ordered allocator (ZKAES_TRACE prints it per phase: the pool remaps physical memory
     // when a large request does not fit a cached block, which is host-synchronous work)
     static double& alloc_seconds() {
-        static double t = 0;
+        static thread_local double t = 0;
         return t;
+    }
+    // the pool of the context that is working on THIS host thread (set at every C-ABI entry point); null = the device's default pool
+    static cudaMemPool_t& pool() {
+        static thread_local cudaMemPool_t p = nullptr;
+        return p;
     }
     // the arena of the context that is proving on THIS host thread (one context per thread); null = stream-ordered pool only
     static DevArena*& arena() {
@@ -172,7 +181,7 @@ struct DevBuf {
             if ((p = a->alloc(n)) != nullptr) return cudaSuccess;
         }
         auto t0 = std::chrono::steady_clock::now();
-        cudaError_t e = cudaMallocAsync(&p, n, stream);
+        cudaError_t e = pool() ? cudaMallocFromPoolAsync(&p, n, pool(), stream) : cudaMallocAsync(&p, n, stream);
         alloc_seconds() += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return e;
     }

@@ -209,8 +209,8 @@ struct PhaseTrace {
         uint64_t used_high = 0, reserved = 0, zero = 0;
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaMemPool_t pool = DevBuf::pool();  // the working context's pool (set at the ABI entry)
+        if (pool || cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used_high);
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
@@ -232,7 +232,8 @@ struct ScratchScope {
     bool measuring = false;
     explicit ScratchScope(zkaes_ctx* c) : ctx(c) {
         static const bool enabled = !(getenv("ZKAES_ARENA") && getenv("ZKAES_ARENA")[0] == '0');
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) pool = nullptr;
+        pool = ctx->pool;
+        if (!pool && cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) pool = nullptr;
         if (enabled && ctx->arena_state == 0 && ctx->scratch_peak && pool) {
             cudaStreamSynchronize(ctx->stream);
             cudaMemPoolTrimTo(pool, 0);
@@ -830,14 +831,17 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));
     ZK_TRY(po_z_poly(ctx, zpoly.as<Fr>(), w_poly.as<Fr>(), len_w, x_poly.as<Fr>(), x));
     tr.mark("r2: r_alpha, t, z polys");
-    // rhs = r_alpha (eta_a z_a + eta_b z_b + eta_c z_a z_b) - t z has degree <= 3|H| + 1: the reference multiplies on the 4|H|
-    // domain (five forward NTTs of 4|H| live at once: 43 GB at 4 KiB, the prover's memory peak).  Here the 4|H| domain is walked
-    // as its four cosets s_j H, s_j = w_4H^j: every buffer is |H|-sized, each coset yields rhs mod (X^|H| - i^j), and a 4-point
-    // transform across the cosets returns the four coefficient blocks.  Same polynomial, 19 GB instead of 43 GB.
-    const size_t n4 = 4 * h;
+    // rhs = r_alpha (eta_a z_a + eta_b z_b + eta_c z_a z_b) - t z: deg r_alpha = |H| - 1, deg z_a = deg z_b = |H| (one blinding coefficient),
+    // deg t < |H|, deg z = |H|, so deg rhs = 3|H| - 1 -- 3|H| coefficients, like the mask.  The reference multiplies on the 4|H| domain
+    // (five forward NTTs of 4|H| live at once: 43 GB at 4 KiB).  Here q_1 = mask + rhs is evaluated on THREE cosets s_j H of size |H|,
+    // s_j = w_4H^j (s_j^|H| = 1, i, -1): every buffer is |H|-sized, each coset yields rhs mod (X^|H| - s_j^|H|) = c_0 + s_j^|H| c_1 + s_j^2|H| c_2,
+    // and a 3 x 3 Vandermonde solve per index returns the three coefficient blocks (po_coset3_combine, as for h_2 in round 3).
+    // [round 1 walked all four cosets of the 4|H| domain: 24 transforms of |H| instead of 18.]
+    const size_t n3 = 3 * h;
     const int log4h = pk.log_h + 2;
+    constexpr int NCOSET2 = 3;
     DevBuf e_ra, k_ra, k_za, k_zb, k_t, k_z;
-    ZK_CUDA(ctx, e_ra.alloc(sizeof(Fr) * n4, st));
+    ZK_CUDA(ctx, e_ra.alloc(sizeof(Fr) * n3, st));
     for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) ZK_CUDA(ctx, bfr->alloc(sizeof(Fr) * h, st));
     {
         const Fr w4h = domain_gen(log4h);
@@ -851,16 +855,16 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             ZK_TRY(po_scale_powers(ctx, dst, dst, s, h));
             return ntt(ctx, dst, pk.log_h, false, false);
         };
-        // s_j and s_j^|H| of the four cosets
-        Fr s4[4], s4h[4];
+        // s_j and s_j^|H| of the cosets
+        Fr s4[NCOSET2], s4h[NCOSET2];
         s4[0] = Fr::one();
         s4h[0] = Fr::one();
-        for (int j = 1; j < 4; ++j) {
+        for (int j = 1; j < NCOSET2; ++j) {
             s4[j] = s4[j - 1] * w4h;
             s4h[j] = s4h[j - 1] * i4;
         }
         if (ctx->nranks == 1) {
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NCOSET2; ++j) {
                 Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
                 ZK_TRY(to_coset_h(k_ra.as<Fr>(), ra.as<Fr>(), h, s4[j], s4h[j]));
                 ZK_TRY(to_coset_h(k_za.as<Fr>(), za.as<Fr>(), h + 1, s4[j], s4h[j]));
@@ -878,28 +882,28 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
             const Fr* src[5] = {ra.as<Fr>(), za.as<Fr>(), zb.as<Fr>(), tpoly.as<Fr>(), zpoly.as<Fr>()};
             const size_t len[5] = {h, h + 1, h + 1, h, h + 1};
             ZK_TRY(run_coset_waves(
-                ctx, 4, 5, 1.5, h, [&](Fr* dst, int j, int p) -> int { return to_coset_h(dst, src[p], len[p], s4[j], s4h[j]); },
+                ctx, NCOSET2, 5, 1.5, h, [&](Fr* dst, int j, int p) -> int { return to_coset_h(dst, src[p], len[p], s4[j], s4h[j]); },
                 [&](int j, const std::vector<Fr*>& T) -> int {
                     Fr* Rj = e_ra.as<Fr>() + (size_t)j * h;
                     ZK_TRY(po_round2(ctx, Rj, T[0], T[1], T[2], T[3], T[4], eta, h));
                     ZK_TRY(ntt(ctx, Rj, pk.log_h, true, false));
                     return po_scale_powers(ctx, Rj, Rj, s4[j].inverse(), h);
                 }));
-            for (int j = 0; j < 4; ++j) ZK_TRY(comm_broadcast(ctx, e_ra.as<Fr>() + (size_t)j * h, sizeof(Fr) * h, j % ctx->nranks));
+            for (int j = 0; j < NCOSET2; ++j) ZK_TRY(comm_broadcast(ctx, e_ra.as<Fr>() + (size_t)j * h, sizeof(Fr) * h, j % ctx->nranks));
         }
-        ZK_TRY(po_coset4_combine(ctx, e_ra.as<Fr>(), h, i4.inverse()));  // rhs coefficients (degree <= 3|H| + 1)
+        ZK_TRY(po_coset3_combine(ctx, e_ra.as<Fr>(), h, s4h));  // rhs coefficients (degree 3|H| - 1)
     }
     for (DevBuf* bfr : {&k_ra, &k_za, &k_zb, &k_t, &k_z}) bfr->release();
     ra.release();
     zpoly.release();
     ZK_TRY(po_vec(ctx, 0, e_ra.as<Fr>(), e_ra.as<Fr>(), mask.as<Fr>(), len_mask));  // q_1 = mask + rhs
     DevBuf h1, xg1;
-    ZK_CUDA(ctx, h1.alloc(sizeof(Fr) * (n4 - h), st));
+    ZK_CUDA(ctx, h1.alloc(sizeof(Fr) * (n3 - h), st));
     ZK_CUDA(ctx, xg1.alloc(sizeof(Fr) * h, st));
-    ZK_TRY(po_divide_vanishing(ctx, e_ra.as<Fr>(), n4, h, h1.as<Fr>(), xg1.as<Fr>()));
+    ZK_TRY(po_divide_vanishing(ctx, e_ra.as<Fr>(), n3, h, h1.as<Fr>(), xg1.as<Fr>()));
     e_ra.release();
     const Fr* g1 = xg1.as<Fr>() + 1;  // q_1 = h_1 v_H + X g_1
-    const size_t len_g1 = h - 1, len_h1 = 2 * h + 1;
+    const size_t len_g1 = h - 1, len_h1 = 2 * h;  // deg h_1 = deg q_1 - |H| = 2|H| - 1 (ark-marlin commits 2|H| + 1 coefficients: the top one is zero)
     tr.mark("r2: products + division");
     Committed c_t, c_g1, c_h1;
     ZK_TRY(pc_commit(ctx, pk, tpoly.as<Fr>(), h, -1, false, zk, &c_t));
