@@ -53,6 +53,7 @@ def _load():
         "zkaes_dev_download": (c_int, [vp, vp, vp, c_size_t]),
         "zkaes_msm_g1": (c_int, [vp, c_int, vp, vp, c_size_t, vp]),
         "zkaes_msm_g1_device": (c_int, [vp, c_int, vp, vp, c_size_t, c_int, vp]),
+        "zkaes_msm_g1_small": (c_int, [vp, c_int, vp, vp, c_size_t, c_int, vp]),
         "zkaes_msm_g1_prepare_bases": (c_int, [vp, c_int, vp, c_size_t]),
         "zkaes_msm_g1_windows_bytes": (c_size_t, [vp, c_int, c_size_t]),
         "zkaes_msm_g1_windows": (c_int, [vp, c_int, vp, vp, c_size_t, c_size_t, c_int, vp]),
@@ -234,6 +235,14 @@ class Context:
         self._check(lib().zkaes_msm_g1(self._h, curve, _ptr(bases), _ptr(scalars), n, _ptr(out)))
         return out
 
+    def msm_g1_small(self, curve: int, bases: np.ndarray, values: np.ndarray, value_bits: int) -> np.ndarray:
+        """sum values[i] * bases[i] for int32 values with |v| <= 2^(value_bits - 1): the single-pass path of the Lagrange-basis commitments"""
+        n = values.shape[0]
+        assert bases.shape == (n, 12) and values.dtype == np.int32
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(lib().zkaes_msm_g1_small(self._h, curve, _ptr(bases), _ptr(values), n, value_bits, _ptr(out)))
+        return out
+
     def msm_g1_device(self, curve: int, bases_dev, scalars_dev, n: int, scalars_montgomery: bool = False, bases_prepared: bool = False) -> np.ndarray:
         out = np.zeros(12, dtype=np.uint64)
         flags = int(scalars_montgomery) | (2 if bases_prepared else 0)
@@ -338,7 +347,8 @@ class Circuit:
             pass
 
 
-PK_INFO_FIELDS = ("msg_len", "num_constraints", "num_variables", "nnz_a", "nnz_b", "nnz_c", "h", "k", "x", "max_degree", "num_instance_used")
+PK_INFO_FIELDS = ("msg_len", "num_constraints", "num_variables", "nnz_a", "nnz_b", "nnz_c", "h", "k", "x", "max_degree", "num_instance_used",
+                  "lagrange_points")
 
 
 def _ok(rc, what):

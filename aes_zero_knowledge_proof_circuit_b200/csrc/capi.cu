@@ -70,6 +70,26 @@ static int msm_host_impl(zkaes_ctx* ctx, const void* bases, const void* scalars,
     return msm_device_impl<C>(ctx, db.p, ds.p, n, 0, out96);
 }
 
+// small signed scalars (host buffers): the Lagrange-basis commitments' kernel path (msm.cu, "small-scalar MSM") on its own
+static constexpr int MSM_SMALL_WINDOWS = 32;
+template <class C>
+static int msm_small_host_impl(zkaes_ctx* ctx, const void* bases, const int32_t* vals, size_t n, int c, void* out96) {
+    DevBuf db, dv, win;
+    cudaStream_t st = ctx->stream;
+    ZK_CUDA(ctx, db.alloc(96 * n, st));
+    ZK_CUDA(ctx, dv.alloc(4 * n, st));
+    ZK_CUDA(ctx, win.alloc(sizeof(XYZZ<C>) * MSM_SMALL_WINDOWS, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(db.p, bases, 96 * n, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(ctx, cudaMemcpyAsync(dv.p, vals, 4 * n, cudaMemcpyHostToDevice, st));
+    ZK_TRY(msm_small_window_sums<C>(ctx, db.p, dv.as<int32_t>(), n, 0, 1, c, MSM_SMALL_WINDOWS, win.p));
+    std::vector<XYZZ<C>> h(MSM_SMALL_WINDOWS);
+    ZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win.p, sizeof(XYZZ<C>) * MSM_SMALL_WINDOWS, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    Affine<C> r = msm_sum_windows_host<C>(h.data(), h.size());
+    memcpy(out96, &r, 96);
+    return ZK_OK;
+}
+
 // ---- single-process multi-GPU (zkaes_ctx_create_multi) ------------------------------------------------------------------------
 // The opaque key handle: the leader's key plus, for a multi-GPU context, one key per peer rank (each holds its rank's SRS share).
 struct zkaes_pk {
@@ -347,6 +367,9 @@ int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value) {
     } else if (k == "msm_prefetch") {
         if (value < 0 || value > 2) return fail(ctx, ZK_ERR_ARG, "msm_prefetch must be 0, 1 or 2");
         ctx->msm_prefetch = value;
+    } else if (k == "r1_lagrange") {
+        if (value != 0 && value != 1) return fail(ctx, ZK_ERR_ARG, "r1_lagrange must be 0 or 1");
+        ctx->r1_lagrange = value;
     } else if (k == "msm_madd_call") {
         if (value != 0 && value != 1) return fail(ctx, ZK_ERR_ARG, "msm_madd_call must be 0 or 1");
         ctx->msm_madd_call = value;
@@ -406,6 +429,17 @@ int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases, const v
     if (n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "msm: n must be < 2^31");
     return CURVE_DISPATCH(ctx, curve_id, msm_device_impl<G1_377Params>(ctx, bases, scalars, n, mont, out96),
                           msm_device_impl<G1_381Params>(ctx, bases, scalars, n, mont, out96));
+}
+int zkaes_msm_g1_small(zkaes_ctx* ctx, int curve_id, const void* bases, const int32_t* values, size_t n, int value_bits, void* out96) {
+    NEED_CTX(ctx);
+    if ((n && (!bases || !values)) || !out96) return fail(ctx, ZK_ERR_ARG, "small msm: null pointer");
+    if (n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "small msm: n must be < 2^31");
+    if (value_bits < 1 || value_bits > 13) return fail(ctx, ZK_ERR_ARG, "small msm: value_bits must be 1..13");
+    const int64_t lim = (int64_t)1 << (value_bits - 1);
+    for (size_t i = 0; i < n; ++i)
+        if (values[i] > lim || values[i] < -lim) return fail(ctx, ZK_ERR_ARG, "small msm: |value| exceeds 2^(value_bits - 1)");
+    return CURVE_DISPATCH(ctx, curve_id, msm_small_host_impl<G1_377Params>(ctx, bases, values, n, value_bits, out96),
+                          msm_small_host_impl<G1_381Params>(ctx, bases, values, n, value_bits, out96));
 }
 int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, size_t n) {
     NEED_CTX(ctx);

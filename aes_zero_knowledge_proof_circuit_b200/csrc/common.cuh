@@ -105,6 +105,7 @@ struct zkaes_ctx {
     int msm_plan_ranks = 1;  // stand-alone sharded MSM entry points (zkaes_msm_g1_windows / _fold): ranks sharing the MSM, so the window plan fits the per-rank share
     int msm_prefetch = 0;    // 1 / 2: stage the next entry's point in shared memory (cp.async / cp.async.bulk + mbarrier) while the current one is added
     int msm_madd_call = 1;   // 1: the mixed addition issues its ten products through one out-of-line multiplier (XYZZ::madd_call)
+    int r1_lagrange = 1;     // 1: encrypt() commits to w, z_A, z_B in the Lagrange basis when the key holds those points (prover.cu, pk_build_lagrange)
     int msm_window_max = 23;  // cap of the automatic window choice: bounds the bucket array (2^(c-1) W points of 192 B: 8.9 GB at c = 23, W = 11)
     // multi-GPU: this context's rank among the contexts that share one sharded MSM (comm.cu) -- one process per GPU
     // (zkaes_ctx_comm_init), or one process driving all GPUs (zkaes_ctx_create_multi: the leader, rank 0, owns the peers)

@@ -513,6 +513,109 @@ int msm_window_sums(zkaes_ctx* ctx, const void* d_bases, const void* d_scalars, 
     return ZK_OK;
 }
 
+// ---- small-scalar MSM: sum_j v_j * bases[j] for signed integers |v_j| <= 2^(c-1), c <= 13 -------------------------------------------------
+// The prover's Lagrange-basis commitments (prover.cu, round 1): the evaluations of w, z_A, z_B over H are bits or sums of a few bits,
+// so one c-bit digit per term is the whole scalar -- n_nonzero mixed additions instead of W * n.  The same sort / slice accumulation /
+// merge / reduce kernels run on a plan of S PSEUDO-WINDOWS: window s takes the terms [s m, (s + 1) m), m = ceil(n / S), with its own
+// 2^(c-1) buckets (so the few distinct values do not put all terms into one bucket run), and the result is the PLAIN sum of the S window
+// sums (no doublings between them: msm_sum_windows_host).  vals[start + j * stride] is term j's value (cyclic sharding reads every N-th).
+__global__ void __launch_bounds__(256) k_msm_digits_small(const int32_t* __restrict__ vals, size_t n, size_t start, size_t stride, size_t padded,
+                                                          uint32_t* __restrict__ digits) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= padded) return;
+    uint32_t e = MSM_DIGIT_NONE;
+    if (j < n) {
+        const int32_t v = vals[start + j * stride];
+        if (v > 0) e = (uint32_t)(v - 1);
+        if (v < 0) e = (uint32_t)(-v - 1) | 0x80000000u;
+    }
+    digits[j] = e;
+}
+
+template <class C>
+int msm_small_window_sums(zkaes_ctx* ctx, const void* d_bases, const int32_t* d_vals, size_t n, size_t val_start, size_t val_stride, int c, int S,
+                          void* d_window_sums) {
+    cudaStream_t st = ctx->stream;
+    if (c < 1 || ((uint32_t)1 << (c - 1)) > DIG_SMALL_KEYS) return fail(ctx, ZK_ERR_ARG, "small msm: digit width out of range");
+    if (S < 1 || n >= ((size_t)1 << 31)) return fail(ctx, ZK_ERR_ARG, "small msm: bad sizes");
+    if (n == 0) {
+        ZK_CUDA(ctx, cudaMemsetAsync(d_window_sums, 0, sizeof(XYZZ<C>) * S, st));
+        return ZK_OK;
+    }
+    MsmPlan p;
+    p.c = c;
+    p.W = S;
+    p.nbw = (uint32_t)1 << (c - 1);
+    p.nb = p.nbw * (uint32_t)S;
+    const size_t m = (n + (size_t)S - 1) / (size_t)S, padded = m * (size_t)S;
+    const uint32_t L = msm_slice_len(padded);
+    const size_t slices = (padded + L - 1) / L;
+    DevBuf counts, offsets, sorted, buckets, partials, head, tail, tail_bucket, digits;
+    ZK_CUDA(ctx, buckets.alloc(sizeof(XYZZ<C>) * (size_t)p.nb, st));
+    ZK_CUDA(ctx, cudaMemsetAsync(buckets.p, 0, sizeof(XYZZ<C>) * (size_t)p.nb, st));
+    ZK_CUDA(ctx, counts.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+    ZK_CUDA(ctx, offsets.alloc(sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+    ZK_CUDA(ctx, sorted.alloc(sizeof(uint32_t) * padded, st));
+    ZK_CUDA(ctx, digits.alloc(sizeof(uint32_t) * padded, st));
+    ZK_CUDA(ctx, head.alloc(sizeof(XYZZ<C>) * slices, st));
+    ZK_CUDA(ctx, tail.alloc(sizeof(XYZZ<C>) * slices, st));
+    ZK_CUDA(ctx, tail_bucket.alloc(sizeof(uint32_t) * slices, st));
+    k_msm_digits_small<<<cdiv(padded, 256), 256, 0, st>>>(d_vals, n, val_start, val_stride, padded, digits.as<uint32_t>());
+    ctx->launches++;
+    // few keys per window: the shared-memory histogram passes (k_msm_sort_pass_small), one launch per pseudo-window; entry = the term's index
+    auto sort_pass = [&](const uint32_t* offs, uint32_t* out) {
+        for (int s = 0; s < S; ++s) {
+            const size_t off = (size_t)s * p.nbw;
+            k_msm_sort_pass_small<<<cdiv(m, 256 * DIG_TILE_ITERS), 256, 0, st>>>(digits.as<uint32_t>() + (size_t)s * m, m, (uint32_t)((size_t)s * m), p.nbw,
+                                                                                 counts.as<uint32_t>() + off, offs ? offs + off : nullptr, out);
+        }
+        ctx->launches += S;
+    };
+    ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * ((size_t)p.nb + 1), st));
+    sort_pass(nullptr, nullptr);
+    ZK_TRY(exclusive_scan_u32(ctx, counts.as<uint32_t>(), offsets.as<uint32_t>(), p.nb + 1));
+    ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
+    sort_pass(offsets.as<uint32_t>(), sorted.as<uint32_t>());
+    const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
+    zkaes_ctx::ProfSpan span{};
+    if (ctx->prof) {
+        cudaEventCreate(&span.e0);
+        cudaEventCreate(&span.e1);
+        cudaEventRecord(span.e0, st);
+    }
+    msm_launch_accumulate<C>(ctx, slices, bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                             tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+    if (ctx->prof) {
+        cudaEventRecord(span.e1, st);
+        span.terms = n;
+        span.madds = (uint64_t)n;  // upper bound: zero values produce no entry
+        ctx->prof_spans.push_back(span);
+    }
+    k_msm_merge<C><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                                                       tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+    k_msm_merge_heavy<C><<<cdiv(slices, 4), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
+                                                           tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
+    const uint32_t bs = p.nbw < RED_BS ? p.nbw : RED_BS;  // one bucket per thread
+    const uint32_t bpw = p.nbw / bs;
+    ZK_CUDA(ctx, partials.alloc(sizeof(XYZZ<C>) * (size_t)bpw * S, st));
+    k_msm_reduce<C><<<dim3(bpw, S), bs, 0, st>>>(buckets.as<XYZZ<C>>(), p.nbw, 1, partials.as<XYZZ<C>>());
+    k_msm_window_final<C><<<S, 32, 0, st>>>(partials.as<XYZZ<C>>(), bpw, reinterpret_cast<XYZZ<C>*>(d_window_sums));
+    ctx->launches += 4;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+template int msm_small_window_sums<G1_377Params>(zkaes_ctx*, const void*, const int32_t*, size_t, size_t, size_t, int, int, void*);
+template int msm_small_window_sums<G1_381Params>(zkaes_ctx*, const void*, const int32_t*, size_t, size_t, size_t, int, int, void*);
+
+template <class C>
+Affine<C> msm_sum_windows_host(const XYZZ<C>* sums, size_t count) {
+    XYZZ<C> total = XYZZ<C>::inf();
+    for (size_t i = 0; i < count; ++i) total.add(sums[i]);
+    return total.to_affine();
+}
+template Affine<G1_377Params> msm_sum_windows_host<G1_377Params>(const XYZZ<G1_377Params>*, size_t);
+template Affine<G1_381Params> msm_sum_windows_host<G1_381Params>(const XYZZ<G1_381Params>*, size_t);
+
 // Horner fold of window sums (host): total = sum_w 2^(c*w) * S_w, then to affine.
 template <class C>
 Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& p) {

@@ -19,6 +19,14 @@ int msm_bases_to_internal(zkaes_ctx* ctx, const void* src, void* dst, size_t n);
 template <class C>
 Affine<C> msm_fold_windows_host(const XYZZ<C>* sums, int n_sets, const MsmPlan& p);
 
+// Small-scalar MSM (signed integers |v| <= 2^(c-1), c <= 13): S pseudo-window sums (XYZZ, device) whose PLAIN sum is
+// sum_j vals[val_start + j * val_stride] * bases[j], j < n  (msm.cu, "small-scalar MSM")
+template <class C>
+int msm_small_window_sums(zkaes_ctx* ctx, const void* d_bases, const int32_t* d_vals, size_t n, size_t val_start, size_t val_stride, int c, int S,
+                          void* d_window_sums);
+template <class C>
+Affine<C> msm_sum_windows_host(const XYZZ<C>* sums, size_t count);
+
 // out[i] = sum_{j < i} in[j]  (n <= 2^30)
 int exclusive_scan_u32(zkaes_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n);
 

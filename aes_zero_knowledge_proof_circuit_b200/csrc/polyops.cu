@@ -134,6 +134,34 @@ __global__ void k_spmv_bits(F* out, const uint32_t* __restrict__ row_ptr, const 
         for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e) s += (int)coeff[e] * (int)z[col[e]];
     st_fr(out + r, small_to_fr(s));
 }
+// the same row sums as plain integers (the Lagrange-basis commitment of z_A / z_B takes them as one signed digit each)
+__global__ void k_spmv_bits_i32(int32_t* out, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const int8_t* __restrict__ coeff,
+                                const uint8_t* __restrict__ z, size_t nrows, size_t n_out) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_out) return;
+    int s = 0;
+    if (r < nrows)
+        for (uint32_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e) s += (int)coeff[e] * (int)z[col[e]];
+    out[r] = s;
+}
+// the full assignment in H order: position j * ratio holds instance variable j, the positions in between the witness (zero padded)
+__global__ void k_assignment_h_i32(int32_t* out, const uint8_t* __restrict__ z, size_t h, size_t ratio, size_t num_instance, size_t num_witness) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= h) return;
+    int v;
+    if (k % ratio == 0) {
+        const size_t j = k / ratio;
+        v = j < num_instance ? (int)z[j] : 0;
+    } else {
+        const size_t wi = k - k / ratio - 1;
+        v = wi < num_witness ? (int)z[num_instance + wi] : 0;
+    }
+    out[k] = v;
+}
+__global__ void k_scale_strided(F* out, const F* a, F s, size_t stride, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) st_fr(out + i * stride, ld_fr(a + i * stride) * s);
+}
 __global__ void k_w_evals(F* out, const uint8_t* __restrict__ z, const F* x_evals, size_t h, size_t ratio, size_t num_instance,
                           size_t num_witness) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +402,19 @@ int po_den_k(zkaes_ctx* ctx, F* out, const F* table, const uint32_t* ridx, const
 int po_spmv_bits(zkaes_ctx* ctx, F* out, const uint32_t* row_ptr, const uint32_t* col, const int8_t* coeff, const uint8_t* z, size_t nrows,
                  size_t n_out) {
     LAUNCH(ctx, k_spmv_bits, n_out, TB, out, row_ptr, col, coeff, z, nrows, n_out);
+    return ZK_OK;
+}
+int po_spmv_bits_i32(zkaes_ctx* ctx, int32_t* out, const uint32_t* row_ptr, const uint32_t* col, const int8_t* coeff, const uint8_t* z, size_t nrows,
+                     size_t n_out) {
+    LAUNCH(ctx, k_spmv_bits_i32, n_out, TB, out, row_ptr, col, coeff, z, nrows, n_out);
+    return ZK_OK;
+}
+int po_assignment_h_i32(zkaes_ctx* ctx, int32_t* out, const uint8_t* z, size_t h, size_t ratio, size_t num_instance, size_t num_witness) {
+    LAUNCH(ctx, k_assignment_h_i32, h, TB, out, z, h, ratio, num_instance, num_witness);
+    return ZK_OK;
+}
+int po_scale_strided(zkaes_ctx* ctx, F* out, const F* a, const F& s, size_t stride, size_t count) {
+    LAUNCH(ctx, k_scale_strided, count, TB, out, a, s, stride, count);
     return ZK_OK;
 }
 int po_w_evals(zkaes_ctx* ctx, F* out, const uint8_t* z, const F* x_evals, size_t h, size_t ratio, size_t num_instance, size_t num_witness) {

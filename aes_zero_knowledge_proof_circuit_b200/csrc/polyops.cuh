@@ -34,6 +34,13 @@ int po_den_k(zkaes_ctx* ctx, FrS* out, const FrS* table, const uint32_t* ridx, c
 // sparse rows (CSR, int8 coefficients) times the bit assignment z: out[r] = sum coeff * z[col]  for r < nrows, 0 for nrows <= r < n_out
 int po_spmv_bits(zkaes_ctx* ctx, FrS* out, const uint32_t* row_ptr, const uint32_t* col, const int8_t* coeff, const uint8_t* z, size_t nrows,
                  size_t n_out);
+// the same row sums as int32 (no field conversion): the small-scalar MSM's input
+int po_spmv_bits_i32(zkaes_ctx* ctx, int32_t* out, const uint32_t* row_ptr, const uint32_t* col, const int8_t* coeff, const uint8_t* z, size_t nrows,
+                     size_t n_out);
+// the full variable assignment laid out over H as ark-marlin orders it (instance variable j at j * ratio, witness in between, zero padded), as int32
+int po_assignment_h_i32(zkaes_ctx* ctx, int32_t* out, const uint8_t* z, size_t h, size_t ratio, size_t num_instance, size_t num_witness);
+// out[i * stride] = a[i * stride] * s, i < count
+int po_scale_strided(zkaes_ctx* ctx, FrS* out, const FrS* a, const FrS& s, size_t stride, size_t count);
 // w_evals over H (ahp/prover.rs first round): 0 on the X-subgroup positions, else w_ext[k - k/ratio - 1] - x_evals[k]
 int po_w_evals(zkaes_ctx* ctx, FrS* out, const uint8_t* z, const FrS* x_evals, size_t h, size_t ratio, size_t num_instance, size_t num_witness);
 // c[0] -= r ; c[n] += r      (c + r * (X^n - 1); c must have n + 1 entries)

@@ -298,6 +298,12 @@ struct zkaes_pk_impl {
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
     Aff* srs = nullptr;     // this rank's share of tau^i G, i <= D: the points i = rank (mod nranks), in the MSM kernels' internal form
     size_t srs_count = 0;
+    // Lagrange-basis points for the round-1 commitments (pk_build_lagrange; absent = those commitments use the powers above):
+    //   lag[j]  = L_k(tau) G,  lagw[j] = ((L_k(tau) - [k in X] l_k^X(tau)) / v_X(tau)) G   for k = rank + nranks * j < |H|
+    Aff *lag = nullptr, *lagw = nullptr;
+    size_t lag_count = 0;
+    Aff v_h, v_hx;          // v_H(tau) G and (v_H(tau) / v_X(tau)) G (host): the blinding terms r v_H of z_A, z_B and of w
+    int small_bits[2] = {0, 0};  // digit width of the row sums of A z and B z over bit assignments (|sum| <= 2^(bits-1)); 0 = too wide
     Aff gamma_g[3];         // gamma tau^i G (host)
     Aff index_comms[12];
     uint8_t tau_seed[32] = {}, gamma_seed[32] = {};  // the test SRS's trapdoor seeds (a key file can regenerate the SRS from them)
@@ -315,6 +321,8 @@ struct zkaes_pk_impl {
         cudaFree(heavy_flag);
         cudaFree(heavy_cols);
         cudaFree(srs);
+        cudaFree(lag);
+        cudaFree(lagw);
         witness_free(wit);
     }
 };
@@ -369,6 +377,30 @@ struct Committed {
     Comm comm;
     Blind rand, shifted_rand;
 };
+// Lagrange-basis commitment (pk_build_lagrange): sum_k vals[k] * basis_k + r * v_point, vals = |H| small signed integers on the device
+// (|v| <= 2^(bits-1)), this rank holding the basis points k = rank (mod nranks); then marlin_pc's hiding terms as in kzg_commit.
+constexpr int SMALL_WINDOWS = 32;
+int lagrange_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Aff* basis, const int32_t* vals, int bits, const Fr& r_mask, const Aff& v_point,
+                    ChaCha20Rng& zk, Committed* out) {
+    const size_t N = (size_t)ctx->nranks;
+    cudaStream_t st = ctx->stream;
+    DevBuf win, all;
+    const size_t wbytes = sizeof(XY) * SMALL_WINDOWS;
+    ZK_CUDA(ctx, win.alloc(wbytes, st));
+    ZK_CUDA(ctx, all.alloc(wbytes * N, st));
+    ZK_TRY(msm_small_window_sums<C>(ctx, basis, vals, pk.lag_count, (size_t)ctx->rank, N, bits, SMALL_WINDOWS, win.p));
+    ZK_TRY(comm_all_gather(ctx, win.p, all.p, wbytes));
+    std::vector<XY> hsum((size_t)SMALL_WINDOWS * N);
+    ZK_CUDA(ctx, cudaMemcpyAsync(hsum.data(), all.p, wbytes * N, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    Aff cm = g1_add(msm_sum_windows_host<C>(hsum.data(), hsum.size()), g1_mul(v_point, r_mask));
+    out->rand.c.clear();
+    for (int i = 0; i < 3; ++i) out->rand.c.push_back(fr_rand(zk));
+    for (int i = 0; i < 3; ++i) cm = g1_add(cm, g1_mul(pk.gamma_g[i], out->rand.c[i]));
+    out->comm.comm = cm;
+    out->comm.has_shifted = false;
+    return ZK_OK;
+}
 // marlin_pc commit of one labeled polynomial (degree bound -> extra commitment on the shifted powers)
 int pc_commit(zkaes_ctx* ctx, const zkaes_pk_impl& pk, const Fr* coeffs, size_t n, long bound, bool hiding, ChaCha20Rng& zk, Committed* out) {
     ZK_TRY(kzg_commit(ctx, pk, coeffs, n, 0, hiding, zk, &out->comm.comm, &out->rand));
@@ -396,6 +428,18 @@ int pk_build_shape(zkaes_ctx* ctx, zkaes_pk_impl& pk, size_t msg_len) {
     cudaStream_t st = ctx->stream;
     const CsrMatrix* M[3] = {&c.a, &c.b, &c.c};
     for (int m = 0; m < 3; ++m) pk.nnz[m] = M[m]->nnz();
+    for (int m = 0; m < 2; ++m) {  // every variable of this circuit is a bit: a row sum lies in [-(sum of negative coefficients), sum of positive ones]
+        long bound = 1;
+        const CsrMatrix& A = *M[m];
+        for (size_t r = 0; r + 1 < A.row_ptr.size(); ++r) {
+            long pos = 0, neg = 0;
+            for (uint32_t e = A.row_ptr[r]; e < A.row_ptr[r + 1]; ++e) (A.coeff[e] > 0 ? pos : neg) += std::abs((long)A.coeff[e]);
+            bound = std::max(bound, std::max(pos, neg));
+        }
+        int bits = 1;
+        while (((long)1 << (bits - 1)) < bound) ++bits;
+        pk.small_bits[m] = bits <= 13 ? bits : 0;
+    }
     // ark-marlin balance_matrices swaps rows while A is the denser matrix; for this circuit nnz(A) < nnz(B) so it is the identity
     if (pk.nnz[0] >= pk.nnz[1]) return fail(ctx, ZK_ERR_UNSUPPORTED, "synthesize_keys: matrix A denser than B (balance_matrices not implemented)");
     size_t nnz_max = std::max(pk.nnz[0], std::max(pk.nnz[1], pk.nnz[2]));
@@ -486,6 +530,69 @@ int pk_build_srs(zkaes_ctx* ctx, zkaes_pk_impl& pk, bool generate_points) {
     return ZK_OK;
 }
 
+// Lagrange-basis points over H for the round-1 commitments (msm_commit_small).  The evaluations of z_A, z_B over H are row sums of a few bits
+// and the numerator of w is the bit assignment itself, so in the basis {L_k(tau) G} their commitments are MSMs with one small signed digit per
+// term instead of W = 11 windows of a 253-bit coefficient: same group elements, same proof bytes.
+//   z_M^(X) = sum_k (Mz)_k L_k(X) + r v_H(X)
+//   w^(X)   = (sum_{k not in X} w_k L_k(X) - (x^(X) - sum_j x_j L_{k_j}(X)) + r v_H(X)) / v_X(X)      [x^ interpolates itself over H, k_j = j |H|/|X|]
+//           = sum_{k in H} a_k (L_k(X) - [k = k_j] l_j^X(X)) / v_X(X) + r v_H(X) / v_X(X),             a = the full assignment in H order
+// and every (L_k - [k in X] l_j^X) / v_X is a polynomial (L_k vanishes on X for k outside it; L_{k_j} - l_j^X vanishes on X), so the points
+// are commitments an SRS holder can derive (group-element inverse NTT); with the test SRS's tau in hand they are fixed-base multiples:
+//   L_k(tau) = v_H(tau)/|H| * w^k / (tau - w^k),   l_j^X(tau) = v_X(tau)/|X| * w^k / (tau - w^k)  (k = k_j).
+// 2 x 96 B per element of H (12.9 GB at 4 KiB on one GPU, sharded cyclically like the SRS): built only if that leaves room for the prover's
+// scratch (ZKAES_LAGRANGE=0 disables it).
+int pk_build_lagrange(zkaes_ctx* ctx, zkaes_pk_impl& pk) {
+    if (getenv("ZKAES_LAGRANGE") && getenv("ZKAES_LAGRANGE")[0] == '0') return ZK_OK;
+    const size_t h = pk.h, x = pk.x, N = (size_t)ctx->nranks, r = (size_t)ctx->rank;
+    cudaStream_t st = ctx->stream;
+    const Fr tau = fr_from_seed(pk.tau_seed);
+    const Fr vh = vanishing(tau, h), vx = vanishing(tau, x);
+    if (vh.is_zero() || vx.is_zero()) return ZK_OK;  // tau inside H: no Lagrange form (the powers still work)
+    const size_t count = h > r ? (h - r + N - 1) / N : 0;
+    {   // room: the two point arrays for good, three |H| vectors of scalars while building, and afterwards the prover's scratch (about 480 B per
+        // element of H at its round-3 / opening peak, measured 30.6 GB at |H| = 2^26) plus a margin
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->pool) cudaMemPoolTrimTo(ctx->pool, 0);
+        size_t mfree = 0, mtotal = 0;
+        ZK_CUDA(ctx, cudaMemGetInfo(&mfree, &mtotal));
+        const size_t keep = 2 * sizeof(Aff) * count, build = 3 * sizeof(Fr) * h, later = 560 * h / N + ((size_t)2 << 30);
+        // every rank must take the same path (the commitments' all-gathers pair up): all build, or none does
+        const uint32_t mine = mfree >= keep + std::max(build, later) ? 1u : 0u;
+        DevBuf flag, flags;
+        ZK_CUDA(ctx, flag.alloc(sizeof(uint32_t), st));
+        ZK_CUDA(ctx, flags.alloc(sizeof(uint32_t) * N, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(flag.p, &mine, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ZK_TRY(comm_all_gather(ctx, flag.p, flags.p, sizeof(uint32_t)));
+        std::vector<uint32_t> all(N);
+        ZK_CUDA(ctx, cudaMemcpyAsync(all.data(), flags.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+        ZK_CUDA(ctx, cudaStreamSynchronize(st));
+        for (uint32_t f : all)
+            if (!f) return ZK_OK;
+    }
+    ZK_CUDA(ctx, cudaMalloc((void**)&pk.lag, sizeof(Aff) * std::max<size_t>(count, 1)));
+    ZK_CUDA(ctx, cudaMalloc((void**)&pk.lagw, sizeof(Aff) * std::max<size_t>(count, 1)));
+    DevBuf d, u, sc;
+    ZK_CUDA(ctx, d.alloc(sizeof(Fr) * h, st));
+    ZK_CUDA(ctx, u.alloc(sizeof(Fr) * h, st));
+    ZK_CUDA(ctx, sc.alloc(sizeof(Fr) * h, st));
+    ZK_TRY(po_rsub_scalar(ctx, d.as<Fr>(), pk.elems_h, tau, h));       // tau - w^k
+    ZK_TRY(po_batch_inverse(ctx, u.as<Fr>(), d.as<Fr>(), h));
+    ZK_TRY(po_vec(ctx, 2, u.as<Fr>(), u.as<Fr>(), pk.elems_h, h));     // u_k = w^k / (tau - w^k)
+    const Fr hinv = Fr::from_u64(h).inverse(), xinv = Fr::from_u64(x).inverse();
+    const Fr c_l = vh * hinv;                  // L_k(tau) = c_l u_k
+    const Fr c_w = c_l * vx.inverse();         // L_k(tau) / v_X(tau)
+    ZK_TRY(po_scale(ctx, sc.as<Fr>(), u.as<Fr>(), c_l, h));
+    ZK_TRY(fb_mul_scalars_device<C>(ctx, sc.p, count, pk.lag, r, N));
+    ZK_TRY(po_scale(ctx, sc.as<Fr>(), u.as<Fr>(), c_w, h));
+    ZK_TRY(po_scale_strided(ctx, sc.as<Fr>(), u.as<Fr>(), c_w - xinv, h / x, x));  // k in X: (L_k - l_j^X) / v_X = u_k (c_w - 1/|X|)
+    ZK_TRY(fb_mul_scalars_device<C>(ctx, sc.p, count, pk.lagw, r, N));
+    pk.lag_count = count;
+    pk.v_h = g1_mul(Aff::generator(), vh);
+    pk.v_hx = g1_mul(Aff::generator(), vh * vx.inverse());
+    ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    return ZK_OK;
+}
+
 // index polynomials (ahp/indexer.rs arithmetize_matrix) and, unless they come from a key file, their 12 commitments
 int pk_build_index_polys(zkaes_ctx* ctx, zkaes_pk_impl& pk, bool compute, bool commit) {
     const size_t h = pk.h, k = pk.k;
@@ -542,6 +649,8 @@ int pk_synthesize(zkaes_ctx* ctx, size_t msg_len, const uint8_t tau_seed[32], co
     tr.mark("keys: index polys + 12 commitments");
     pk_build_vk(pk);
     tr.mark("keys: verifying key");
+    ZK_TRY(pk_build_lagrange(ctx, pk));
+    tr.mark("keys: Lagrange-basis points");
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = pkp.release();
     return ZK_OK;
@@ -649,6 +758,8 @@ int pk_load(zkaes_ctx* ctx, const char* path, zkaes_pk_impl** out) {
     if (fgetc(file.f) != EOF) return fail(ctx, ZK_ERR_ARG, "pk_load: trailing bytes in the key file");
     pk_build_vk(pk);
     if (pk.vk_full != vk_file) return fail(ctx, ZK_ERR_ARG, "pk_load: the verifying key in the file differs from the one its commitments and seeds give");
+    ZK_TRY(pk_build_lagrange(ctx, pk));
+    tr.mark("load: Lagrange-basis points from the seeds");
     ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = pkp.release();
     return ZK_OK;
@@ -660,7 +771,7 @@ const std::vector<uint8_t>& pk_verifying_key(const zkaes_pk_impl* pk) { return p
 void pk_info(const zkaes_pk_impl* pk, uint64_t info[ZK_PK_INFO_WORDS]) {
     const AesCircuit& c = pk->circ;
     uint64_t v[ZK_PK_INFO_WORDS] = {c.msg_len, c.num_constraints, (uint64_t)c.num_instance + c.num_witness, pk->nnz[0], pk->nnz[1], pk->nnz[2],
-                                    pk->h, pk->k, pk->x, pk->D, c.num_instance_used};
+                                    pk->h, pk->k, pk->x, pk->D, c.num_instance_used, pk->lag ? pk->lag_count : 0};
     memcpy(info, v, sizeof(v));
 }
 
@@ -800,9 +911,22 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_TRY(po_mask_fix(ctx, mask.as<Fr>(), h));  // mask[0] = -(mask[|H|] + mask[2|H|])
     tr.mark("r1: mask sample+upload");
     Committed c_w, c_za, c_zb, c_mask;
-    ZK_TRY(pc_commit(ctx, pk, w_poly.as<Fr>(), len_w, -1, true, zk, &c_w));
-    ZK_TRY(pc_commit(ctx, pk, za.as<Fr>(), h + 1, -1, true, zk, &c_za));
-    ZK_TRY(pc_commit(ctx, pk, zb.as<Fr>(), h + 1, -1, true, zk, &c_zb));
+    if (pk.lag && ctx->r1_lagrange && pk.small_bits[0] && pk.small_bits[1]) {
+        // w, z_A, z_B in the Lagrange basis: one small digit per element of H (the bit assignment; the row sums of A z, B z)
+        DevBuf vals;
+        ZK_CUDA(ctx, vals.alloc(sizeof(int32_t) * h, st));
+        ZK_TRY(po_assignment_h_i32(ctx, vals.as<int32_t>(), z, h, h / x, c.num_instance, c.num_witness));
+        ZK_TRY(lagrange_commit(ctx, pk, pk.lagw, vals.as<int32_t>(), 1, r_w, pk.v_hx, zk, &c_w));
+        Committed* cz[2] = {&c_za, &c_zb};
+        for (int m = 0; m < 2; ++m) {
+            ZK_TRY(po_spmv_bits_i32(ctx, vals.as<int32_t>(), pk.csr_ptr[m], pk.csr_col[m], pk.csr_cf[m], z, c.num_constraints, h));
+            ZK_TRY(lagrange_commit(ctx, pk, pk.lag, vals.as<int32_t>(), pk.small_bits[m], r_ab[m], pk.v_h, zk, cz[m]));
+        }
+    } else {
+        ZK_TRY(pc_commit(ctx, pk, w_poly.as<Fr>(), len_w, -1, true, zk, &c_w));
+        ZK_TRY(pc_commit(ctx, pk, za.as<Fr>(), h + 1, -1, true, zk, &c_za));
+        ZK_TRY(pc_commit(ctx, pk, zb.as<Fr>(), h + 1, -1, true, zk, &c_zb));
+    }
     ZK_TRY(pc_commit(ctx, pk, mask.as<Fr>(), len_mask, -1, false, zk, &c_mask));
     {
         std::vector<uint8_t> b;

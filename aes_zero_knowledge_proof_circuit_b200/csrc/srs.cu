@@ -55,6 +55,22 @@ __global__ void __launch_bounds__(128) k_fb_mul(const Affine<C>* __restrict__ ta
     out[i] = acc.to_affine();
 }
 
+// out[i] = scalars[start + i * stride] * G for Montgomery-form Fr scalars in HBM (the Lagrange-basis points of the prover key)
+template <class C>
+__global__ void __launch_bounds__(128) k_fb_mul_vec(const Affine<C>* __restrict__ table, const Fp<typename C::FrP>* __restrict__ scalars, size_t start,
+                                                   size_t stride, size_t n, Affine<C>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using Fr = Fp<typename C::FrP>;
+    Fr s = scalars[start + i * stride].from_mont();
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int w = 0; w < FB_WINDOWS; ++w) {
+        uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+        if (d) acc.madd(table[w * FB_ROW + d - 1]);
+    }
+    out[i] = acc.to_affine();
+}
+
 template <class F>
 __global__ void k_pow_table_srs(F* out, size_t count, F base, int shift) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,6 +85,20 @@ __global__ void k_pow_table_srs(F* out, size_t count, F base, int shift) {
     out[i] = r;
 }
 
+// the 32 x 255 table of d * 2^(8w) * G
+template <class C>
+static int fb_table_build(zkaes_ctx* ctx, DevBuf& table) {
+    cudaStream_t st = ctx->stream;
+    DevBuf rows;
+    ZK_CUDA(ctx, rows.alloc(sizeof(Affine<C>) * FB_WINDOWS, st));
+    ZK_CUDA(ctx, table.alloc(sizeof(Affine<C>) * FB_WINDOWS * FB_ROW, st));
+    k_fb_rows<C><<<1, FB_WINDOWS, 0, st>>>(rows.as<Affine<C>>());
+    k_fb_fill<C><<<cdiv(FB_WINDOWS * FB_ROW, 64), 64, 0, st>>>(rows.as<Affine<C>>(), table.as<Affine<C>>());
+    ctx->launches += 2;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+
 template <class C>
 int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* d_out, size_t start, size_t stride) {
     using Fr = Fp<typename C::FrP>;
@@ -78,22 +108,33 @@ int srs_powers_device(zkaes_ctx* ctx, const uint8_t seed32[32], size_t n, void* 
     for (int i = 0; i < 32; ++i) tau.v[i >> 2] |= (uint32_t)seed32[i] << (8 * (i & 3));
     tau.v[7] &= 0x0fffffffu;
     tau = tau.to_mont();
-    DevBuf rows, table, lo, hi;
-    ZK_CUDA(ctx, rows.alloc(sizeof(Affine<C>) * FB_WINDOWS, st));
-    ZK_CUDA(ctx, table.alloc(sizeof(Affine<C>) * FB_WINDOWS * FB_ROW, st));
+    DevBuf table, lo, hi;
+    ZK_TRY(fb_table_build<C>(ctx, table));
     size_t hi_cnt = ((start + n * stride) >> 10) + 1;
     ZK_CUDA(ctx, lo.alloc(sizeof(Fr) * 1024, st));
     ZK_CUDA(ctx, hi.alloc(sizeof(Fr) * hi_cnt, st));
-    k_fb_rows<C><<<1, FB_WINDOWS, 0, st>>>(rows.as<Affine<C>>());
-    k_fb_fill<C><<<cdiv(FB_WINDOWS * FB_ROW, 64), 64, 0, st>>>(rows.as<Affine<C>>(), table.as<Affine<C>>());
     k_pow_table_srs<Fr><<<4, 256, 0, st>>>(lo.as<Fr>(), 1024, tau, 0);
     k_pow_table_srs<Fr><<<cdiv(hi_cnt, 256), 256, 0, st>>>(hi.as<Fr>(), hi_cnt, tau, 10);
     if (n) k_fb_mul<C><<<cdiv(n, 128), 128, 0, st>>>(table.as<Affine<C>>(), lo.as<Fr>(), hi.as<Fr>(), start, stride, n,
                                                      reinterpret_cast<Affine<C>*>(d_out));
-    ctx->launches += 5;
+    ctx->launches += 3;
     ZK_CUDA(ctx, cudaGetLastError());
     return ZK_OK;
 }
+
+template <class C>
+int fb_mul_scalars_device(zkaes_ctx* ctx, const void* d_scalars, size_t n, void* d_out, size_t start, size_t stride) {
+    using Fr = Fp<typename C::FrP>;
+    DevBuf table;
+    ZK_TRY(fb_table_build<C>(ctx, table));
+    if (n) k_fb_mul_vec<C><<<cdiv(n, 128), 128, 0, ctx->stream>>>(table.as<Affine<C>>(), reinterpret_cast<const Fr*>(d_scalars), start, stride, n,
+                                                                  reinterpret_cast<Affine<C>*>(d_out));
+    ctx->launches++;
+    ZK_CUDA(ctx, cudaGetLastError());
+    return ZK_OK;
+}
+template int fb_mul_scalars_device<G1_377Params>(zkaes_ctx*, const void*, size_t, void*, size_t, size_t);
+template int fb_mul_scalars_device<G1_381Params>(zkaes_ctx*, const void*, size_t, void*, size_t, size_t);
 
 template int srs_powers_device<G1_377Params>(zkaes_ctx*, const uint8_t*, size_t, void*, size_t, size_t);
 template int srs_powers_device<G1_381Params>(zkaes_ctx*, const uint8_t*, size_t, void*, size_t, size_t);

@@ -116,6 +116,13 @@ int zkaes_msm_g1(zkaes_ctx* ctx, int curve_id, const void* bases_host, const voi
 #define ZKAES_MSM_BASES_PREPARED 2
 int zkaes_msm_g1_device(zkaes_ctx* ctx, int curve_id, const void* bases_dev, const void* scalars_dev, size_t n,
                         int flags, void* out_affine96_host);
+/* Small signed scalars: sum_i values[i] * bases[i] for |values[i]| <= 2^(value_bits - 1), value_bits in 1..13 (host buffers).
+ * One signed digit per term is the whole scalar, so the bucket method runs a single pass of at most n mixed additions (the
+ * general entry points spend W = 11 windows on a 253-bit scalar).  The kernel path of the prover's Lagrange-basis
+ * commitments to w, z_A, z_B (ark-marlin 0.3.0 ahp/prover.rs first round, whose evaluations over H are bits and sums of a
+ * few bits), exported so that it can be checked against zkaes_msm_g1 term by term. */
+int zkaes_msm_g1_small(zkaes_ctx* ctx, int curve_id, const void* bases_host, const int32_t* values_host, size_t n, int value_bits,
+                       void* out_affine96);
 /* Kept for ABI stability: the kernels read the arkworks form directly (12 x u32 Montgomery limbs per coordinate), so
  * "preparing" bases is the identity and ZKAES_MSM_BASES_PREPARED changes nothing. */
 int zkaes_msm_g1_prepare_bases(zkaes_ctx* ctx, int curve_id, void* bases_dev, size_t n);
@@ -196,9 +203,10 @@ int zkaes_witness_aes128_ecb(zkaes_ctx* ctx, const zkaes_circuit* c, const uint8
  * proof_out may be NULL to query the size; *proof_len is in/out (capacity in, bytes written out).  The bytes are the
  * ark-serialize 0.3.0 CanonicalSerialize form of ark_marlin::Proof (what `deserialize_proof`, src/lib.rs:52, reads).
  * info[]: 0 msg_len, 1 num_constraints, 2 num_variables, 3-5 nnz(A,B,C), 6 |H|, 7 |K|, 8 |X|, 9 SRS max degree,
- *         10 instance variables used. */
+ *         10 instance variables used, 11 Lagrange-basis points held per basis on this rank (0 = round 1 commits through the
+ *         SRS powers; see the tuning key "r1_lagrange"). */
 typedef struct zkaes_pk zkaes_pk;
-#define ZKAES_PK_INFO_WORDS 11
+#define ZKAES_PK_INFO_WORDS 12
 int zkaes_synthesize_keys(zkaes_ctx* ctx, size_t plaintext_len, const uint8_t tau_seed32[32], const uint8_t gamma_seed32[32], zkaes_pk** out);
 void zkaes_pk_free(zkaes_pk* pk);
 /* Key files (the reference regenerates SRS and keys in every process, src/lib.rs:138-174, and its

@@ -21,7 +21,7 @@ pub const ZKAES_MSM_BASES_PREPARED: c_int = 2;
 pub const ZKAES_PK_FILE_SRS: c_int = 1;
 pub const ZKAES_PK_FILE_INDEX_POLYS: c_int = 2;
 pub const ZKAES_CIRCUIT_INFO_WORDS: usize = 18;
-pub const ZKAES_PK_INFO_WORDS: usize = 11;
+pub const ZKAES_PK_INFO_WORDS: usize = 12;
 
 #[repr(C)]
 pub struct zkaes_ctx {
@@ -90,6 +90,7 @@ extern "C" {
     pub fn zkaes_dev_download(ctx: *mut zkaes_ctx, host: *mut c_void, dev: *const c_void, bytes: usize) -> c_int;
     // ---- MSM (ark-ec VariableBaseMSM seam)
     pub fn zkaes_msm_g1(ctx: *mut zkaes_ctx, curve_id: c_int, bases_host: *const c_void, scalars_host: *const c_void, n: usize, out_affine96: *mut c_void) -> c_int;
+    pub fn zkaes_msm_g1_small(ctx: *mut zkaes_ctx, curve_id: c_int, bases_host: *const c_void, values_host: *const i32, n: usize, value_bits: c_int, out_affine96: *mut c_void) -> c_int;
     pub fn zkaes_msm_g1_device(ctx: *mut zkaes_ctx, curve_id: c_int, bases_dev: *const c_void, scalars_dev: *const c_void, n: usize, flags: c_int, out_affine96_host: *mut c_void) -> c_int;
     pub fn zkaes_msm_g1_prepare_bases(ctx: *mut zkaes_ctx, curve_id: c_int, bases_dev: *mut c_void, n: usize) -> c_int;
     pub fn zkaes_msm_g1_windows_bytes(ctx: *mut zkaes_ctx, curve_id: c_int, n_total: usize) -> usize;

@@ -3,6 +3,7 @@ bit-exactly with the CPU oracle on the same seeded inputs; large sizes use size-
 import numpy as np
 import pytest
 
+import aes_zero_knowledge_proof_circuit_b200 as zk
 from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 pytestmark = pytest.mark.gpu
@@ -135,6 +136,43 @@ def test_msm_matches_oracle(ctx, oracle, curve, n):
     got = ctx.msm_g1(curve, bases, sc)
     exp = oracle.g1_msm(curve, bases, sc, algo=0)
     assert (got == exp).all(), (curve, n)
+
+
+@pytest.mark.parametrize("curve", CURVES)
+@pytest.mark.parametrize("n,bits", [(0, 1), (1, 1), (5, 2), (1000, 1), (1000, 2), (4097, 5), (70001, 13), (200000, 1), (200000, 2)])
+def test_small_scalar_msm_matches_oracle(ctx, oracle, curve, n, bits):
+    """zkaes_msm_g1_small (one signed digit per term, 32 pseudo-windows whose sums are added without doublings: the kernel path of the
+    Lagrange-basis commitments) against the CPU oracle's MSM on the same terms with the values taken mod r -- bits, sums of a few bits,
+    the widest digits allowed, equal and opposite points inside one bucket, zeros, a point at infinity, all-equal values (one bucket
+    run per pseudo-window)."""
+    rng = np.random.default_rng(curve * 131 + n * 7 + bits)
+    lim = 1 << (bits - 1)
+    vals = rng.integers(-lim, lim + 1, size=n).astype(np.int32) if bits > 1 else rng.integers(0, 2, size=n).astype(np.int32)
+    bases = oracle.g1_walk(curve, 4242 + n, 3, n)
+    if n > 8:
+        vals[0] = lim
+        vals[1] = -lim
+        vals[2] = 0
+        bases[4] = bases[3]
+        vals[3] = vals[4] = 1   # equal points in one bucket: a doubling
+        bases[6] = bases[5]
+        vals[5], vals[6] = 1, -1  # P + (-P)
+        bases[7] = 0            # infinity
+        vals[7] = 1
+    if n == 200000 and bits == 2:
+        vals[:] = 2             # every term in the same bucket of its pseudo-window
+    sc = ints_to_limbs([int(v) % FR[curve] for v in vals], 4) if n else np.zeros((0, 4), dtype=np.uint64)
+    got = ctx.msm_g1_small(curve, bases, vals, bits)
+    exp = oracle.g1_msm(curve, bases, sc, algo=0)
+    assert (got == exp).all(), (curve, n, bits)
+
+
+def test_small_scalar_msm_rejects_wide_values(ctx, oracle):
+    bases = oracle.g1_walk(377, 1, 3, 4)
+    with pytest.raises(zk.ZkAesError):
+        ctx.msm_g1_small(377, bases, np.array([0, 1, 3, 0], dtype=np.int32), 2)   # |3| > 2^(2-1)
+    with pytest.raises(zk.ZkAesError):
+        ctx.msm_g1_small(377, bases, np.array([0, 1, 1, 0], dtype=np.int32), 14)  # digit width out of range
 
 
 @pytest.mark.parametrize("window", [3, 5, 8, 11, 13, 16])

@@ -51,6 +51,22 @@ def test_proof_bytes_match_oracle_golden(ctx, pk16, golden):
     assert ct2 == ct and proof2 != proof
 
 
+def test_lagrange_basis_round1_gives_the_same_proof_bytes(ctx, pk16, golden):
+    """Round 1 commits to w, z_A, z_B in the Lagrange basis (one small digit per element of H) when the key holds those points, and
+    through the SRS powers (253-bit coefficients) otherwise: same group elements, hence the same golden proof bytes on both paths."""
+    assert pk16.info["lagrange_points"] == pk16.info["h"]  # single GPU: every L_k(tau) G lives on this rank
+    msg, key, seed = (bytes.fromhex(golden[k]) for k in ("message", "key", "zk_seed"))
+    try:
+        ctx.set_tuning("r1_lagrange", 0)
+        _, powers = ctx.encrypt(pk16, msg, key, seed)
+        ctx.set_tuning("r1_lagrange", 1)
+        _, lagrange = ctx.encrypt(pk16, msg, key, seed)
+    finally:
+        ctx.set_tuning("r1_lagrange", 1)
+    assert powers.hex() == golden["proof"]
+    assert lagrange.hex() == golden["proof"]
+
+
 def test_proof_bytes_match_second_golden(ctx, pk16):
     """another message, key and zk seed (FIPS-197 Appendix C.1) under the same proving key: byte-identical to the oracle prover again"""
     with open(os.path.join(GOLD, "marlin_proof_16B_fips_c1.json")) as f:
