@@ -293,7 +293,7 @@ struct zkaes_pk_impl {
     int8_t* kcoef[3] = {};
     uint8_t* heavy_flag = nullptr;  // per variable: column has > HEAVY_COL entries over A, B, C
     uint32_t* heavy_cols = nullptr;
-    size_t n_heavy = 0;
+    size_t n_heavy = 0, heavy_max_len = 0;  // heavy_max_len: entries of the longest heavy column within one matrix
     Fr* elems_h = nullptr;
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
     Aff* srs = nullptr;     // this rank's share of tau^i G, i <= D: the points i = rank (mod nranks), in the MSM kernels' internal form
@@ -332,6 +332,18 @@ int fr_rand_device(zkaes_ctx* ctx, ChaCha20Rng& rng, FrS* out, size_t count);  /
 namespace {
 
 int ntt(zkaes_ctx* ctx, Fr* data, int log_n, bool inverse, bool coset) { return ntt_device<Fr377Params>(ctx, CURVE, data, log_n, inverse, coset); }
+
+// this rank's contiguous slice of an n-element vector that every rank needs in full afterwards (all-gather in place): equal slices, or the
+// whole vector when the ranks do not divide n evenly or the slices would be tiny
+void shard_slice(const zkaes_ctx* ctx, size_t n, size_t* start, size_t* count) {
+    const size_t N = (size_t)ctx->nranks;
+    *start = 0;
+    *count = n;
+    if (N > 1 && n % N == 0 && n / N >= 4096) {
+        *count = n / N;
+        *start = (size_t)ctx->rank * *count;
+    }
+}
 
 // commit(poly) through the device MSM: sum coeffs[i] * srs[offset + i].
 // Multi-GPU: rank r keeps the SRS points i = r (mod N) (cyclic, so that polynomials of every length and the shifted
@@ -504,6 +516,7 @@ int pk_build_shape(zkaes_ctx* ctx, zkaes_pk_impl& pk, size_t msg_len) {
             if (col_total[j] > HEAVY_COL) {
                 flag[j] = 1;
                 cols.push_back((uint32_t)j);
+                pk.heavy_max_len = std::max<size_t>(pk.heavy_max_len, col_total[j]);  // bound of the column's length in any one matrix
             }
         pk.n_heavy = cols.size();
         ZK_CUDA(ctx, dev_upload(&pk.heavy_flag, flag, st));
@@ -876,32 +889,44 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, x_poly.alloc(sizeof(Fr) * x, st));
     ZK_TRY(po_bits_to_fr(ctx, x_poly.as<Fr>(), z, x));  // formatted input = the instance section of z
     ZK_TRY(ntt(ctx, x_poly.as<Fr>(), pk.log_x, true, false));
-    ZK_CUDA(ctx, x_evals.alloc(sizeof(Fr) * h, st));
-    ZK_CUDA(ctx, cudaMemsetAsync(x_evals.p, 0, sizeof(Fr) * h, st));
-    ZK_CUDA(ctx, cudaMemcpyAsync(x_evals.p, x_poly.p, sizeof(Fr) * x, cudaMemcpyDeviceToDevice, st));
-    ZK_TRY(ntt(ctx, x_evals.as<Fr>(), pk.log_h, false, false));
-    ZK_CUDA(ctx, wbuf.alloc(sizeof(Fr) * (h + 1), st));
-    ZK_TRY(po_w_evals(ctx, wbuf.as<Fr>(), z, x_evals.as<Fr>(), h, h / x, c.num_instance, c.num_witness));
-    x_evals.release();
-    ZK_TRY(ntt(ctx, wbuf.as<Fr>(), pk.log_h, true, false));
-    ZK_CUDA(ctx, cudaMemsetAsync(wbuf.as<Fr>() + h, 0, sizeof(Fr), st));
+    // w, z_A, z_B are three independent chains (w: two |H| transforms and the division by v_X; z_M: a sparse product and one transform): with
+    // several ranks each chain has one owner and the coefficient vectors are broadcast (2.1 GB each at 4 KiB) instead of every rank repeating all three
+    const int nr = ctx->nranks;
+    const int own_w = 0, own_z[2] = {nr > 1 ? 1 : 0, nr > 2 ? 2 : (nr > 1 ? 1 : 0)};
     Fr r_w = fr_rand(zk), r_a = fr_rand(zk), r_b = fr_rand(zk);
-    ZK_TRY(po_add_vanishing(ctx, wbuf.as<Fr>(), h, r_w));
     const size_t len_w = h + 1 - x;
     ZK_CUDA(ctx, w_poly.alloc(sizeof(Fr) * len_w, st));
-    ZK_CUDA(ctx, rem.alloc(sizeof(Fr) * h, st));
-    ZK_TRY(po_divide_vanishing(ctx, wbuf.as<Fr>(), h + 1, x, w_poly.as<Fr>(), rem.as<Fr>()));
-    wbuf.release();
+    if (ctx->rank == own_w) {
+        ZK_CUDA(ctx, x_evals.alloc(sizeof(Fr) * h, st));
+        ZK_CUDA(ctx, cudaMemsetAsync(x_evals.p, 0, sizeof(Fr) * h, st));
+        ZK_CUDA(ctx, cudaMemcpyAsync(x_evals.p, x_poly.p, sizeof(Fr) * x, cudaMemcpyDeviceToDevice, st));
+        ZK_TRY(ntt(ctx, x_evals.as<Fr>(), pk.log_h, false, false));
+        ZK_CUDA(ctx, wbuf.alloc(sizeof(Fr) * (h + 1), st));
+        ZK_TRY(po_w_evals(ctx, wbuf.as<Fr>(), z, x_evals.as<Fr>(), h, h / x, c.num_instance, c.num_witness));
+        x_evals.release();
+        ZK_TRY(ntt(ctx, wbuf.as<Fr>(), pk.log_h, true, false));
+        ZK_CUDA(ctx, cudaMemsetAsync(wbuf.as<Fr>() + h, 0, sizeof(Fr), st));
+        ZK_TRY(po_add_vanishing(ctx, wbuf.as<Fr>(), h, r_w));
+        ZK_CUDA(ctx, rem.alloc(sizeof(Fr) * h, st));
+        ZK_TRY(po_divide_vanishing(ctx, wbuf.as<Fr>(), h + 1, x, w_poly.as<Fr>(), rem.as<Fr>()));
+        wbuf.release();
+        rem.release();
+    }
     ZK_CUDA(ctx, za.alloc(sizeof(Fr) * (h + 1), st));
     ZK_CUDA(ctx, zb.alloc(sizeof(Fr) * (h + 1), st));
     DevBuf* zab[2] = {&za, &zb};
     const Fr r_ab[2] = {r_a, r_b};
     for (int m = 0; m < 2; ++m) {
+        if (ctx->rank != own_z[m]) continue;
         Fr* p = zab[m]->as<Fr>();
         ZK_TRY(po_spmv_bits(ctx, p, pk.csr_ptr[m], pk.csr_col[m], pk.csr_cf[m], z, c.num_constraints, h));
         ZK_TRY(ntt(ctx, p, pk.log_h, true, false));
         ZK_CUDA(ctx, cudaMemsetAsync(p + h, 0, sizeof(Fr), st));
         ZK_TRY(po_add_vanishing(ctx, p, h, r_ab[m]));
+    }
+    if (nr > 1) {
+        ZK_TRY(comm_broadcast(ctx, w_poly.p, sizeof(Fr) * len_w, own_w));
+        for (int m = 0; m < 2; ++m) ZK_TRY(comm_broadcast(ctx, zab[m]->p, sizeof(Fr) * (h + 1), own_z[m]));
     }
     tr.mark("r1: w, z_a, z_b polys");
     // mask polynomial: degree 3|H| + 2 zk - 3; force sum over H to zero by fixing the constant term
@@ -941,15 +966,21 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const Fr vh_alpha = vanishing(alpha, h);
     DevBuf ra, tpoly, zpoly, tmp;
     ZK_CUDA(ctx, ra.alloc(sizeof(Fr) * h, st));
-    ZK_CUDA(ctx, tmp.alloc(sizeof(Fr) * h, st));
-    ZK_TRY(po_rsub_scalar(ctx, tmp.as<Fr>(), pk.elems_h, alpha, h));
-    ZK_TRY(po_batch_inverse(ctx, ra.as<Fr>(), tmp.as<Fr>(), h));
-    ZK_TRY(po_scale(ctx, ra.as<Fr>(), ra.as<Fr>(), vh_alpha, h));  // r(alpha, h_i) = v_H(alpha) / (alpha - h_i)
+    {
+        size_t h0 = 0, hn = h;  // elementwise over H: a slice per rank, all-gathered in place
+        shard_slice(ctx, h, &h0, &hn);
+        ZK_CUDA(ctx, tmp.alloc(sizeof(Fr) * hn, st));
+        Fr* rs = ra.as<Fr>() + h0;
+        ZK_TRY(po_rsub_scalar(ctx, tmp.as<Fr>(), pk.elems_h + h0, alpha, hn));
+        ZK_TRY(po_batch_inverse(ctx, rs, tmp.as<Fr>(), hn));
+        ZK_TRY(po_scale(ctx, rs, rs, vh_alpha, hn));  // r(alpha, h_i) = v_H(alpha) / (alpha - h_i)
+        if (hn != h) ZK_TRY(comm_all_gather(ctx, rs, ra.p, sizeof(Fr) * hn));
+    }
     tmp.release();
     ZK_CUDA(ctx, tpoly.alloc(sizeof(Fr) * h, st));
     CscView csc[3];
     for (int m = 0; m < 3; ++m) csc[m] = CscView{pk.csc_ptr[m], pk.csc_row[m], pk.csc_cf[m]};
-    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), pk.heavy_flag, pk.heavy_cols, pk.n_heavy, nvar, h, x));
+    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), pk.heavy_flag, pk.heavy_cols, pk.n_heavy, pk.heavy_max_len, nvar, h, x));
     ZK_TRY(ntt(ctx, tpoly.as<Fr>(), pk.log_h, true, false));
     ZK_TRY(ntt(ctx, ra.as<Fr>(), pk.log_h, true, false));  // r_alpha polynomial
     ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));
@@ -1060,13 +1091,21 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     za.release(); w_poly.release(); h1.release();
     DevBuf fpoly, den, inv;
     ZK_CUDA(ctx, fpoly.alloc(sizeof(Fr) * k, st));
-    ZK_CUDA(ctx, den.alloc(sizeof(Fr) * k, st));
-    ZK_CUDA(ctx, inv.alloc(sizeof(Fr) * k, st));
-    ZK_CUDA(ctx, cudaMemsetAsync(fpoly.p, 0, sizeof(Fr) * k, st));
-    for (int m = 0; m < 3; ++m) {
-        ZK_TRY(po_den_k(ctx, den.as<Fr>(), pk.elems_h, pk.krow[m], pk.kcol[m], alpha, beta, k));
-        ZK_TRY(po_batch_inverse(ctx, inv.as<Fr>(), den.as<Fr>(), k));
-        ZK_TRY(po_gather_fma(ctx, fpoly.as<Fr>(), pk.elems_h, pk.krow[m], pk.kcoef[m], inv.as<Fr>(), eta[m] * hinv * vv, k));
+    {
+        // f over K is elementwise (three denominators, their batch inversion, the weighted sum): with several ranks each takes a slice of K and
+        // the slices are all-gathered in place (32 |K| bytes over NVLink against 7/8 of the inversions at N = 8); the inverse transform needs all of f
+        size_t k0 = 0, kn = k;
+        shard_slice(ctx, k, &k0, &kn);
+        ZK_CUDA(ctx, den.alloc(sizeof(Fr) * kn, st));
+        ZK_CUDA(ctx, inv.alloc(sizeof(Fr) * kn, st));
+        Fr* fs = fpoly.as<Fr>() + k0;
+        ZK_CUDA(ctx, cudaMemsetAsync(fs, 0, sizeof(Fr) * kn, st));
+        for (int m = 0; m < 3; ++m) {
+            ZK_TRY(po_den_k(ctx, den.as<Fr>(), pk.elems_h, pk.krow[m] + k0, pk.kcol[m] + k0, alpha, beta, kn));
+            ZK_TRY(po_batch_inverse(ctx, inv.as<Fr>(), den.as<Fr>(), kn));
+            ZK_TRY(po_gather_fma(ctx, fs, pk.elems_h, pk.krow[m] + k0, pk.kcoef[m] + k0, inv.as<Fr>(), eta[m] * hinv * vv, kn));
+        }
+        if (kn != k) ZK_TRY(comm_all_gather(ctx, fs, fpoly.p, sizeof(Fr) * kn));
     }
     den.release(); inv.release();
     ZK_TRY(ntt(ctx, fpoly.as<Fr>(), pk.log_k, true, false));
