@@ -577,20 +577,10 @@ int msm_small_window_sums(zkaes_ctx* ctx, const void* d_bases, const int32_t* d_
     ZK_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * (size_t)p.nb, st));
     sort_pass(offsets.as<uint32_t>(), sorted.as<uint32_t>());
     const uint32_t* bases = reinterpret_cast<const uint32_t*>(d_bases);
-    zkaes_ctx::ProfSpan span{};
-    if (ctx->prof) {
-        cudaEventCreate(&span.e0);
-        cudaEventCreate(&span.e1);
-        cudaEventRecord(span.e0, st);
-    }
+    // not entered in the profile spans (zkaes_ctx_profile): their mixed-addition count is an upper bound taken from the term count, and here
+    // zero values -- half of a bit vector -- produce no entry; bench.py's roofline is about the general-scalar launches
     msm_launch_accumulate<C>(ctx, slices, bases, sorted.as<uint32_t>(), offsets.as<uint32_t>(), p.nb, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
                              tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
-    if (ctx->prof) {
-        cudaEventRecord(span.e1, st);
-        span.terms = n;
-        span.madds = (uint64_t)n;  // upper bound: zero values produce no entry
-        ctx->prof_spans.push_back(span);
-    }
     k_msm_merge<C><<<cdiv(slices, 128), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),
                                                        tail.as<XYZZ<C>>(), tail_bucket.as<uint32_t>());
     k_msm_merge_heavy<C><<<cdiv(slices, 4), 128, 0, st>>>(offsets.as<uint32_t>(), (uint32_t)slices, L, buckets.as<XYZZ<C>>(), head.as<XYZZ<C>>(),

@@ -220,15 +220,40 @@ __global__ void __launch_bounds__(128) k_t_evals(F* out, CscView a, CscView b, C
     }
     st_fr(out + reindex_by_subdomain(j, period, x), tot);
 }
-// heavy columns (the constant one, key and round-key bits: touched by every ECB block).  The constant-one column has an entry in millions of
-// rows: with one CTA per column it alone took 110 ms per proof at 4 KiB (profiles/r2_launches_bench_4k.txt, k_t_evals_heavy).  So a column is cut
-// into chunks of T_HEAVY_CHUNK entries per matrix: CTA (column, chunk) sums its chunk, a second kernel adds a column's partial sums.
-static constexpr uint32_t T_HEAVY_CHUNK = 8192;
-__global__ void __launch_bounds__(256) k_t_evals_heavy(F* partials, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha,
-                                                       const uint32_t* __restrict__ heavy_cols) {
+// heavy columns (key and round-key bits, the wires every ECB block touches: 165,249 columns of ~450 entries at 4 KiB): one CTA per variable
+__global__ void __launch_bounds__(256) k_t_evals_heavy(F* out, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha,
+                                                       const uint32_t* __restrict__ heavy_cols, size_t period, size_t x) {
     __shared__ F sh[256];
     const size_t j = heavy_cols[blockIdx.x];
-    const uint32_t s0 = blockIdx.y * T_HEAVY_CHUNK;
+    F tot = F::zero();
+    const CscView* ms[3] = {&a, &b, &c};
+    const F etas[3] = {eta_a, eta_b, eta_c};
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi) {
+        const CscView& m = *ms[mi];
+        const uint32_t lo = m.ptr[j], hi = m.ptr[j + 1];
+        if (hi == lo) continue;
+        F s = F::zero();
+        for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) s = s + t_term(ld_fr(r_alpha + m.row[e]), m.coeff[e]);
+        tot = tot + s * etas[mi];
+    }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fr(out + reindex_by_subdomain(j, period, x), sh[0]);
+}
+// giant columns (the constant one: 25.6 M entries over A, B, C at 4 KiB): with one CTA the column alone took 110 ms per proof
+// (profiles/r2_launches_bench_4k.txt, k_t_evals_heavy).  A giant column is cut into chunks of T_GIANT_CHUNK entries per matrix: CTA
+// (column, chunk) sums its chunk, a second kernel adds the column's partial sums.
+static constexpr uint32_t T_GIANT_CHUNK = 8192;
+__global__ void __launch_bounds__(256) k_t_evals_giant(F* partials, CscView a, CscView b, CscView c, F eta_a, F eta_b, F eta_c, const F* r_alpha,
+                                                       const uint32_t* __restrict__ giant_cols) {
+    __shared__ F sh[256];
+    const size_t j = giant_cols[blockIdx.x];
+    const uint32_t s0 = blockIdx.y * T_GIANT_CHUNK;
     F tot = F::zero();
     const CscView* ms[3] = {&a, &b, &c};
     const F etas[3] = {eta_a, eta_b, eta_c};
@@ -238,7 +263,7 @@ __global__ void __launch_bounds__(256) k_t_evals_heavy(F* partials, CscView a, C
         const CscView& m = *ms[mi];
         const uint32_t end = m.ptr[j + 1];
         if (end - m.ptr[j] <= s0) continue;
-        const uint32_t lo = m.ptr[j] + s0, hi = end - lo > T_HEAVY_CHUNK ? lo + T_HEAVY_CHUNK : end;
+        const uint32_t lo = m.ptr[j] + s0, hi = end - lo > T_GIANT_CHUNK ? lo + T_GIANT_CHUNK : end;
         any = true;
         F s = F::zero();
         for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) s = s + t_term(ld_fr(r_alpha + m.row[e]), m.coeff[e]);
@@ -253,14 +278,14 @@ __global__ void __launch_bounds__(256) k_t_evals_heavy(F* partials, CscView a, C
     }
     if (threadIdx.x == 0) st_fr(partials + (size_t)blockIdx.x * gridDim.y + blockIdx.y, sh[0]);
 }
-__global__ void __launch_bounds__(256) k_t_evals_heavy_sum(F* out, const F* partials, uint32_t chunks_max, CscView a, CscView b, CscView c,
-                                                           const uint32_t* __restrict__ heavy_cols, size_t period, size_t x) {
+__global__ void __launch_bounds__(256) k_t_evals_giant_sum(F* out, const F* partials, uint32_t chunks_max, CscView a, CscView b, CscView c,
+                                                           const uint32_t* __restrict__ giant_cols, size_t period, size_t x) {
     __shared__ F sh[256];
-    const size_t j = heavy_cols[blockIdx.x];
+    const size_t j = giant_cols[blockIdx.x];
     uint32_t len = a.ptr[j + 1] - a.ptr[j];
     len = max(len, b.ptr[j + 1] - b.ptr[j]);
     len = max(len, c.ptr[j + 1] - c.ptr[j]);
-    const uint32_t chunks = (len + T_HEAVY_CHUNK - 1) / T_HEAVY_CHUNK;  // the chunks k_t_evals_heavy wrote
+    const uint32_t chunks = (len + T_GIANT_CHUNK - 1) / T_GIANT_CHUNK;  // the chunks k_t_evals_giant wrote
     F tot = F::zero();
     for (uint32_t s = threadIdx.x; s < chunks; s += blockDim.x) tot = tot + ld_fr(partials + (size_t)blockIdx.x * chunks_max + s);
     sh[threadIdx.x] = tot;
@@ -459,17 +484,23 @@ int po_divide_vanishing(zkaes_ctx* ctx, const F* c, size_t len, size_t n, F* q, 
     return ZK_OK;
 }
 int po_t_evals(zkaes_ctx* ctx, F* out, const CscView m[3], const F eta[3], const F* r_alpha, const uint8_t* heavy_flag,
-               const uint32_t* heavy_cols, size_t n_heavy, size_t heavy_max_len, size_t nvar, size_t h, size_t x) {
+               const uint32_t* heavy_cols, size_t n_heavy, const uint32_t* giant_cols, size_t n_giant, size_t giant_max_len, size_t nvar, size_t h,
+               size_t x) {
     cudaStream_t st = ctx->stream;
     ZK_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(F) * h, st));
     LAUNCH(ctx, k_t_evals, nvar, 128, out, m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, heavy_flag, nvar, h / x, x);
     if (n_heavy) {
-        const unsigned chunks = (unsigned)std::max<size_t>((heavy_max_len + T_HEAVY_CHUNK - 1) / T_HEAVY_CHUNK, 1);
+        k_t_evals_heavy<<<(unsigned)n_heavy, 256, 0, st>>>(out, m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, heavy_cols, h / x, x);
+        ctx->launches++;
+        ZK_CUDA(ctx, cudaGetLastError());
+    }
+    if (n_giant) {
+        const unsigned chunks = (unsigned)std::max<size_t>((giant_max_len + T_GIANT_CHUNK - 1) / T_GIANT_CHUNK, 1);
         if (chunks > 65535) return fail(ctx, ZK_ERR_UNSUPPORTED, "t_evals: a matrix column with more than 2^29 entries");
         DevBuf partials;
-        ZK_CUDA(ctx, partials.alloc(sizeof(F) * n_heavy * chunks, st));
-        k_t_evals_heavy<<<dim3((unsigned)n_heavy, chunks), 256, 0, st>>>(partials.as<F>(), m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, heavy_cols);
-        k_t_evals_heavy_sum<<<(unsigned)n_heavy, 256, 0, st>>>(out, partials.as<F>(), chunks, m[0], m[1], m[2], heavy_cols, h / x, x);
+        ZK_CUDA(ctx, partials.alloc(sizeof(F) * n_giant * chunks, st));
+        k_t_evals_giant<<<dim3((unsigned)n_giant, chunks), 256, 0, st>>>(partials.as<F>(), m[0], m[1], m[2], eta[0], eta[1], eta[2], r_alpha, giant_cols);
+        k_t_evals_giant_sum<<<(unsigned)n_giant, 256, 0, st>>>(out, partials.as<F>(), chunks, m[0], m[1], m[2], giant_cols, h / x, x);
         ctx->launches += 2;
         ZK_CUDA(ctx, cudaGetLastError());
     }

@@ -54,10 +54,11 @@ struct CscView {
     const uint32_t* row;
     const int8_t* coeff;
 };
-// Columns with many entries (heavy_flag[j] != 0, listed in heavy_cols; heavy_max_len = the longest of them in any one matrix) are cut into
-// chunks, one CTA per (column, chunk), instead of one thread per column.
+// Columns with many entries (heavy_flag[j] != 0) get one CTA each (heavy_cols) instead of one thread; the few with more than 2^16 entries
+// (giant_cols; giant_max_len = a bound of their length in any one matrix) are cut into chunks, one CTA per (column, chunk).
 int po_t_evals(zkaes_ctx* ctx, FrS* out, const CscView m[3], const FrS eta[3], const FrS* r_alpha, const uint8_t* heavy_flag,
-               const uint32_t* heavy_cols, size_t n_heavy, size_t heavy_max_len, size_t nvar, size_t h, size_t x);
+               const uint32_t* heavy_cols, size_t n_heavy, const uint32_t* giant_cols, size_t n_giant, size_t giant_max_len, size_t nvar, size_t h,
+               size_t x);
 // out = ra * (eta_a * za + eta_b * zb + eta_c * za * zb) - t * z
 int po_round2(zkaes_ctx* ctx, FrS* out, const FrS* ra, const FrS* za, const FrS* zb, const FrS* t, const FrS* z, const FrS eta[3], size_t n);
 // den = ab - alpha * row - beta * col + rc   (in place into row)

@@ -293,7 +293,8 @@ struct zkaes_pk_impl {
     int8_t* kcoef[3] = {};
     uint8_t* heavy_flag = nullptr;  // per variable: column has > HEAVY_COL entries over A, B, C
     uint32_t* heavy_cols = nullptr;
-    size_t n_heavy = 0, heavy_max_len = 0;  // heavy_max_len: entries of the longest heavy column within one matrix
+    uint32_t* giant_cols = nullptr;  // the heavy columns with more than GIANT_COL entries (the constant one): not in heavy_cols
+    size_t n_heavy = 0, n_giant = 0, giant_max_len = 0;  // giant_max_len: bound of a giant column's entries within one matrix
     Fr* elems_h = nullptr;
     Fr* idx_poly[12] = {};  // a_row a_col a_val a_row_col b_... (coefficients, k each)
     Aff* srs = nullptr;     // this rank's share of tau^i G, i <= D: the points i = rank (mod nranks), in the MSM kernels' internal form
@@ -320,6 +321,7 @@ struct zkaes_pk_impl {
         cudaFree(elems_h);
         cudaFree(heavy_flag);
         cudaFree(heavy_cols);
+        cudaFree(giant_cols);
         cudaFree(srs);
         cudaFree(lag);
         cudaFree(lagw);
@@ -509,18 +511,23 @@ int pk_build_shape(zkaes_ctx* ctx, zkaes_pk_impl& pk, size_t msg_len) {
         ZK_CUDA(ctx, cudaStreamSynchronize(st));  // host vectors go out of scope
     }
     {
-        constexpr uint32_t HEAVY_COL = 128;
+        constexpr uint32_t HEAVY_COL = 128, GIANT_COL = 1u << 16;
         std::vector<uint8_t> flag(nvar, 0);
-        std::vector<uint32_t> cols;
+        std::vector<uint32_t> cols, giants;
         for (size_t j = 0; j < nvar; ++j)
-            if (col_total[j] > HEAVY_COL) {
+            if (col_total[j] > GIANT_COL) {
+                flag[j] = 1;
+                giants.push_back((uint32_t)j);
+                pk.giant_max_len = std::max<size_t>(pk.giant_max_len, col_total[j]);  // bound of the column's length in any one matrix
+            } else if (col_total[j] > HEAVY_COL) {
                 flag[j] = 1;
                 cols.push_back((uint32_t)j);
-                pk.heavy_max_len = std::max<size_t>(pk.heavy_max_len, col_total[j]);  // bound of the column's length in any one matrix
             }
         pk.n_heavy = cols.size();
+        pk.n_giant = giants.size();
         ZK_CUDA(ctx, dev_upload(&pk.heavy_flag, flag, st));
         ZK_CUDA(ctx, dev_upload(&pk.heavy_cols, cols, st));
+        ZK_CUDA(ctx, dev_upload(&pk.giant_cols, giants, st));
         ZK_CUDA(ctx, cudaStreamSynchronize(st));
     }
     ZK_TRY(witness_upload(ctx, c, pk.wit));
@@ -980,7 +987,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     ZK_CUDA(ctx, tpoly.alloc(sizeof(Fr) * h, st));
     CscView csc[3];
     for (int m = 0; m < 3; ++m) csc[m] = CscView{pk.csc_ptr[m], pk.csc_row[m], pk.csc_cf[m]};
-    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), pk.heavy_flag, pk.heavy_cols, pk.n_heavy, pk.heavy_max_len, nvar, h, x));
+    ZK_TRY(po_t_evals(ctx, tpoly.as<Fr>(), csc, eta, ra.as<Fr>(), pk.heavy_flag, pk.heavy_cols, pk.n_heavy, pk.giant_cols, pk.n_giant, pk.giant_max_len, nvar, h, x));
     ZK_TRY(ntt(ctx, tpoly.as<Fr>(), pk.log_h, true, false));
     ZK_TRY(ntt(ctx, ra.as<Fr>(), pk.log_h, true, false));  // r_alpha polynomial
     ZK_CUDA(ctx, zpoly.alloc(sizeof(Fr) * (h + 1), st));

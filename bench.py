@@ -296,7 +296,9 @@ def bench_prove(args, rank, world, local_rank):
         "dtype": "u32x8 / u32x12 Montgomery (BLS12-377 Fr / Fq integers)", "data": "synthetic",
         "config": {"workload": f"encrypt() prove, {msg_len}-byte message ({msg_len // 16} ECB blocks), AES-128-ECB R1CS, Marlin/BLS12-377",
                    "msg_len": msg_len, "constraints": n_constraints, "H": pk.info["h"], "K": pk.info["k"], "srs_points": pk.info["max_degree"] + 1,
-                   "parallelism": "single GPU" if world == 1 else f"MSM point-range x{world} (NCCL all-gather of window sums), witness/NTT replicated",
+                   "parallelism": "single GPU" if world == 1 else (f"MSM point-range x{world} (NCCL all-gather of window sums), coset transforms spread over the ranks, "
+                                                                     "w / z_A / z_B chains one owner each, r_alpha and f in slices; witness and transcript replicated"),
+                   "r1_lagrange_basis": bool(pk.info.get("lagrange_points")),
                    "cache": "per-step working set (index polynomials + SRS + round buffers) exceeds the 126 MB L2; no flush needed",
                    "key_setup_s": setup_s, "proof_bytes": len(proof), "proof_sha256": hashlib.sha256(proof).hexdigest(),
                    "ciphertext_sha256": hashlib.sha256(ct).hexdigest(), "verified": verified},
