@@ -125,6 +125,7 @@ struct zkaes_ctx {
     DevArena arena;
     uint64_t scratch_peak = 0;   // pool high-water mark of the last encrypt() that ran without the arena
     int arena_state = 0;         // 0 = not tried yet, 1 = active, -1 = disabled / allocation failed
+    uint64_t arena_domain = 0;   // |H| of the key the peak was measured with: a key of another size releases the arena and measures again
 };
 
 namespace zk {

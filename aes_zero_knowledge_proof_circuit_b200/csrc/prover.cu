@@ -194,6 +194,12 @@ struct Blind {
 
 // ZKAES_TRACE=1: wall-clock per prover phase on stderr (development aid; synchronises the stream at phase boundaries)
 struct PhaseTrace {
+    // the largest per-phase pool peak seen since ScratchScope last cleared it: mark() resets the pool's high-water mark at every phase
+    // boundary, so under ZKAES_TRACE the scope's own reading at the end of encrypt() would only cover the last phase
+    static uint64_t& high_seen() {
+        static thread_local uint64_t v = 0;
+        return v;
+    }
     bool on;
     cudaStream_t st;
     std::chrono::steady_clock::time_point t0;
@@ -214,6 +220,7 @@ struct PhaseTrace {
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &used_high);
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
+            if (used_high > high_seen()) high_seen() = used_high;
         }
         fprintf(stderr, "[zkaes] %-28s %9.2f ms (allocator %7.2f ms)   device %6.1f GB in use | pool: phase peak %6.1f GB live, %6.1f GB reserved\n",
                 what, std::chrono::duration<double, std::milli>(t1 - t0).count(), DevBuf::alloc_seconds() * 1e3, (double)(mtotal - mfree) / 1e9,
@@ -230,10 +237,22 @@ struct ScratchScope {
     zkaes_ctx* ctx;
     cudaMemPool_t pool = nullptr;
     bool measuring = false;
-    explicit ScratchScope(zkaes_ctx* c) : ctx(c) {
+    ScratchScope(zkaes_ctx* c, uint64_t domain_h) : ctx(c) {
         static const bool enabled = !(getenv("ZKAES_ARENA") && getenv("ZKAES_ARENA")[0] == '0');
         pool = ctx->pool;
         if (!pool && cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) pool = nullptr;
+        if (ctx->arena_domain != domain_h) {
+            // a key of another size: the arena was carved for the previous key's peak -- too small for a larger circuit, tens of
+            // GB held for nothing after a smaller one.  Give it back and measure this key's peak on the pool, as on the first call.
+            if (ctx->arena.base) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ctx->arena.base);
+                ctx->arena.reset(nullptr, 0);
+            }
+            ctx->arena_state = 0;
+            ctx->scratch_peak = 0;
+            ctx->arena_domain = domain_h;
+        }
         if (enabled && ctx->arena_state == 0 && ctx->scratch_peak && pool) {
             cudaStreamSynchronize(ctx->stream);
             cudaMemPoolTrimTo(pool, 0);
@@ -252,6 +271,7 @@ struct ScratchScope {
         } else if (pool) {
             uint64_t zero = 0;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero);
+            PhaseTrace::high_seen() = 0;
             measuring = true;
         }
     }
@@ -265,7 +285,9 @@ struct ScratchScope {
         }
         if (measuring) {
             uint64_t high = 0;
-            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) == cudaSuccess && high > ctx->scratch_peak) ctx->scratch_peak = high;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) != cudaSuccess) high = 0;
+            if (PhaseTrace::high_seen() > high) high = PhaseTrace::high_seen();  // traced run: the phases' peaks
+            if (high > ctx->scratch_peak) ctx->scratch_peak = high;
         }
     }
 };
@@ -863,7 +885,7 @@ int pk_encrypt(zkaes_ctx* ctx, const zkaes_pk_impl* pkp, const uint8_t* msg, siz
     const size_t nvar = (size_t)c.num_instance + c.num_witness;
     ChaCha20Rng zk(zk_seed);
     PhaseTrace tr(st);
-    ScratchScope scratch(ctx);
+    ScratchScope scratch(ctx, pk.h);
 
     // ---- K1: witness ---------------------------------------------------------------------------------------------------
     DevBuf dmsg, dkey, dz, dct;

@@ -67,6 +67,24 @@ def test_lagrange_basis_round1_gives_the_same_proof_bytes(ctx, pk16, golden):
     assert lagrange.hex() == golden["proof"]
 
 
+def test_scratch_arena_follows_the_key_size(ctx, pk16, golden):
+    """The scratch arena is carved for one key's peak (second proof on a context): a key of another size must release it and measure
+    again -- a larger circuit must not be squeezed into the small key's arena, and going back must still give the golden bytes."""
+    msg, key, seed = (bytes.fromhex(golden[k]) for k in ("message", "key", "zk_seed"))
+    for _ in range(3):  # measure, carve, use
+        assert ctx.encrypt(pk16, msg, key, seed)[1].hex() == golden["proof"]
+    pk64 = ctx.synthesize_keys(64, TAU, GAMMA)
+    try:
+        m64 = bytes(range(64))
+        for _ in range(3):
+            ct, proof = ctx.encrypt(pk64, m64, key, seed)
+            assert zk.verify_encryption(pk64.verifying_key(), proof, ct)
+    finally:
+        pk64.close()
+    for _ in range(3):
+        assert ctx.encrypt(pk16, msg, key, seed)[1].hex() == golden["proof"]
+
+
 def test_proof_bytes_match_second_golden(ctx, pk16):
     """another message, key and zk seed (FIPS-197 Appendix C.1) under the same proving key: byte-identical to the oracle prover again"""
     with open(os.path.join(GOLD, "marlin_proof_16B_fips_c1.json")) as f:
