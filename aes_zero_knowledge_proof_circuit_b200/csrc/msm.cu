@@ -523,13 +523,7 @@ __global__ void __launch_bounds__(256) k_msm_digits_small(const int32_t* __restr
                                                           uint32_t* __restrict__ digits) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= padded) return;
-    uint32_t e = MSM_DIGIT_NONE;
-    if (j < n) {
-        const int32_t v = vals[start + j * stride];
-        if (v > 0) e = (uint32_t)(v - 1);
-        if (v < 0) e = (uint32_t)(-v - 1) | 0x80000000u;
-    }
-    digits[j] = e;
+    digits[j] = j < n ? msm_small_digit(vals[start + j * stride]) : MSM_DIGIT_NONE;
 }
 
 template <class C>

@@ -89,6 +89,13 @@ ZK_HD void msm_digits_all(const uint32_t* s, uint32_t flip, const MsmPlan& p, ui
     }
 }
 
+// Small-scalar MSM (msm.cu, msm_small_window_sums): the whole scalar is one signed digit, same encoding as above.
+ZK_HD uint32_t msm_small_digit(int32_t v) {
+    if (v > 0) return (uint32_t)(v - 1);
+    if (v < 0) return (uint32_t)(-(int64_t)v - 1) | 0x80000000u;
+    return MSM_DIGIT_NONE;
+}
+
 // ---- 128-bit moves of points -----------------------------------------------------------------------------------------
 template <class C>
 ZK_HD Affine<C> msm_load_affine(const uint32_t* bases, uint32_t idx) {

@@ -84,6 +84,73 @@ static int emul(const uint32_t* bases, const uint32_t* scalars, size_t n, int fo
     return p.c;
 }
 
+// The small-scalar pipeline (msm.cu, msm_small_window_sums): one signed digit per term, S pseudo-windows of m = ceil(n / S) consecutive terms with
+// 2^(c-1) buckets each, the entry of a term is its own index, slice accumulation / merges over the whole entry array, one bucket per reduction
+// segment, and the PLAIN sum of the S window sums.
+template <class C>
+static int emul_small(const uint32_t* bases, const int32_t* vals, size_t n, size_t start, size_t stride, int c, int S, uint32_t L, uint32_t* out96) {
+    MsmPlan p;
+    p.c = c;
+    p.W = S;
+    p.nbw = 1u << (c - 1);
+    p.nb = p.nbw * (uint32_t)S;
+    const size_t m = (n + (size_t)S - 1) / (size_t)S, padded = m * (size_t)S;
+    std::vector<uint32_t> digits(padded ? padded : 1), counts(p.nb + 1, 0u), offsets(p.nb + 1);
+    for (size_t j = 0; j < padded; ++j) digits[j] = j < n ? msm_small_digit(vals[start + j * stride]) : MSM_DIGIT_NONE;
+    for (size_t j = 0; j < padded; ++j)
+        if (digits[j] != MSM_DIGIT_NONE) {
+            if ((digits[j] & 0x7fffffffu) >= p.nbw) return -2;  // value wider than the digit
+            counts[(uint32_t)(j / m) * p.nbw + (digits[j] & 0x7fffffffu)]++;
+        }
+    uint32_t run = 0;
+    for (size_t k = 0; k <= p.nb; ++k) {
+        offsets[k] = run;
+        run += counts[k];
+    }
+    std::vector<uint32_t> sorted(run ? run : 1);
+    std::fill(counts.begin(), counts.end(), 0u);
+    for (size_t j = 0; j < padded; ++j)
+        if (digits[j] != MSM_DIGIT_NONE) {
+            const uint32_t key = (uint32_t)(j / m) * p.nbw + (digits[j] & 0x7fffffffu);
+            sorted[offsets[key] + counts[key]++] = (uint32_t)j | (digits[j] & 0x80000000u);
+        }
+    std::vector<XYZZ<C>> buckets(p.nb, XYZZ<C>::inf());
+    const size_t slices = (padded + L - 1) / L;
+    std::vector<XYZZ<C>> head(slices + 1), tail(slices + 1);
+    std::vector<uint32_t> tail_bucket(slices + 1, 0x12345678u);
+    memset((void*)head.data(), 0x5a, sizeof(XYZZ<C>) * head.size());
+    memset((void*)tail.data(), 0x5a, sizeof(XYZZ<C>) * tail.size());
+    for (size_t t = 0; t < slices; ++t)
+        msm_slice_accumulate<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), p.nb, sorted.data(), bases, buckets.data(), head.data(), tail.data(),
+                                tail_bucket.data());
+    for (size_t t = 0; t < slices + 1; ++t)
+        msm_merge_slice<C>((uint32_t)t, (uint32_t)slices, L, offsets.data(), buckets.data(), head.data(), tail.data(), tail_bucket.data());
+    for (size_t t = 0; t < slices + 1; ++t) {
+        XYZZ<C> sum = XYZZ<C>::inf(), lane_sum;
+        uint32_t b = 0;
+        bool any = false;
+        for (uint32_t lane = 0; lane < 32; ++lane)
+            if (msm_merge_lane<C>((uint32_t)t, lane, (uint32_t)slices, L, offsets.data(), head.data(), tail.data(), tail_bucket.data(), &lane_sum, &b)) {
+                sum.add(lane_sum);
+                any = true;
+            }
+        if (any) buckets[b] = sum;
+    }
+    XYZZ<C> total = XYZZ<C>::inf();
+    for (int w = 0; w < S; ++w)
+        for (uint32_t sid = 0; sid < p.nbw; ++sid) total.add(msm_reduce_segment<C>(buckets.data() + (size_t)w * p.nbw, p.nbw, 1, sid));
+    Affine<C> r = total.to_affine();
+    memcpy(out96, r.x.v, 48);
+    memcpy(out96 + 12, r.y.v, 48);
+    return 1;
+}
+extern "C" int msm_emul_small(int curve, const uint32_t* bases, const int32_t* vals, size_t n, size_t start, size_t stride, int c, int S, uint32_t L,
+                              uint32_t* out96) {
+    if (curve == 377) return emul_small<G1_377Params>(bases, vals, n, start, stride, c, S, L, out96);
+    if (curve == 381) return emul_small<G1_381Params>(bases, vals, n, start, stride, c, S, L, out96);
+    return -1;
+}
+
 // The pair-round pipeline (per window: 2^R-aligned sort, R rounds of pair products / inversion / affine additions, then the
 // slice accumulation over the pair sums), as msm.cu's msm_accumulate_paired sequences it.
 template <class C>

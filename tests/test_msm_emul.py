@@ -46,8 +46,21 @@ def emul():
         assert rc > 0
         return out
 
+    lib.msm_emul_small.restype = ctypes.c_int
+    lib.msm_emul_small.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]
+
+    def run_small(curve, bases, vals, n, start=0, stride=1, c=2, S=32, L=32):
+        bases = np.ascontiguousarray(bases, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.int32)
+        out = np.zeros(12, dtype=np.uint64)
+        rc = lib.msm_emul_small(curve, bases.ctypes.data, vals.ctypes.data, n, start, stride, c, S, L, out.ctypes.data)
+        assert rc > 0, rc
+        return out
+
     run.lib = lib
     run.paired = run_paired
+    run.small = run_small
     return run
 
 
@@ -140,3 +153,43 @@ def test_automatic_plan(emul):
     assert plan(1 << 27, nranks=8) == plan(1 << 24)          # the plan follows the per-rank share
     assert plan(1 << 27, cmax=23)[:2] == (23, 11)
     assert plan(1 << 20, bits=255, forced=16)[:2] == (16, 16)
+
+
+@pytest.mark.parametrize("curve", [377, 381])
+@pytest.mark.parametrize("c,S,L,n", [(1, 32, 32, 150), (1, 3, 5, 150), (2, 32, 7, 150), (2, 4, 1, 33), (3, 5, 64, 150), (13, 2, 3, 40), (1, 7, 4, 5), (2, 32, 32, 1)])
+def test_emulated_small_scalar_pipeline_matches_oracle(emul, oracle, curve, c, S, L, n):
+    """the Lagrange-basis commitments' MSM (msm_small_window_sums): one signed digit per term, S pseudo-windows summed without doublings --
+    bits, {-2..2}, the widest digit, fewer terms than pseudo-windows, bucket runs cut by many slices, equal / opposite points, infinity"""
+    rng = np.random.default_rng(c * 1000 + S * 10 + L)
+    lim = 1 << (c - 1)
+    vals = (rng.integers(0, 2, size=n) if c == 1 else rng.integers(-lim, lim + 1, size=n)).astype(np.int32)
+    bases = oracle.g1_walk(curve, 77 + n, 3, n)
+    if n > 16:
+        vals[0], vals[1], vals[2] = lim, -lim if c > 1 else 0, 0
+        bases[4] = bases[3]
+        vals[3] = vals[4] = 1
+        if c > 1:
+            bases[6] = bases[5]
+            vals[5], vals[6] = 1, -1
+        bases[7] = 0
+        vals[7] = 1
+    sc = ints_to_limbs([int(v) % FR[curve] for v in vals], 4)
+    exp = oracle.g1_msm(curve, bases, sc).reshape(-1)
+    assert (emul.small(curve, bases, vals, n, c=c, S=S, L=L) == exp).all()
+
+
+def test_emulated_small_scalar_cyclic_share(emul, oracle):
+    """rank r of N reads every N-th value starting at r against its own every-N-th bases (prover.cu lagrange_commit): the shares add up to the whole"""
+    curve, n, N = 377, 101, 4
+    rng = np.random.default_rng(9)
+    vals = rng.integers(-2, 3, size=n).astype(np.int32)
+    bases = oracle.g1_walk(curve, 5, 7, n)
+    parts = []
+    for r in range(N):
+        local = np.ascontiguousarray(bases[r::N])
+        parts.append(emul.small(curve, local, vals, len(local), start=r, stride=N, c=2, S=8, L=3))
+    total = parts[0]
+    for p in parts[1:]:
+        total = oracle.g1_add(curve, total, p)
+    sc = ints_to_limbs([int(v) % FR[curve] for v in vals], 4)
+    assert (total == oracle.g1_msm(curve, bases, sc).reshape(-1)).all()

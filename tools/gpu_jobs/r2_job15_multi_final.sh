@@ -11,15 +11,5 @@ timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N
 cut -c1-420 gpurun_out/j15_bench_4k_${N}gpu.json
 if [ "${3:-trace}" = "trace" ]; then
 ZKAES_TRACE=1 timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29572 bench.py --gpus $N --steps 1 --warmup 3 > gpurun_out/j15_trace_bench_${N}gpu.json 2> gpurun_out/j15_phase_trace_4k_${N}gpu_raw.txt; echo "trace rc=$?"
-python - <<PY
-fi
-import re, collections
-rows = collections.defaultdict(list)
-for line in open("gpurun_out/j15_phase_trace_4k_${N}gpu_raw.txt"):
-    m = re.match(r"\[zkaes\] (.{28})\s+([0-9.]+) ms", line)
-    if m: rows[m.group(1).strip()].append(float(m.group(2)))
-for k, v in rows.items():
-    last = v[-${N}:]
-    print(f"{k:28s} max over ranks of the last proof {max(last):9.2f} ms   min {min(last):9.2f}")
-PY
+python tools/trace_summary.py gpurun_out/j15_phase_trace_4k_${N}gpu_raw.txt $N
 fi
