@@ -16,6 +16,9 @@
 // host (portable arithmetic in ff.cuh) because the result is consumed by the host-side transcript anyway.
 // Multi-GPU: each rank runs 1-6 on its point range; window sums are all-gathered and folded (see capi.cu).
 //
+// Small signed scalars (the prover's Lagrange-basis commitments, zkaes_msm_g1_small): msm_small_window_sums below -- one digit per term,
+// steps 3-6 on S pseudo-windows whose sums are added without doublings.
+//
 // Large inputs are processed in chunks of at most MSM_CHUNK points so that the sort scratch stays bounded;
 // buckets persist across chunks.  No host synchronisation inside an MSM: grids are sized from upper bounds and the
 // kernels read the actual entry count from offsets[nb].

@@ -92,7 +92,9 @@ int zkaes_ctx_set_msm_window(zkaes_ctx* ctx, int window_bits);
 /* Further keys: "msm_madd_call" (0 / 1: ten inlined products per mixed addition / ten calls of one out-of-line multiplier, the default),
  * "msm_prefetch" (0 / 1 / 2: stage the next entry's point in shared memory with cp.async / cp.async.bulk + mbarrier; measured no gain,
  * default 0), "msm_plan_ranks" (the number of ranks that share a zkaes_msm_g1_windows / zkaes_msm_g1_fold MSM, so that the window plan
- * fits the per-rank share; every rank must set the same value; default 1). */
+ * fits the per-rank share; every rank must set the same value; default 1), "r1_lagrange" (1 / 0: zkaes_encrypt commits to w, z_A, z_B
+ * through the key's Lagrange-basis points with one small digit per term, or through the SRS powers as ark-marlin does; same commitments,
+ * same proof bytes; default 1, without effect on a key that holds no such points -- zkaes_pk_info word 11). */
 int zkaes_ctx_set_tuning(zkaes_ctx* ctx, const char* key, int value);
 
 /* ---- device memory (thin wrappers so non-CUDA hosts can keep inputs resident in HBM) -------------------- */
