@@ -481,7 +481,7 @@ def serialize_proof(fields: ProofFields) -> bytes:
 
 
 def pairing_selftest(a: int, b: int) -> bytes:
-    """e(a G1, b G2) as 576 canonical bytes (test hook, compared with oracle/pairing_ref.py)."""
+    """e(a G1, b G2) as 576 canonical bytes (test hook, compared with tools/pairing_model.py)."""
     out = np.zeros(576, dtype=np.uint8)
     ab = np.frombuffer(int(a).to_bytes(32, "little"), dtype=np.uint8)
     bb = np.frombuffer(int(b).to_bytes(32, "little"), dtype=np.uint8)

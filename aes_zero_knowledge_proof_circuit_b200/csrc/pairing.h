@@ -10,7 +10,7 @@
 // flattened); G2 is the D-type twist y^2 = x^3 + 1/u over Fq2, untwisted by (x', y') -> (x' w^2, y' w^3).
 // The Miller loop runs over the BLS parameter x with affine G2 arithmetic; the final exponentiation is the plain power
 // (q^12 - 1)/r.  Only pairing EQUATIONS are checked, which hold for any bilinear non-degenerate pairing; GT values are
-// cross-checked bit for bit against the big-integer model in oracle/pairing_ref.py (tests/test_verifier.py).
+// cross-checked bit for bit against the big-integer model in tools/pairing_model.py (tests/test_verifier.py).
 #pragma once
 #include <cstdint>
 

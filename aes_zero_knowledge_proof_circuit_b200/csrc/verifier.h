@@ -27,7 +27,7 @@ int verify_encryption_host(const uint8_t* vk, size_t vk_len, const uint8_t* proo
 int proof_deserialize_host(const uint8_t* proof, size_t len, struct zkaes_proof_fields* out, std::string* err);
 int proof_serialize_host(const struct zkaes_proof_fields* in, std::vector<uint8_t>& out, std::string* err);
 
-// e(a G1, b G2) as 12 x 48 canonical LE bytes (c[0].c0, c[0].c1, c[1].c0, ...): test hook against oracle/pairing_ref.py
+// e(a G1, b G2) as 12 x 48 canonical LE bytes (c[0].c0, c[0].c1, c[1].c0, ...): test hook against tools/pairing_model.py
 void pairing_selftest(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]);
 
 }  // namespace zk

@@ -273,7 +273,7 @@ typedef struct zkaes_proof_fields {
 int zkaes_proof_deserialize(const uint8_t* proof, size_t proof_len, zkaes_proof_fields* out);
 int zkaes_proof_serialize(const zkaes_proof_fields* in, uint8_t* out, size_t* len);  /* out may be NULL to query the size */
 
-/* Test hook: e(a G1, b G2) for canonical 32-byte LE scalars, as 12 x 48 canonical LE bytes (oracle/pairing_ref.py layout). */
+/* Test hook: e(a G1, b G2) for canonical 32-byte LE scalars, as 12 x 48 canonical LE bytes (tools/pairing_model.py layout). */
 int zkaes_selftest_pairing(const uint8_t a32[32], const uint8_t b32[32], uint8_t out576[576]);
 
 #ifdef __cplusplus

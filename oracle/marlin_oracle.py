@@ -937,8 +937,8 @@ def verifying_key_bytes(index_vk: bytes, x_padded: int, max_degree: int, h: int,
     {comm: compressed G1, shifted_comm: None}, marlin_pc::VerifierKey {kzg10 vk {g, gamma_g: G1; h, beta_h = tau h: compressed G2},
     degree_bounds_and_shift_powers: Some([(bound, tau^(D - bound) G)]) ascending, max_degree, supported_degree}.
     `index_vk` is IndexVerifierKey's ToBytes form (Index.vk_bytes()).  Built independently of the product (oracle G1 arithmetic,
-    big-integer G2 from oracle/pairing_ref.py)."""
-    from . import pairing_ref as pr
+    big-integer G2 from tools/pairing_model.py)."""
+    from tools import pairing_model as pr
 
     tau, gamma = seed_to_scalar(tau_seed), seed_to_scalar(gamma_seed)
     g1 = lambda s: g1_serialize_compressed(orc().g1_mul_gen(CURVE, ints_to_limbs([s % P], 4))[0])

@@ -34,7 +34,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (test infrastructure): builds oracle/liboracle.so if missing."""
-    from tests.oracle_lib import Oracle
+    from oracle.cpu import Oracle
 
     return Oracle()
 

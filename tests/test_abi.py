@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import aes_zero_knowledge_proof_circuit_b200 as zk
-from tests.oracle_lib import FQ, FR, ints_to_limbs, rand_fr
+from oracle.cpu import FQ, FR, ints_to_limbs, rand_fr
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

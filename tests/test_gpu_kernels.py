@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import aes_zero_knowledge_proof_circuit_b200 as zk
-from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
+from oracle.cpu import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 pytestmark = pytest.mark.gpu
 CURVES = [377, 381]

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.oracle_lib import FR, ints_to_limbs, limbs_to_ints, rand_fr
+from oracle.cpu import FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

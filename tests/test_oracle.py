@@ -8,7 +8,7 @@ import random
 import numpy as np
 import pytest
 
-from tests.oracle_lib import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
+from oracle.cpu import FQ, FR, ints_to_limbs, limbs_to_ints, rand_fr
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 

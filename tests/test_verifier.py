@@ -1,6 +1,6 @@
 """verify_encryption (host verifier, csrc/verifier.cpp + csrc/pairing.h) -- CPU tier, no GPU needed.
 
-  * the C++ pairing against the big-integer model (oracle/pairing_ref.py): GT values bit for bit, bilinearity;
+  * the C++ pairing against the big-integer model (tools/pairing_model.py): GT values bit for bit, bilinearity;
   * the reference's own verifier assertions (tests/integration_tests.rs:313-372: accept the proof for the right ciphertext,
     reject it for a wrong one) on the golden 16-byte proof, with a verifying key built independently by the oracle."""
 import json
@@ -9,7 +9,7 @@ import os
 import pytest
 
 import aes_zero_knowledge_proof_circuit_b200 as zk
-from oracle import pairing_ref as pr
+from tools import pairing_model as pr
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "marlin_proof_16B.json")
 
@@ -25,7 +25,7 @@ def _gt_bytes(e):
 
 
 def test_pairing_matches_big_integer_model():
-    # NOTE on independence: oracle/pairing_ref.py re-exports tools/pairing_model.py, which also GENERATES the product's pairing constants
+    # NOTE on independence: tools/pairing_model.py also GENERATES the product's pairing constants
     # (twist coefficient, G2 generator, final exponent).  This test therefore pins the C++ tower / Miller loop arithmetic, not the constants;
     # the constants are pinned by test_accepts_golden_proof_and_rejects_wrong_ciphertext and the GPU tier, where the pairing verifier must
     # agree with the oracle's TRAPDOOR verifier (G1 only, no G2 constant involved) on every accept / reject.
@@ -122,7 +122,7 @@ def test_non_canonical_encodings_are_refused(golden):
     t = bytearray(proof); t[o["comm0"] + 47] |= 0xC0; cases["infinity and sign flags"] = bytes(t)
     t = bytearray(proof); t[o["comm0"] + 47] = (t[o["comm0"] + 47] & 0x3F) | 0x40; cases["infinity with non-zero x"] = bytes(t)
     # (e) a point of the curve outside the prime-order subgroup (BLS12-377 G1 has a cofactor): smallest x with x^3 + 1 a square
-    from tests.oracle_lib import FQ
+    from oracle.cpu import FQ
     q = FQ[377]
     x = next(x for x in range(2, 100) if pow(x ** 3 + 1, (q - 1) // 2, q) == 1)
     t = bytearray(proof); t[o["comm0"]:o["comm0"] + 48] = x.to_bytes(48, "little"); cases["outside the subgroup"] = bytes(t)

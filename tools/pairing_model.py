@@ -1,5 +1,5 @@
 """Big-integer model of the BLS12-377 ate pairing: derives the constants of csrc/pairing_params_gen.h (through
-tools/gen_pairing_params.py) and, re-exported as oracle/pairing_ref.py, serves the tests as the reference the product's host
+tools/gen_pairing_params.py) and serves the tests as the reference the product's host
 pairing (csrc/pairing.h) is compared with bit for bit.  A development / test script: nothing in the product imports it.
 
 Parity unpinned against arkworks' GT values: only pairing EQUATIONS are ever checked, and those hold for any bilinear
