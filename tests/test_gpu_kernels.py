@@ -234,6 +234,26 @@ def test_msm_edge_cases(ctx, oracle):
     assert (ctx.msm_g1(curve, bases, big) == oracle.g1_msm(curve, bases, big)).all()
 
 
+def test_srs_powers_across_normalisation_chunks(ctx, oracle):
+    """The fixed-base kernels leave XYZZ sums in a chunk buffer of 2^22 points and a second kernel normalises runs of 32 points with one
+    inversion each: points on both sides of the run and chunk boundaries against the oracle's tau^i G, and every point on the curve."""
+    import torch
+
+    curve, n = 377, (1 << 22) + 37
+    r = FR[curve]
+    seed = bytes(range(7, 39))
+    tau = int.from_bytes(seed, "little") & ((1 << 252) - 1)
+    d_bases = torch.empty(n * 96, dtype=torch.uint8, device="cuda")
+    ctx.srs_powers_device(curve, seed, n, d_bases)
+    ctx.sync()
+    bases = d_bases.cpu().numpy().view(np.uint64).reshape(n, 12)
+    idx = [0, 1, 31, 32, 33, 63, 64, (1 << 22) - 33, (1 << 22) - 1, 1 << 22, (1 << 22) + 1, (1 << 22) + 31, (1 << 22) + 32, n - 1]
+    exp = oracle.g1_mul_gen(curve, ints_to_limbs([pow(tau, i, r) for i in idx], 4))
+    assert (bases[idx] == exp).all()
+    assert oracle.g1_on_curve(curve, bases[:: 257])
+    assert oracle.g1_on_curve(curve, bases[(1 << 22) - 64:])
+
+
 def test_srs_powers_and_large_msm_properties(ctx, oracle):
     """2^18 terms: SRS generated on the device, checked on-curve + first points against the oracle; MSM checked by
     linearity (msm(a)+msm(b) == msm(a+b mod r)) and by the trapdoor identity msm(s, tau^i G) == (sum s_i tau^i) G."""
