@@ -5,8 +5,8 @@
 // ark-marlin 0.3.0 Marlin::verify: Fiat-Shamir replay of the three AHP rounds, ahp/mod.rs construct_linear_combinations,
 // ark-poly-commit 0.3.0 marlin_pc::check_combinations (degree-bound adjustment with the shift powers) and one KZG
 // pairing equation per query point.  The verifier is CPU code in the reference and CPU code here;
-// no device is needed.  Deviation: the two query points are checked one after the other instead of through ark's
-// randomised batch (which draws from the caller's rng); accept/reject is the same up to the batch's soundness error.
+// no device is needed.  The two query points are checked through one randomised product as in ark's KZG10::batch_check; ark draws
+// the randomizer from the caller's rng, here it is a hash of the points being combined (this ABI has no rng argument).
 #include "verifier.h"
 #include "../../include/zkaes_b200.h"
 
@@ -626,6 +626,7 @@ int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t
         // ---- marlin_pc check_combinations + KZG10 check per query point -------------------------------------------------------------
         const std::vector<LC>* groups[2] = {&at_beta, &at_gamma};
         const Fr points[2] = {beta, gamma};
+        Aff lhs[2];  // per query point: C - v G - rv gamma G + z W
         for (int g = 0; g < 2; ++g) {
             XY comb = XY::inf();
             Fr comb_v = Fr::zero(), cj = Fr::one();
@@ -661,8 +662,26 @@ int verify_encryption_host(const uint8_t* vk_bytes, size_t vk_len, const uint8_t
             if (has_rv[g]) comb.madd(g1_scale(gamma_G, rv[g]).neg());
             // C - v G - rv gamma G = (tau - z) W   <=>   e(C - v G - rv gamma G + z W, H) * e(-W, tau H) = 1
             comb.madd(g1_scale(W[g], points[g]));
-            if (!pairing::pairing_product_is_one(comb.to_affine(), H, W[g].neg(), beta_H)) return 0;
+            lhs[g] = comb.to_affine();
         }
+        // KZG10::batch_check (ark-poly-commit 0.3.0 kzg10/mod.rs): the two equations e(lhs_g, H) = e(W_g, tau H) are folded with randomizers
+        // 1 and rho into ONE product of two pairings.  ark draws rho (128 bits) from the caller's rng; this ABI has no rng argument, so rho
+        // is the Blake2s hash of the four points -- fixed by the statement before the check, which is all the argument needs.  A proof whose
+        // two equations do not both hold passes with probability 2^-128.
+        std::vector<uint8_t> hb;
+        for (int g = 0; g < 2; ++g) {
+            g1_to_bytes(lhs[g], hb);
+            g1_to_bytes(W[g], hb);
+        }
+        uint8_t digest[32];
+        Blake2s::digest(hb, digest);
+        Fr rho = Fr::zero();
+        for (int i = 0; i < 16; ++i) rho.v[i >> 2] |= (uint32_t)digest[i] << (8 * (i & 3));
+        rho = rho.to_mont();
+        XY total_c = XY::from_affine(lhs[0]), total_w = XY::from_affine(W[0]);
+        total_c.madd(g1_scale(lhs[1], rho));
+        total_w.madd(g1_scale(W[1], rho));
+        if (!pairing::pairing_product_is_one(total_c.to_affine(), H, total_w.to_affine().neg(), beta_H)) return 0;
         *accepted = 1;
         return 0;
     } catch (const std::exception& e) {

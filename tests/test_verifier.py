@@ -77,6 +77,11 @@ def test_rejects_tampered_proofs(golden):
     t = bytearray(proof)
     t[w_beta + 49 + 2] ^= 4
     assert zk.verify_encryption(vk, bytes(t), ct) is False
+    # both opening witnesses exchanged: the two KZG equations are checked as ONE randomised product (KZG10::batch_check); two wrong
+    # equations must not cancel
+    t = bytearray(proof)
+    t[w_beta: w_beta + 48], t[w_beta + 81: w_beta + 81 + 48] = proof[w_beta + 81: w_beta + 81 + 48], proof[w_beta: w_beta + 48]
+    assert zk.verify_encryption(vk, bytes(t), ct) is False
 
 
 def test_malformed_inputs_are_errors(golden):
