@@ -8,8 +8,8 @@
 //
 // Tower (ark-bls12-377's): Fq2 = Fq[u]/(u^2 + 5); Fq12 = Fq2[w]/(w^6 - u) (ark's Fq6 = Fq2[v]/(v^3 - u), Fq12 = Fq6[w]/(w^2 - v)
 // flattened); G2 is the D-type twist y^2 = x^3 + 1/u over Fq2, untwisted by (x', y') -> (x' w^2, y' w^3).
-// The Miller loop runs over the BLS parameter x with affine G2 arithmetic; the final exponentiation is the plain power
-// (q^12 - 1)/r.  Only pairing EQUATIONS are checked, which hold for any bilinear non-degenerate pairing; GT values are
+// The Miller loop runs over the BLS parameter x with affine G2 arithmetic; the final exponentiation of pairing() is the plain power
+// (q^12 - 1)/r, the equation check uses the structured form (its cube, see below).  Only pairing EQUATIONS are checked, which hold for any bilinear non-degenerate pairing; GT values are
 // cross-checked bit for bit against the big-integer model in tools/pairing_model.py (tests/test_verifier.py).
 #pragma once
 #include <cstdint>
@@ -191,9 +191,104 @@ inline Fq12 miller_loop(const G1A& p, const G2A& q) {
 }
 inline Fq12 final_exponentiation(const Fq12& f) { return f.pow(pairing_params::FINAL_EXP, pairing_params::FINAL_EXP_LIMBS); }
 inline Fq12 pairing(const G1A& p, const G2A& q) { return final_exponentiation(miller_loop(p, q)); }
+
+// ---- structured final exponentiation (for the equation checks; the plain power above defines the GT VALUES the tests compare) --------------------
+// f^(3 (q^12 - 1) / r) = easy part f^((q^6 - 1)(q^2 + 1)), then the BLS12 hard part through
+//     3 (q^4 - q^2 + 1) / r = (x - 1)^2 (x + q) (x^2 + q^2 - 1) + 3           (checked for this curve by tools/pairing_model.py's integers),
+// i.e. five powers by the 64-bit x, two Frobenius maps and a handful of products instead of a 4,300-bit power.  The result is the CUBE of the
+// plain power; 3 does not divide r, so "== 1" is the same statement (tests/pairing_check.cpp compares the two bit for bit).
+struct Fq6 {  // Fq2[v] / (v^3 - u): the even (or odd) coefficients of an Fq12 element, v = w^2
+    Fq2 a, b, c;
+    Fq6 operator+(const Fq6& o) const { return {a + o.a, b + o.b, c + o.c}; }
+    Fq6 operator-(const Fq6& o) const { return {a - o.a, b - o.b, c - o.c}; }
+    Fq6 operator*(const Fq6& o) const {
+        const Fq2 t0 = a * o.a, t1 = a * o.b + b * o.a, t2 = a * o.c + b * o.b + c * o.a, t3 = b * o.c + c * o.b, t4 = c * o.c;
+        return {t0 + t3.mul_by_u(), t1 + t4.mul_by_u(), t2};
+    }
+    Fq6 mul_by_v() const { return {c.mul_by_u(), a, b}; }
+    Fq6 inverse() const {
+        const Fq2 t0 = a * a - (b * c).mul_by_u(), t1 = (c * c).mul_by_u() - a * b, t2 = b * b - a * c;
+        const Fq2 d = (a * t0 + (c * t1 + b * t2).mul_by_u()).inverse();
+        return {t0 * d, t1 * d, t2 * d};
+    }
+};
+inline Fq12 fq12_conj6(const Fq12& f) {  // f^(q^6): w -> -w
+    Fq12 r = f;
+    for (int i = 1; i < 6; i += 2) r.c[i] = f.c[i].neg();
+    return r;
+}
+inline Fq12 fq12_inverse(const Fq12& f) {  // (A + w B)^-1 = (A - w B) / (A^2 - v B^2)
+    const Fq6 A = {f.c[0], f.c[2], f.c[4]}, B = {f.c[1], f.c[3], f.c[5]};
+    const Fq6 n = (A * A - (B * B).mul_by_v()).inverse();
+    const Fq6 ra = A * n, rb = B * n;
+    Fq12 r;
+    r.c[0] = ra.a; r.c[2] = ra.b; r.c[4] = ra.c;
+    r.c[1] = rb.a.neg(); r.c[3] = rb.b.neg(); r.c[5] = rb.c.neg();
+    return r;
+}
+// w^(q-1) = u^((q-1)/6) =: g, so (c_i w^i)^q = conj(c_i) g^i w^i (u^q = -u because -5 is a non-residue); for q^2 the factor is norm(g)^i in Fq
+struct FrobeniusTable {
+    Fq2 g[6];
+    Fq n[6];
+    FrobeniusTable() {
+        uint32_t e[12];  // (q - 1) / 6 by long division of the modulus limbs
+        uint64_t rem = 0;
+        for (int i = 11; i >= 0; --i) {
+            const uint64_t cur = (rem << 32) | (uint64_t)(Fq377Params::MOD(i) - (i == 0 ? 1u : 0u));  // q is odd: the low limb does not borrow
+            e[i] = (uint32_t)(cur / 6);
+            rem = cur % 6;
+        }
+        Fq2 base = {Fq::zero(), Fq::one()}, acc = Fq2::one();
+        for (int i = 12 * 32 - 1; i >= 0; --i) {
+            acc = acc * acc;
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * base;
+        }
+        g[0] = Fq2::one();
+        n[0] = Fq::one();
+        const Fq nn = acc.c0 * acc.c0 + Fq2::times5(acc.c1 * acc.c1);
+        for (int i = 1; i < 6; ++i) {
+            g[i] = g[i - 1] * acc;
+            n[i] = n[i - 1] * nn;
+        }
+    }
+};
+inline const FrobeniusTable& frobenius_table() {
+    static const FrobeniusTable t;
+    return t;
+}
+inline Fq12 fq12_frobenius(const Fq12& f) {
+    const FrobeniusTable& t = frobenius_table();
+    Fq12 r;
+    for (int i = 0; i < 6; ++i) r.c[i] = Fq2{f.c[i].c0, f.c[i].c1.neg()} * t.g[i];
+    return r;
+}
+inline Fq12 fq12_frobenius2(const Fq12& f) {
+    const FrobeniusTable& t = frobenius_table();
+    Fq12 r;
+    for (int i = 0; i < 6; ++i) r.c[i] = f.c[i].scale(t.n[i]);
+    return r;
+}
+inline Fq12 fq12_pow_x(const Fq12& f) {
+    const uint32_t x[2] = {(uint32_t)pairing_params::BLS_X, (uint32_t)(pairing_params::BLS_X >> 32)};
+    return f.pow(x, 2);
+}
+inline Fq12 final_exponentiation_cubed(const Fq12& f) {
+    Fq12 m = fq12_conj6(f) * fq12_inverse(f);  // f^(q^6 - 1): from here on the inverse is the conjugate
+    m = fq12_frobenius2(m) * m;                // ^(q^2 + 1)
+    const Fq12 t0 = fq12_pow_x(m) * fq12_conj6(m);                                       // m^(x - 1)
+    const Fq12 t1 = fq12_pow_x(t0) * fq12_conj6(t0);                                     // m^((x - 1)^2)
+    const Fq12 t2 = fq12_pow_x(t1) * fq12_frobenius(t1);                                 // ^(x + q)
+    const Fq12 t3 = fq12_pow_x(fq12_pow_x(t2)) * fq12_frobenius2(t2) * fq12_conj6(t2);   // ^(x^2 + q^2 - 1)
+    return t3 * (m * m * m);
+}
 // e(a1, b1) * e(a2, b2) == 1 with one final exponentiation
 inline bool pairing_product_is_one(const G1A& a1, const G2A& b1, const G1A& a2, const G2A& b2) {
-    return final_exponentiation(miller_loop(a1, b1) * miller_loop(a2, b2)) == Fq12::one();
+    const Fq12 f = miller_loop(a1, b1) * miller_loop(a2, b2);
+    // a Miller value is never zero for points of order r; if it were, the plain power decides (0 != 1)
+    bool zero = true;
+    for (int i = 0; i < 6; ++i) zero = zero && f.c[i].is_zero();
+    if (zero) return false;
+    return final_exponentiation_cubed(f) == Fq12::one();
 }
 
 }  // namespace pairing

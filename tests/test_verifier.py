@@ -37,6 +37,26 @@ def test_pairing_matches_big_integer_model():
     assert zk.pairing_selftest(7, 0) == _gt_bytes(pr.F12ONE)
 
 
+def test_structured_final_exponentiation_is_the_cube_of_the_plain_power():
+    """csrc/pairing.h checks pairing equations with the BLS12 hard-part chain (five powers by x, Frobenius maps) instead of the 4,300-bit
+    power: tests/pairing_check.cpp requires it to equal the plain power cubed bit for bit, the Frobenius maps to be the q-th / q^2-th powers,
+    the inverse to invert, and e(aP, bQ) e(-abP, Q) == 1 (and != 1 one step off) through the equation form the verifier calls."""
+    import ctypes
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "pairing_check.cpp")
+    out = os.path.join(root, "tests", "_pairing_check.so")
+    hdr = os.path.join(root, "aes_zero_knowledge_proof_circuit_b200", "csrc", "pairing.h")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    lib = ctypes.CDLL(out)
+    lib.pairing_fast_check.restype = ctypes.c_int
+    lib.pairing_fast_check.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
+    for a, b in ((1, 1), (0x1234567, 0xFEDCBA9876543), (2**63 + 5, 3)):
+        assert lib.pairing_fast_check(a, b) == 0, (a, b)
+
+
 def test_accepts_golden_proof_and_rejects_wrong_ciphertext(golden):
     vk, proof, ct = bytes.fromhex(golden["verifying_key"]), bytes.fromhex(golden["proof"]), bytes.fromhex(golden["ciphertext"])
     assert zk.verify_encryption(vk, proof, ct) is True
