@@ -85,6 +85,27 @@ def test_scratch_arena_follows_the_key_size(ctx, pk16, golden):
         assert ctx.encrypt(pk16, msg, key, seed)[1].hex() == golden["proof"]
 
 
+def test_proof_bytes_match_two_block_golden(ctx):
+    """32-byte message (two ECB blocks sharing one key schedule; |H| = 2^19, |X| = 512 interleaved with period 1024): key bytes, ciphertext
+    and proof bytes equal the oracle prover's, on both round-1 paths"""
+    with open(os.path.join(GOLD, "marlin_proof_32B.json")) as f:
+        g = json.load(f)
+    pk = ctx.synthesize_keys(32, bytes.fromhex(g["tau_seed"]), bytes.fromhex(g["gamma_seed"]))
+    try:
+        assert (pk.info["h"], pk.info["k"], pk.info["x"], pk.info["max_degree"]) == (g["h"], g["k"], g["x"], g["max_degree"])
+        assert hashlib.sha256(pk.vk_bytes()).hexdigest() == g["vk_sha256"]
+        assert pk.verifying_key().hex() == g["verifying_key"]
+        msg, key, seed = (bytes.fromhex(g[k]) for k in ("message", "key", "zk_seed"))
+        for lagrange in (1, 0):
+            ctx.set_tuning("r1_lagrange", lagrange)
+            ct, proof = ctx.encrypt(pk, msg, key, seed)
+            assert ct.hex() == g["ciphertext"]
+            assert proof.hex() == g["proof"], f"r1_lagrange={lagrange}"
+    finally:
+        ctx.set_tuning("r1_lagrange", 1)
+        pk.close()
+
+
 def test_proof_bytes_match_second_golden(ctx, pk16):
     """another message, key and zk seed (FIPS-197 Appendix C.1) under the same proving key: byte-identical to the oracle prover again"""
     with open(os.path.join(GOLD, "marlin_proof_16B_fips_c1.json")) as f:

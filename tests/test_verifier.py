@@ -187,7 +187,23 @@ def test_second_golden_proof_and_cross_statements(golden):
     assert zk.verify_encryption(vk, p1, c2) is False
 
 
-@pytest.mark.parametrize("name", ["marlin_proof_16B.json", "marlin_proof_16B_fips_c1.json"])
+def test_two_block_golden_proof(golden):
+    """32-byte message (two ECB blocks; |H| = 2^19, |X| = 512): the product's host verifier accepts the oracle prover's proof under the oracle's
+    key bytes, rejects a flipped ciphertext bit and a truncated statement, and a one-block key does not verify it"""
+    with open(os.path.join(os.path.dirname(GOLD), "marlin_proof_32B.json")) as f:
+        g = json.load(f)
+    vk, proof, ct = bytes.fromhex(g["verifying_key"]), bytes.fromhex(g["proof"]), bytes.fromhex(g["ciphertext"])
+    assert (g["h"], g["k"], g["x"]) == (1 << 19, 1 << 20, 512) and len(ct) == 32
+    assert ct[:16].hex() == golden["ciphertext"]  # ECB: the first block is the one-block fixture's
+    assert zk.verify_encryption(vk, proof, ct) is True
+    bad = bytearray(ct)
+    bad[17] ^= 0x20
+    assert zk.verify_encryption(vk, proof, bytes(bad)) is False
+    assert zk.verify_encryption(vk, proof, ct[:16]) is False
+    assert zk.verify_encryption(bytes.fromhex(golden["verifying_key"]), proof, ct[:16]) is False
+
+
+@pytest.mark.parametrize("name", ["marlin_proof_16B.json", "marlin_proof_16B_fips_c1.json", "marlin_proof_32B.json"])
 def test_proof_wire_format_round_trip(name):
     """deserialize_proof / serialize_proof (src/lib.rs:52): fields equal the oracle's reading of the same bytes, and packing
     them again reproduces the bytes"""

@@ -22,6 +22,9 @@ TAU_SEED, GAMMA_SEED, ZK_SEED = bytes(range(32)), bytes(range(1, 33)), bytes([7]
 VARIANTS = {
     "marlin_proof_16B.json": (MSG, KEY, ZK_SEED),
     "marlin_proof_16B_fips_c1.json": (bytes.fromhex("00112233445566778899aabbccddeeff"), bytes(range(16)), bytes([0xA5] * 32)),
+    # third fixture: TWO ECB blocks (|H| = 2^19, |K| = 2^20, |X| = 512): the key schedule is shared, the X-subdomain interleaving and the
+    # padding of the instance differ from the one-block case
+    "marlin_proof_32B.json": (MSG + bytes.fromhex("00112233445566778899aabbccddeeff"), KEY, bytes([0x3C] * 32)),
 }
 
 
